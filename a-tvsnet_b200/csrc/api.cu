@@ -1,0 +1,16 @@
+// api.cu - version / error string / device query of the C ABI (include/atvs.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void atvs_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int atvs_version(void) { return 100; }
+extern "C" const char* atvs_last_error(void) { return g_err; }
+extern "C" int atvs_device_sm_count(void) { return atvs_num_sms(); }

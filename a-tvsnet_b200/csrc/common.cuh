@@ -1,0 +1,39 @@
+// common.cuh - error plumbing shared by every translation unit of libatvs.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/atvs.h"
+
+void atvs_set_error(const char* fmt, ...);
+
+#define ATVS_CHECK_ARG(cond, code, ...)                   \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            atvs_set_error(__VA_ARGS__);                  \
+            return (code);                                \
+        }                                                 \
+    } while (0)
+
+#define ATVS_CUDA(call)                                                               \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            atvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,               \
+                           cudaGetErrorString(e__));                                  \
+            return (int)e__;                                                          \
+        }                                                                             \
+    } while (0)
+
+#define ATVS_LAUNCH_CHECK()  ATVS_CUDA(cudaPeekAtLastError())
+
+static inline int atvs_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}

@@ -1,0 +1,532 @@
+// geom.cu - plane-sweep geometry kernels of libatvs.so (compiled with --fmad=false).
+//
+//   atvs_get_homographies            <- homography_warping.py:179-227
+//   atvs_homography_warping          <- homography_warping.py:230-271 + interpolate :31-104
+//   atvs_homography_warping_by_depth <- homography_warping.py:108-176
+//   atvs_build_cost_volume           <- model.py:157-200 (and the L1 variant :272-280)
+//   atvs_prob2depth                  <- model.py:80-129, 13-76
+//
+// The coordinate arithmetic uses explicit round-to-nearest intrinsics in the order the CPU
+// oracle documents (oracle/homography_warping.py), so homographies, sample coordinates,
+// floor() cells and validity masks are bit-identical to the oracle; only the last blend may
+// differ by rounding of the products (it does not: same order, no FMA).
+#include "common.cuh"
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
+namespace {
+
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return ADD(ADD(MUL(a0, b0), MUL(a1, b1)), MUL(a2, b2));
+}
+
+struct M3 {
+    float m[3][3];
+};
+
+__device__ __forceinline__ M3 mm3(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i][j] = dot3(a.m[i][0], b.m[0][j], a.m[i][1], b.m[1][j], a.m[i][2], b.m[2][j]);
+    return r;
+}
+
+__device__ __forceinline__ M3 inv3(const M3& k) {
+    const float a = k.m[0][0], b = k.m[0][1], c = k.m[0][2];
+    const float d = k.m[1][0], e = k.m[1][1], f = k.m[1][2];
+    const float g = k.m[2][0], h = k.m[2][1], i = k.m[2][2];
+    const float c00 = SUB(MUL(e, i), MUL(f, h));
+    const float c01 = SUB(MUL(d, i), MUL(f, g));
+    const float c02 = SUB(MUL(d, h), MUL(e, g));
+    const float det = ADD(SUB(MUL(a, c00), MUL(b, c01)), MUL(c, c02));
+    M3 r;
+    r.m[0][0] = DIV(c00, det);
+    r.m[0][1] = DIV(SUB(MUL(c, h), MUL(b, i)), det);
+    r.m[0][2] = DIV(SUB(MUL(b, f), MUL(c, e)), det);
+    r.m[1][0] = DIV(SUB(MUL(f, g), MUL(d, i)), det);
+    r.m[1][1] = DIV(SUB(MUL(a, i), MUL(c, g)), det);
+    r.m[1][2] = DIV(SUB(MUL(c, d), MUL(a, f)), det);
+    r.m[2][0] = DIV(c02, det);
+    r.m[2][1] = DIV(SUB(MUL(b, g), MUL(a, h)), det);
+    r.m[2][2] = DIV(SUB(MUL(a, e), MUL(b, d)), det);
+    return r;
+}
+
+struct Cam {
+    M3 R, K;
+    float t[3];
+};
+
+__device__ __forceinline__ Cam load_cam(const float* cam) {  // (2,4,4) row-major
+    Cam c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            c.R.m[i][j] = cam[i * 4 + j];
+            c.K.m[i][j] = cam[16 + i * 4 + j];
+        }
+        c.t[i] = cam[i * 4 + 3];
+    }
+    return c;
+}
+
+__device__ __forceinline__ M3 transpose3(const M3& a) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+    return r;
+}
+
+// c = -(R^T t)
+__device__ __forceinline__ void centre(const M3& Rt, const float* t, float* c) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[i] = -dot3(Rt.m[i][0], t[0], Rt.m[i][1], t[1], Rt.m[i][2], t[2]);
+}
+
+__global__ void k_get_homographies(const float* __restrict__ lcam, const float* __restrict__ rcam, int B, int D,
+                                   const float* __restrict__ dstart, const float* __restrict__ dint,
+                                   int inverse_depth, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * D) return;
+    const int b = idx / D, d = idx % D;
+    const Cam L = load_cam(lcam + (size_t)b * 32), R = load_cam(rcam + (size_t)b * 32);
+    const float depth = ADD(dstart[b], MUL((float)d, dint[b]));
+    const M3 Kli = inv3(L.K);
+    const M3 RlT = transpose3(L.R), RrT = transpose3(R.R);
+    float cl[3], cr[3];
+    centre(RlT, L.t, cl);
+    centre(RrT, R.t, cr);
+    M3 m0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float crel = SUB(cr[i], cl[i]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float tv = MUL(crel, L.R.m[2][j]);
+            const float sc = inverse_depth ? MUL(tv, depth) : DIV(tv, depth);
+            m0.m[i][j] = SUB(i == j ? 1.0f : 0.0f, sc);
+        }
+    }
+    const M3 m1 = mm3(RlT, Kli);
+    const M3 m2 = mm3(m0, m1);
+    const M3 Hm = mm3(R.K, mm3(R.R, m2));
+    float* o = out + (size_t)idx * 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = Hm.m[i][j];
+}
+
+// ------------------------------------------------------------------ sampling helpers
+struct Sample {
+    int x0, y0;            // top-left cell (valid only)
+    float wa, wb, wc, wd;  // bilinear areas
+    bool valid;
+    bool finite;
+};
+
+// (u, v) texture coordinates -> bilinear cell, homography_warping.py:37-43,59-95
+__device__ __forceinline__ Sample make_sample(float u, float v, int H, int W) {
+    Sample s;
+    const float x = SUB(u, 0.5f), y = SUB(v, 0.5f);
+    s.valid = (x >= 0.0f) && (y >= 0.0f) && (x < (float)(W - 1)) && (y < (float)(H - 1)) && !isnan(x) && !isnan(y);
+    s.finite = isfinite(x) && isfinite(y);
+    if (s.valid) {
+        const float fx = floorf(x), fy = floorf(y);
+        s.x0 = (int)fx;
+        s.y0 = (int)fy;
+        const float x1 = (float)(s.x0 + 1), y1 = (float)(s.y0 + 1);
+        const float dx1 = SUB(x1, x), dx0 = SUB(x, fx), dy1 = SUB(y1, y), dy0 = SUB(y, fy);
+        s.wa = MUL(dy1, dx1);
+        s.wb = MUL(dy1, dx0);
+        s.wc = MUL(dy0, dx1);
+        s.wd = MUL(dy0, dx0);
+    } else {
+        s.x0 = s.y0 = 0;
+        s.wa = s.wb = s.wc = s.wd = 0.0f;
+    }
+    return s;
+}
+
+__device__ __forceinline__ void homography_uv(const float* __restrict__ h, int x, int y, float& u, float& v) {
+    const float px = ADD((float)x, 0.5f), py = ADD((float)y, 0.5f);
+    const float xa = ADD(ADD(MUL(h[0], px), MUL(h[1], py)), h[2]);
+    const float ya = ADD(ADD(MUL(h[3], px), MUL(h[4], py)), h[5]);
+    float z = ADD(ADD(MUL(h[6], px), MUL(h[7], py)), h[8]);
+    z = ADD(z, (z == 0.0f) ? 1e-7f : 0.0f);
+    u = DIV(xa, z);
+    v = DIV(ya, z);
+}
+
+__device__ __forceinline__ float blend(const Sample& s, float a, float b, float c, float d) {
+    return ADD(ADD(ADD(MUL(s.wa, a), MUL(s.wb, b)), MUL(s.wc, c)), MUL(s.wd, d));
+}
+
+__device__ __forceinline__ float4 sample4(const Sample& s, const float* __restrict__ img, int W, int C, int c0) {
+    // img points at the (H,W,C) image of this batch element
+    if (!s.valid) {
+        const float z = s.finite ? 0.0f : __int_as_float(0x7fc00000);
+        return make_float4(z, z, z, z);
+    }
+    const float* p = img + ((size_t)s.y0 * W + s.x0) * C + c0;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + C));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)W * C));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + (size_t)W * C + C));
+    return make_float4(blend(s, a.x, b.x, c.x, d.x), blend(s, a.y, b.y, c.y, d.y), blend(s, a.z, b.z, c.z, d.z),
+                       blend(s, a.w, b.w, c.w, d.w));
+}
+
+__device__ __forceinline__ float sample1(const Sample& s, const float* __restrict__ img, int W, int C, int c) {
+    if (!s.valid) return s.finite ? 0.0f : __int_as_float(0x7fc00000);
+    const float* p = img + ((size_t)s.y0 * W + s.x0) * C + c;
+    return blend(s, __ldg(p), __ldg(p + C), __ldg(p + (size_t)W * C), __ldg(p + (size_t)W * C + C));
+}
+
+// nearest: homography_warping.py:45-56 (no zeroing: invalid pixels read image[0,0])
+__device__ __forceinline__ void nearest_cell(float u, float v, int H, int W, int& x0, int& y0, bool& valid) {
+    const float x = SUB(u, 0.5f), y = SUB(v, 0.5f);
+    valid = (x >= 0.0f) && (y >= 0.0f) && (x < (float)(W - 1)) && (y < (float)(H - 1)) && !isnan(x) && !isnan(y);
+    x0 = valid ? __float2int_rn(x) : 0;   // round half to even == tf.round
+    y0 = valid ? __float2int_rn(y) : 0;
+}
+
+// ------------------------------------------------------------------ warping kernels
+// one thread = one pixel x VEC channels.  BYDEPTH: per-pixel inverse depth instead of H.
+template <int VEC, bool BYDEPTH>
+__global__ void k_warp(const float* __restrict__ img, const float* __restrict__ hmat, const float* __restrict__ depth,
+                       int inverse_depth, int B, int H, int W, int C, int method, float* __restrict__ out,
+                       uint8_t* __restrict__ mask) {
+    const int G = C / VEC;
+    const long long total = (long long)B * H * W * G;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float u, v;
+    if (BYDEPTH) {
+        // hmat = (B,12): mat (9) then vec (3), prepared by k_bydepth_setup
+        const float* m = hmat + (size_t)b * 12;
+        const float dep = depth[pix];
+        const float px = ADD((float)x, 0.5f), py = ADD((float)y, 0.5f);
+        float q[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float vv = inverse_depth ? MUL(m[9 + r], dep) : DIV(m[9 + r], dep);
+            q[r] = ADD(ADD(ADD(MUL(m[r * 3], px), MUL(m[r * 3 + 1], py)), m[r * 3 + 2]), vv);
+        }
+        u = DIV(q[0], q[2]);
+        v = DIV(q[1], q[2]);
+    } else {
+        homography_uv(hmat + (size_t)b * 9, x, y, u, v);
+    }
+    const float* im = img + (size_t)b * H * W * C;
+    if (method == 1) {
+        int x0, y0;
+        bool valid;
+        nearest_cell(u, v, H, W, x0, y0, valid);
+        const float* p = im + ((size_t)y0 * W + x0) * C + g * VEC;
+        float* o = out + pix * C + g * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = __ldg(p + i);
+        if (mask && g == 0) mask[pix] = valid ? 1 : 0;
+        return;
+    }
+    const Sample s = make_sample(u, v, H, W);
+    if (VEC == 4) {
+        *reinterpret_cast<float4*>(out + pix * C + g * 4) = sample4(s, im, W, C, g * 4);
+    } else {
+        out[pix * C + g] = sample1(s, im, W, C, g);
+    }
+    if (mask && g == 0) mask[pix] = s.valid ? 1 : 0;
+}
+
+// homography_warping.py:115-146: mat = Kr (Rr (Rl^T Kl^-1)), vec = Kr (Rr c_l) + Kr t_r
+__global__ void k_bydepth_setup(const float* __restrict__ lcam, const float* __restrict__ rcam, int B,
+                                float* __restrict__ mv) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Cam L = load_cam(lcam + (size_t)b * 32), R = load_cam(rcam + (size_t)b * 32);
+    const M3 RlT = transpose3(L.R);
+    float cl[3];
+    centre(RlT, L.t, cl);
+    const M3 mat = mm3(R.K, mm3(R.R, mm3(RlT, inv3(L.K))));
+    float rc[3], v1[3], v2[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rc[i] = dot3(R.R.m[i][0], cl[0], R.R.m[i][1], cl[1], R.R.m[i][2], cl[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        v1[i] = dot3(R.K.m[i][0], rc[0], R.K.m[i][1], rc[1], R.K.m[i][2], rc[2]);
+        v2[i] = dot3(R.K.m[i][0], R.t[0], R.K.m[i][1], R.t[1], R.K.m[i][2], R.t[2]);
+    }
+    float* o = mv + (size_t)b * 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = mat.m[i][j];
+        o[9 + i] = ADD(v1[i], v2[i]);
+    }
+}
+
+// ------------------------------------------------------------------ fused cost volume (K1)
+__device__ __forceinline__ void store4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&lo);
+    pk.y = *reinterpret_cast<unsigned*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(p), pk);
+}
+
+constexpr int K1_DCHUNK = 8;
+
+// grid: x = pixel*channel-group tiles, y = depth chunks, z = batch.
+// one thread = one pixel x 4 channels, looping over K1_DCHUNK planes with the reference
+// float4 kept in registers; every plane's slice goes straight to HBM with streaming stores.
+template <typename OutT, int MODE, bool WARP_REF>
+__global__ void __launch_bounds__(256)
+k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ view, const float* __restrict__ hv,
+                    const float* __restrict__ hr, int D, int h, int w, int F, OutT* __restrict__ out) {
+    const int G = F >> 2;
+    const int hw = h * w;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hw * G) return;
+    const int g = idx % G, pix = idx / G;
+    const int x = pix % w, y = pix / w;
+    const int b = blockIdx.z;
+    const float* refb = ref + (size_t)b * hw * F;
+    const float* viewb = view + (size_t)b * hw * F;
+    const int CO = (MODE == 0) ? 2 * F : F;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!WARP_REF && MODE != 1) r = __ldg(reinterpret_cast<const float4*>(refb + (size_t)pix * F + g * 4));
+    const int d0 = blockIdx.y * K1_DCHUNK;
+    const int d1 = min(D, d0 + K1_DCHUNK);
+    for (int d = d0; d < d1; ++d) {
+        const float* H = hv + ((size_t)b * D + d) * 9;
+        float u, v;
+        homography_uv(H, x, y, u, v);
+        const Sample s = make_sample(u, v, h, w);
+        float4 wv = sample4(s, viewb, w, F, g * 4);
+        if (WARP_REF && MODE != 1) {
+            float ur, vr;
+            homography_uv(hr + ((size_t)b * D + d) * 9, x, y, ur, vr);
+            const Sample sr = make_sample(ur, vr, h, w);
+            r = sample4(sr, refb, w, F, g * 4);
+        }
+        OutT* o = out + (((size_t)b * D + d) * hw + pix) * CO;
+        if (MODE == 0) {
+            store4(o + g * 4, r);
+            store4(o + F + g * 4, wv);
+        } else if (MODE == 1) {
+            store4(o + g * 4, wv);
+        } else {
+            const float m = s.valid ? 1.0f : 0.0f;   // model.py:277-278
+            wv.x = MUL(fabsf(SUB(wv.x, r.x)), m);
+            wv.y = MUL(fabsf(SUB(wv.y, r.y)), m);
+            wv.z = MUL(fabsf(SUB(wv.z, r.z)), m);
+            wv.w = MUL(fabsf(SUB(wv.w, r.w)), m);
+            store4(o + g * 4, wv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ soft-argmin (K4)
+// one thread = one output pixel; single pass over D with an online softmax; the x4 variant
+// interpolates the logits on the fly (tf.image.resize_images, align_corners=True).
+template <int UP>
+__global__ void __launch_bounds__(256)
+k_prob2depth(const float* __restrict__ vol, int B, int D, int H, int W, const float* __restrict__ dstart,
+             const float* __restrict__ dint, float* __restrict__ depth, float* __restrict__ prob) {
+    const int Ho = H * UP, Wo = W * UP;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * Ho * Wo) return;
+    const int X = (int)(idx % Wo), Y = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+    const size_t plane = (size_t)H * W;
+    const float* vb = vol + (size_t)b * D * plane;
+    int x0 = X, x1 = X, y0 = Y, y1 = Y;
+    float fx = 0.f, fy = 0.f;
+    if (UP > 1) {
+        const float sy = DIV((float)(H - 1), (float)(Ho - 1)), sx = DIV((float)(W - 1), (float)(Wo - 1));
+        const float srcy = MUL((float)Y, sy), srcx = MUL((float)X, sx);
+        y0 = (int)floorf(srcy);
+        x0 = (int)floorf(srcx);
+        y1 = min(y0 + 1, H - 1);
+        x1 = min(x0 + 1, W - 1);
+        fy = SUB(srcy, (float)y0);
+        fx = SUB(srcx, (float)x0);
+    }
+    const size_t o00 = (size_t)y0 * W + x0, o01 = (size_t)y0 * W + x1, o10 = (size_t)y1 * W + x0,
+                 o11 = (size_t)y1 * W + x1;
+    auto logit = [&](int d) -> float {
+        const float* p = vb + (size_t)d * plane;
+        if (UP == 1) return __ldg(p + o00);
+        const float tl = __ldg(p + o00), tr = __ldg(p + o01), bl = __ldg(p + o10), br = __ldg(p + o11);
+        const float top = ADD(tl, MUL(SUB(tr, tl), fx));
+        const float bot = ADD(bl, MUL(SUB(br, bl), fx));
+        return ADD(top, MUL(SUB(bot, top), fy));
+    };
+    const float ds = dstart[b], di = dint[b];
+    const float de = ADD(ds, MUL(SUB((float)D, 1.0f), di));
+    const float step = DIV(SUB(de, ds), (float)max(D - 1, 1));
+    float m = -INFINITY, s = 0.f, ws = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float t = -logit(d);
+        if (t > m) {
+            const float sc = expf(m - t);
+            s *= sc;
+            ws *= sc;
+            m = t;
+        }
+        const float e = expf(t - m);
+        s += e;
+        ws += ADD(ds, MUL((float)d, step)) * e;
+    }
+    const float est = ws / s;
+    depth[idx] = est;
+    if (prob) {
+        const float t = DIV(SUB(est, ds), di);
+        const int l0 = min(max((int)floorf(t), 0), D - 1);
+        const int l1 = min(max(l0 - 1, 0), D - 1);
+        const int r0 = min(max((int)ceilf(t), 0), D - 1);
+        const int r1 = min(max(r0 + 1, 0), D - 1);
+        const float inv = 1.0f / s;
+        float p = expf(-logit(l0) - m) * inv;
+        p += expf(-logit(l1) - m) * inv;
+        p += expf(-logit(r0) - m) * inv;
+        p += expf(-logit(r1) - m) * inv;
+        prob[idx] = p;
+    }
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" int atvs_get_homographies(const float* left_cam, const float* right_cam, int B, int D,
+                                     const float* depth_start, const float* depth_interval, int inverse_depth,
+                                     float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(left_cam && right_cam && depth_start && depth_interval && out, ATVS_E_NULL,
+                   "atvs_get_homographies: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0, ATVS_E_SHAPE, "atvs_get_homographies: B=%d D=%d", B, D);
+    const int n = B * D;
+    k_get_homographies<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(left_cam, right_cam, B, D, depth_start,
+                                                                         depth_interval, inverse_depth, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_warp(const float* image, const float* hm, const float* depth, int inverse_depth, bool bydepth,
+                       int B, int H, int W, int C, int method, float* out, uint8_t* mask, cudaStream_t st) {
+    const int vec = (C % 4 == 0) ? 4 : 1;
+    const long long total = (long long)B * H * W * (C / vec);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (vec == 4) {
+        if (bydepth) k_warp<4, true><<<grid, 256, 0, st>>>(image, hm, depth, inverse_depth, B, H, W, C, method, out, mask);
+        else k_warp<4, false><<<grid, 256, 0, st>>>(image, hm, depth, inverse_depth, B, H, W, C, method, out, mask);
+    } else {
+        if (bydepth) k_warp<1, true><<<grid, 256, 0, st>>>(image, hm, depth, inverse_depth, B, H, W, C, method, out, mask);
+        else k_warp<1, false><<<grid, 256, 0, st>>>(image, hm, depth, inverse_depth, B, H, W, C, method, out, mask);
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_homography_warping(const float* image, const float* homography, int B, int H, int W, int C,
+                                       int method, float* out, uint8_t* mask, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(image && homography && out, ATVS_E_NULL, "atvs_homography_warping: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && H > 1 && W > 1 && C > 0, ATVS_E_SHAPE, "atvs_homography_warping: bad shape %d %d %d %d", B,
+                   H, W, C);
+    ATVS_CHECK_ARG(method == 0 || method == 1, ATVS_E_UNSUP, "atvs_homography_warping: method %d", method);
+    ATVS_CHECK_ARG(C % 4 != 0 || (((uintptr_t)image | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_homography_warping: image/out must be 16-byte aligned");
+    return launch_warp(image, homography, nullptr, 0, false, B, H, W, C, method, out, mask, (cudaStream_t)stream);
+}
+
+extern "C" int atvs_homography_warping_by_depth(const float* image, const float* left_cam, const float* right_cam,
+                                                const float* depth_image, int B, int H, int W, int C, int method,
+                                                int inverse_depth, float* out, uint8_t* mask, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(image && left_cam && right_cam && depth_image && out, ATVS_E_NULL,
+                   "atvs_homography_warping_by_depth: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && B <= 1024 && H > 1 && W > 1 && C > 0, ATVS_E_SHAPE,
+                   "atvs_homography_warping_by_depth: bad shape");
+    ATVS_CHECK_ARG(method == 0 || method == 1, ATVS_E_UNSUP, "atvs_homography_warping_by_depth: method %d", method);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* mv = nullptr;
+    ATVS_CUDA(cudaMallocAsync(&mv, sizeof(float) * 12 * B, st));
+    k_bydepth_setup<<<(B + 63) / 64, 64, 0, st>>>(left_cam, right_cam, B, mv);
+    int rc = launch_warp(image, mv, depth_image, inverse_depth, true, B, H, W, C, method, out, mask, st);
+    ATVS_CUDA(cudaFreeAsync(mv, st));
+    return rc;
+}
+
+template <typename OutT>
+static int launch_k1(const float* ref, const float* view, const float* hv, const float* hr, int B, int D, int h, int w,
+                     int F, int mode, OutT* out, cudaStream_t st) {
+    const int G = F / 4;
+    dim3 grid((unsigned)(((long long)h * w * G + 255) / 256), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
+#define K1_GO(MODE, WR) k_build_cost_volume<OutT, MODE, WR><<<grid, 256, 0, st>>>(ref, view, hv, hr, D, h, w, F, out)
+    if (hr) {
+        if (mode == 0) K1_GO(0, true);
+        else if (mode == 2) K1_GO(2, true);
+        else K1_GO(1, false);
+    } else {
+        if (mode == 0) K1_GO(0, false);
+        else if (mode == 1) K1_GO(1, false);
+        else K1_GO(2, false);
+    }
+#undef K1_GO
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* view_feature, const float* homographies,
+                                      const float* ref_homographies, int B, int D, int h, int w, int F, int mode,
+                                      int out_dtype, void* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(view_feature && homographies && out && (mode == 1 || ref_feature), ATVS_E_NULL,
+                   "atvs_build_cost_volume: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && B < 65536 && D > 0 && h > 1 && w > 1 && F > 0, ATVS_E_SHAPE,
+                   "atvs_build_cost_volume: bad shape B=%d D=%d h=%d w=%d F=%d", B, D, h, w, F);
+    ATVS_CHECK_ARG(mode >= 0 && mode <= 2, ATVS_E_UNSUP, "atvs_build_cost_volume: mode %d", mode);
+    ATVS_CHECK_ARG(F % 4 == 0 && (out_dtype != ATVS_BF16 || F % 8 == 0), ATVS_E_SHAPE,
+                   "atvs_build_cost_volume: F=%d must be a multiple of 4 (8 for bf16)", F);
+    ATVS_CHECK_ARG((((uintptr_t)ref_feature | (uintptr_t)view_feature | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_build_cost_volume: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == ATVS_F32)
+        return launch_k1<float>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
+                                (float*)out, st);
+    if (out_dtype == ATVS_BF16)
+        return launch_k1<__nv_bfloat16>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
+                                        (__nv_bfloat16*)out, st);
+    atvs_set_error("atvs_build_cost_volume: out_dtype %d", out_dtype);
+    return ATVS_E_DTYPE;
+}
+
+extern "C" int atvs_prob2depth(const float* prob_volume, int B, int D, int H, int W, const float* depth_start,
+                               const float* depth_interval, int up, float* depth, float* prob_map,
+                               atvs_stream_t stream) {
+    ATVS_CHECK_ARG(prob_volume && depth_start && depth_interval && depth, ATVS_E_NULL, "atvs_prob2depth: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_prob2depth: bad shape");
+    ATVS_CHECK_ARG(up == 1 || up == 4, ATVS_E_UNSUP, "atvs_prob2depth: up=%d (1 or 4)", up);
+    ATVS_CHECK_ARG(up == 1 || (H > 1 && W > 1), ATVS_E_SHAPE, "atvs_prob2depth: up=4 needs H,W > 1");
+    const long long total = (long long)B * H * up * W * up;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (up == 1)
+        k_prob2depth<1><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
+    else
+        k_prob2depth<4><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,433 @@
+// net_fp32.cu - CUDA-core fp32 layer primitives of libatvs.so (the fp32 parity path) plus the
+// dtype-generic elementwise / batch-norm / attention kernels shared with the bf16 path.
+//
+//   atvs_conv3d_fp32        <- network.py:142-215 (conv / conv_bn), :511-550 (deconv_bn)
+//   atvs_bn_relu_add        <- network.py:206-215, 541-550 (BN with batch statistics, F4) + add :696
+//   atvs_attention_*        <- network.py:282-351 (attention_activation), :379-408 (aggregation)
+#include "common.cuh"
+#include "conv_geom.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ direct conv, fp32
+// one thread = one output voxel x all COUT channels; per-tap weights staged in shared memory;
+// grid-stride over 128-voxel tiles so the BN moments are reduced once per CTA.
+template <int COUT>
+__global__ void __launch_bounds__(128)
+k_conv3d_fp32(const float* __restrict__ x, const float* __restrict__ wgt, ConvGeom g, int transposed_w,
+              float* __restrict__ out, double* __restrict__ stats, long long njobs) {
+    extern __shared__ float ws[];             // [Cin][COUT]
+    __shared__ double sstat[2 * COUT];
+    const int tid = threadIdx.x;
+    const int Cin = g.Cin;
+    for (int i = tid; i < 2 * COUT; i += 128) sstat[i] = 0.0;
+    const long long ntiles = (njobs + 127) / 128;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long j = tile * 128 + tid;
+        const bool active = j < njobs;
+        long long r = active ? j : 0;
+        const int jx = (int)(r % g.Wj); r /= g.Wj;
+        const int jy = (int)(r % g.Hj); r /= g.Hj;
+        const int jz = (int)(r % g.Dj);
+        const int b = (int)(r / g.Dj);
+        float acc[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+        for (int tz = 0; tz < g.nt[0]; ++tz)
+            for (int ty = 0; ty < g.nt[1]; ++ty)
+                for (int tx = 0; tx < g.nt[2]; ++tx) {
+                    const int k = (g.kidx[0][tz] * 3 + g.kidx[1][ty]) * 3 + g.kidx[2][tx];
+                    __syncthreads();
+                    for (int i = tid; i < Cin * COUT; i += 128) {
+                        const int ci = i / COUT, co = i % COUT;
+                        ws[i] = transposed_w ? __ldg(wgt + ((size_t)k * COUT + co) * Cin + ci)
+                                             : __ldg(wgt + ((size_t)k * Cin + ci) * COUT + co);
+                    }
+                    __syncthreads();
+                    const int iz = jz * g.s_in + g.koff[0][tz];
+                    const int iy = jy * g.s_in + g.koff[1][ty];
+                    const int ix = jx * g.s_in + g.koff[2][tx];
+                    const bool ok = active && iz >= 0 && iz < g.Din && iy >= 0 && iy < g.Hin && ix >= 0 && ix < g.Win;
+                    if (!ok) continue;
+                    const float* xp = x + ((((size_t)b * g.Din + iz) * g.Hin + iy) * g.Win + ix) * Cin;
+                    if ((Cin & 3) == 0) {
+                        for (int c4 = 0; c4 < Cin; c4 += 4) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c4));
+                            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float* wr = ws + (c4 + q) * COUT;
+#pragma unroll
+                                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xs[q], wr[c], acc[c]);
+                            }
+                        }
+                    } else {
+                        for (int ci = 0; ci < Cin; ++ci) {
+                            const float xv = __ldg(xp + ci);
+                            const float* wr = ws + ci * COUT;
+#pragma unroll
+                            for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, wr[c], acc[c]);
+                        }
+                    }
+                }
+        if (active) {
+            const int oz = jz * g.os + g.p[0], oy = jy * g.os + g.p[1], ox = jx * g.os + g.p[2];
+            float* op = out + ((((size_t)b * g.Do + oz) * g.Ho + oy) * g.Wo + ox) * COUT;
+            if (COUT % 4 == 0) {
+#pragma unroll
+                for (int c = 0; c < COUT; c += 4)
+                    *reinterpret_cast<float4*>(op + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) op[c] = acc[c];
+            }
+        }
+        if (stats) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                float s = active ? acc[c] : 0.f;
+                float q = s * s;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                    q += __shfl_xor_sync(0xffffffffu, q, o);
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&sstat[c], (double)s);
+                    atomicAdd(&sstat[COUT + c], (double)q);
+                }
+            }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        for (int i = tid; i < 2 * COUT; i += 128) atomicAdd(&stats[i], sstat[i]);
+    }
+}
+
+// ------------------------------------------------------------------ BN + ReLU + adds
+template <typename T>
+struct Vec4 {};
+template <>
+struct Vec4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+    static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+    static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned*>(&lo);
+        u.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+    static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+constexpr int BN_MAXC = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, long long count, int C, float eps,
+              int relu, const T* __restrict__ s1, const T* __restrict__ s2, T* __restrict__ out_plain,
+              T* __restrict__ out_sum) {
+    __shared__ float sh_inv[BN_MAXC], sh_off[BN_MAXC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float inv = 1.f, off = 0.f;
+        if (stats) {
+            const double mean = stats[c] / (double)count;
+            double var = stats[C + c] / (double)count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            inv = (float)(1.0 / sqrt(var + (double)eps));
+            off = (float)mean * inv;
+        }
+        sh_inv[c] = inv;
+        sh_off[c] = off;
+    }
+    __syncthreads();
+    const long long n = count * C;
+    if ((C & 3) == 0) {
+        const long long n4 = n >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)((i << 2) % C);
+            const float4 r = __ldcs(reinterpret_cast<const float4*>(raw) + i);
+            float4 y;
+            y.x = r.x * sh_inv[c] - sh_off[c];
+            y.y = r.y * sh_inv[c + 1] - sh_off[c + 1];
+            y.z = r.z * sh_inv[c + 2] - sh_off[c + 2];
+            y.w = r.w * sh_inv[c + 3] - sh_off[c + 3];
+            if (relu) {
+                y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+            }
+            if (out_plain) Vec4<T>::st(out_plain + (i << 2), y);
+            if (out_sum) {
+                if (s1) { const float4 a = Vec4<T>::ld(s1 + (i << 2)); y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w; }
+                if (s2) { const float4 a = Vec4<T>::ld(s2 + (i << 2)); y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w; }
+                Vec4<T>::st(out_sum + (i << 2), y);
+            }
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)(i % C);
+            float y = raw[i] * sh_inv[c] - sh_off[c];
+            if (relu) y = fmaxf(y, 0.f);
+            if (out_plain) Vec4<T>::st1(out_plain + i, y);
+            if (out_sum) {
+                if (s1) y += Vec4<T>::ld1(s1 + i);
+                if (s2) y += Vec4<T>::ld1(s2 + i);
+                Vec4<T>::st1(out_sum + i, y);
+            }
+        }
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void k_cast(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        Vec4<TD>::st1(d + i, Vec4<TS>::ld1(s + i));
+}
+
+template <typename T>
+__global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        Vec4<T>::st1(o + i, Vec4<T>::ld1(a + i) + Vec4<T>::ld1(b + i));
+}
+
+// ------------------------------------------------------------------ attention (AAM)
+constexpr int ATT_MAXN = 8;
+
+// MODE 0: full softmax-weighted sum (single GPU, reference order incl. the +S term)
+// MODE 1: local max of l_n = u_n - s_n
+// MODE 2: partial numerator || denominator against a given max
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_attention(const T* __restrict__ act, const T* __restrict__ x, int N, long long V, int C, const float* __restrict__ gmax,
+            float* __restrict__ out) {
+    const int G = C >> 2;
+    const long long total = V * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long v = idx / G;
+        const int c0 = (int)(idx % G) << 2;
+        float4 u[ATT_MAXN], s[ATT_MAXN];
+#pragma unroll
+        for (int n = 0; n < ATT_MAXN; ++n) {
+            if (n < N) {
+                const T* a = act + ((size_t)n * V + v) * (2 * C);
+                u[n] = Vec4<T>::ld(a + c0);
+                s[n] = Vec4<T>::ld(a + C + c0);
+            }
+        }
+        float res[4], den[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float S = 0.f;
+            if (MODE == 0) {
+#pragma unroll
+                for (int n = 0; n < ATT_MAXN; ++n)
+                    if (n < N) S = (n == 0) ? (&s[n].x)[q] : S + (&s[n].x)[q];
+            }
+            float a[ATT_MAXN];
+            float m = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < ATT_MAXN; ++n)
+                if (n < N) {
+                    a[n] = ((&u[n].x)[q] - (&s[n].x)[q]) + S;
+                    m = fmaxf(m, a[n]);
+                }
+            if (MODE == 1) { res[q] = m; continue; }
+            if (MODE == 2) m = gmax[v * C + c0 + q];
+            float dsum = 0.f;
+#pragma unroll
+            for (int n = 0; n < ATT_MAXN; ++n)
+                if (n < N) {
+                    a[n] = expf(a[n] - m);
+                    dsum += a[n];
+                }
+            float r = 0.f;
+#pragma unroll
+            for (int n = 0; n < ATT_MAXN; ++n)
+                if (n < N) {
+                    const float xv = Vec4<T>::ld1(x + ((size_t)n * V + v) * C + c0 + q);
+                    r += (MODE == 0 ? a[n] / dsum : a[n]) * xv;
+                }
+            res[q] = r;
+            den[q] = dsum;
+        }
+        if (MODE == 2) {
+            *reinterpret_cast<float4*>(out + v * (2 * C) + c0) = make_float4(res[0], res[1], res[2], res[3]);
+            *reinterpret_cast<float4*>(out + v * (2 * C) + C + c0) = make_float4(den[0], den[1], den[2], den[3]);
+        } else {
+            *reinterpret_cast<float4*>(out + v * C + c0) = make_float4(res[0], res[1], res[2], res[3]);
+        }
+    }
+}
+
+__global__ void k_attention_finish(const float* __restrict__ nd, long long V, int C, float* __restrict__ out) {
+    const long long total = V * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long v = i / C;
+        const int c = (int)(i % C);
+        out[i] = nd[v * 2 * C + c] / nd[v * 2 * C + C + c];
+    }
+}
+
+inline unsigned grid_for(long long n, int block, int per_sm) {
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)atvs_num_sms() * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int D, int H, int W, int Cin, int Cout,
+                                int stride, int transposed, float* raw_out, double* stats, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && kernel && raw_out, ATVS_E_NULL, "atvs_conv3d_fp32: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 256, ATVS_E_SHAPE,
+                   "atvs_conv3d_fp32: bad shape");
+    ATVS_CHECK_ARG(transposed ? stride == 2 : (stride == 1 || stride == 2), ATVS_E_UNSUP,
+                   "atvs_conv3d_fp32: stride=%d transposed=%d", stride, transposed);
+    ATVS_CHECK_ARG(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64, ATVS_E_UNSUP,
+                   "atvs_conv3d_fp32: Cout=%d (1, 8, 16, 32 or 64)", Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncls = transposed ? 8 : 1;
+    for (int cls = 0; cls < ncls; ++cls) {
+        const ConvGeom g = make_conv_geom(B, D, H, W, Cin, Cout, stride, transposed, cls);
+        const long long njobs = (long long)B * g.Dj * g.Hj * g.Wj;
+        const unsigned grid = grid_for(njobs, 128, 8);
+        const size_t smem = sizeof(float) * (size_t)Cin * Cout;
+#define CONV_GO(CO)                                                                                              \
+    k_conv3d_fp32<CO><<<grid, 128, smem, st>>>(x, kernel, g, transposed, raw_out, stats, njobs)
+        switch (Cout) {
+            case 1: CONV_GO(1); break;
+            case 8: CONV_GO(8); break;
+            case 16: CONV_GO(16); break;
+            case 32: CONV_GO(32); break;
+            default: CONV_GO(64); break;
+        }
+#undef CONV_GO
+        ATVS_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps, int relu,
+                                const void* skip1, const void* skip2, void* out_plain, void* out_sum, int act_dtype,
+                                atvs_stream_t stream) {
+    ATVS_CHECK_ARG(raw && (out_plain || out_sum), ATVS_E_NULL, "atvs_bn_relu_add: NULL pointer");
+    ATVS_CHECK_ARG(count > 0 && C > 0 && C <= BN_MAXC, ATVS_E_SHAPE, "atvs_bn_relu_add: count=%lld C=%d", count, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = grid_for(count * C / 4 + 1, 256, 8);
+    if (act_dtype == ATVS_F32)
+        k_bn_relu_add<float><<<grid, 256, 0, st>>>(raw, stats, count, C, eps, relu, (const float*)skip1,
+                                                   (const float*)skip2, (float*)out_plain, (float*)out_sum);
+    else if (act_dtype == ATVS_BF16)
+        k_bn_relu_add<__nv_bfloat16><<<grid, 256, 0, st>>>(raw, stats, count, C, eps, relu,
+                                                           (const __nv_bfloat16*)skip1, (const __nv_bfloat16*)skip2,
+                                                           (__nv_bfloat16*)out_plain, (__nv_bfloat16*)out_sum);
+    else {
+        atvs_set_error("atvs_bn_relu_add: act_dtype %d", act_dtype);
+        return ATVS_E_DTYPE;
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(src && dst, ATVS_E_NULL, "atvs_cast: NULL pointer");
+    ATVS_CHECK_ARG(n >= 0, ATVS_E_SHAPE, "atvs_cast: n=%lld", n);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = grid_for(n, 256, 8);
+    if (src_dtype == ATVS_F32 && dst_dtype == ATVS_BF16)
+        k_cast<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    else if (src_dtype == ATVS_BF16 && dst_dtype == ATVS_F32)
+        k_cast<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    else if (src_dtype == ATVS_F32 && dst_dtype == ATVS_F32)
+        k_cast<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    else if (src_dtype == ATVS_BF16 && dst_dtype == ATVS_BF16)
+        k_cast<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    else {
+        atvs_set_error("atvs_cast: dtype %d -> %d", src_dtype, dst_dtype);
+        return ATVS_E_DTYPE;
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_add(const void* a, const void* b, void* out, int dtype, long long n, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(a && b && out, ATVS_E_NULL, "atvs_add: NULL pointer");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = grid_for(n, 256, 8);
+    if (dtype == ATVS_F32) k_add<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n);
+    else if (dtype == ATVS_BF16)
+        k_add<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+    else {
+        atvs_set_error("atvs_add: dtype %d", dtype);
+        return ATVS_E_DTYPE;
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE>
+static int launch_att(const void* act, const void* x, int N, long long V, int C, int dtype, const float* gmax,
+                      float* out, cudaStream_t st, const char* who) {
+    ATVS_CHECK_ARG(act && out && (MODE == 1 || x), ATVS_E_NULL, "%s: NULL pointer", who);
+    ATVS_CHECK_ARG(N > 0 && N <= ATT_MAXN && V > 0 && C > 0 && C % 4 == 0, ATVS_E_SHAPE, "%s: N=%d V=%lld C=%d", who, N,
+                   V, C);
+    const unsigned grid = grid_for(V * (C / 4), 256, 8);
+    if (dtype == ATVS_F32)
+        k_attention<float, MODE><<<grid, 256, 0, st>>>((const float*)act, (const float*)x, N, V, C, gmax, out);
+    else if (dtype == ATVS_BF16)
+        k_attention<__nv_bfloat16, MODE><<<grid, 256, 0, st>>>((const __nv_bfloat16*)act, (const __nv_bfloat16*)x, N, V,
+                                                               C, gmax, out);
+    else {
+        atvs_set_error("%s: dtype %d", who, dtype);
+        return ATVS_E_DTYPE;
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_attention_combine(const void* act, const void* x, int N, long long V, int C, int dtype, float* out,
+                                      atvs_stream_t stream) {
+    return launch_att<0>(act, x, N, V, C, dtype, nullptr, out, (cudaStream_t)stream, "atvs_attention_combine");
+}
+
+extern "C" int atvs_attention_local_max(const void* act, int N, long long V, int C, int dtype, float* lmax,
+                                        atvs_stream_t stream) {
+    return launch_att<1>(act, nullptr, N, V, C, dtype, nullptr, lmax, (cudaStream_t)stream, "atvs_attention_local_max");
+}
+
+extern "C" int atvs_attention_partial(const void* act, const void* x, int N, long long V, int C, int dtype,
+                                      const float* gmax, float* num_den, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(gmax, ATVS_E_NULL, "atvs_attention_partial: gmax is NULL");
+    return launch_att<2>(act, x, N, V, C, dtype, gmax, num_den, (cudaStream_t)stream, "atvs_attention_partial");
+}
+
+extern "C" int atvs_attention_finish(const float* num_den, long long V, int C, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(num_den && out, ATVS_E_NULL, "atvs_attention_finish: NULL pointer");
+    ATVS_CHECK_ARG(V > 0 && C > 0, ATVS_E_SHAPE, "atvs_attention_finish: V=%lld C=%d", V, C);
+    k_attention_finish<<<grid_for(V * C, 256, 8), 256, 0, (cudaStream_t)stream>>>(num_den, V, C, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}

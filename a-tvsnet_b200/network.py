@@ -1,0 +1,309 @@
+"""Layer DSL of /root/reference/cnn_wrapper/network.py (Network :37-119 and the hot-path
+layers conv :142, conv_bn :173, attention_aggregation :379, deconv_bn :511, add :696) on
+torch CUDA tensors, executing hand-written sm_100a kernels through libatvs.so.
+
+Differences that are deliberate and invisible at the call surface:
+  * ``setup()`` records the layer graph; it is executed on the first ``get_output*()`` so
+    that batch-norm (batch statistics, no affine: network.py:206-212 with
+    ``training=True, center=False, scale=False``), ReLU and the ``add`` skip joins run as ONE
+    fused elementwise kernel per conv layer instead of separate graph ops;
+  * activations between layers are bf16 when ``FLAGS.precision == 'bf16'`` (tcgen05 path)
+    and fp32 when ``'fp32'`` (CUDA-core parity path); BN moments always come from the fp32
+    accumulators;
+  * variables are looked up by their TF checkpoint names in ``variables``.
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+from . import variables as V
+from .flags import FLAGS
+
+BN_EPS = 1e-3   # tf.layers.batch_normalization default (network.py:206)
+
+
+def act_dtype():
+    return torch.bfloat16 if FLAGS.precision == 'bf16' else torch.float32
+
+
+def to_act(t):
+    """fp32/bf16 NDHWC tensor -> contiguous tensor in the activation dtype."""
+    L.require_cuda(t)
+    dt = act_dtype()
+    t = t.contiguous()
+    if t.dtype == dt:
+        return t
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.float()
+    out = torch.empty(t.shape, dtype=dt, device=t.device)
+    L.call("atvs_cast", L.ptr(t), L.dtype_code(t), L.ptr(out), L.dtype_code(out), t.numel(), L.stream())
+    return out
+
+
+def _packed_weight(key, w, cin, cout, transposed):
+    cache = V.packed_cache()
+    if key not in cache:
+        nbytes = L.load().atvs_packed_weight_bytes(cin, cout, transposed)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        L.call("atvs_pack_conv_weights_bf16", L.ptr(w), cin, cout, transposed, L.ptr(buf), L.stream())
+        cache[key] = buf
+    return cache[key]
+
+
+def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats):
+    """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)]."""
+    B, D, H, W, cin = x.shape
+    if transposed:
+        od, oh, ow = 2 * D, 2 * H, 2 * W
+    else:
+        od, oh, ow = -(-D // stride), -(-H // stride), -(-W // stride)
+    raw = torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+    if x.dtype == torch.float32:
+        L.call("atvs_conv3d_fp32", L.ptr(x), L.ptr(w), B, D, H, W, cin, cout, stride, int(transposed),
+               L.ptr(raw), L.ptr(stats), L.stream())
+    else:
+        pk = _packed_weight(wkey, w, cin, cout, int(transposed))
+        L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
+               L.ptr(raw), L.ptr(stats), L.stream())
+    return raw, stats
+
+
+def bn_relu_add(raw, stats, relu, skips, want_plain, want_sum, dtype):
+    count = raw.numel() // raw.shape[-1]
+    plain = torch.empty(raw.shape, dtype=dtype, device=raw.device) if want_plain else None
+    summ = torch.empty(raw.shape, dtype=dtype, device=raw.device) if want_sum else None
+    s1 = skips[0] if len(skips) > 0 else None
+    s2 = skips[1] if len(skips) > 1 else None
+    L.call("atvs_bn_relu_add", L.ptr(raw), L.ptr(stats), count, raw.shape[-1], BN_EPS, int(relu), L.ptr(s1),
+           L.ptr(s2), L.ptr(plain), L.ptr(summ), L.F32 if dtype == torch.float32 else L.BF16, L.stream())
+    return plain, summ
+
+
+class _Node(object):
+    __slots__ = ('name', 'kind', 'inputs', 'params', 'value')
+
+    def __init__(self, name, kind, inputs, params, value=None):
+        self.name, self.kind, self.inputs, self.params, self.value = name, kind, inputs, params, value
+
+
+class Network(object):
+    """cnn_wrapper/network.py:37-119.  ``Cls({'data': t}, is_training=True, reuse=...)``."""
+
+    def __init__(self, inputs, is_training=True, dropout_rate=0.9, seed=None, reuse=False, scope_name=None,
+                 outputs=()):
+        self.inputs = inputs
+        self.training = is_training     # accepted; BN always uses batch statistics (F4)
+        self.reuse = reuse              # accepted and ignored
+        self.nodes = OrderedDict()
+        self.terminals = []
+        self._wanted = set(outputs)
+        self._ran = False
+        for k, v in inputs.items():
+            self.nodes[k] = _Node(k, 'input', [], {}, v)
+        self.setup()
+        self._last = self.terminals[-1] if self.terminals else None
+
+    def setup(self):
+        raise NotImplementedError('Must be implemented by the subclass.')
+
+    # -- graph recording ---------------------------------------------------------
+    def feed(self, *args):
+        assert args
+        self.terminals = []
+        for a in args:
+            if a not in self.nodes:
+                raise KeyError('Unknown layer name fed: %s' % a)
+            self.terminals.append(a)
+        return self
+
+    def _add_node(self, name, kind, **params):
+        if not self.terminals:
+            raise RuntimeError('No input variables found for layer %s.' % name)
+        self.nodes[name] = _Node(name, kind, list(self.terminals), params)
+        self.terminals = [name]
+        return self
+
+    def conv(self, kernel_size, filters, strides, name, relu=True, padding='SAME', biased=False, rate=1):
+        self._check(kernel_size, padding, biased, rate)
+        return self._add_node(name, 'conv', filters=filters, stride=strides, relu=relu)
+
+    def conv_bn(self, kernel_size, filters, strides, name, relu=True, center=False, padding='SAME', biased=False,
+                rate=1):
+        self._check(kernel_size, padding, biased, rate)
+        if center:
+            raise NotImplementedError('conv_bn(center=True) is not on the 3-D hot path')
+        return self._add_node(name, 'conv_bn', filters=filters, stride=strides, relu=relu)
+
+    def deconv_bn(self, kernel_size, filters, strides, name, relu=True, center=False, padding='SAME', biased=False):
+        self._check(kernel_size, padding, biased, 1)
+        if strides != 2 or center:
+            raise NotImplementedError('deconv_bn: only stride 2, center=False')
+        return self._add_node(name, 'deconv_bn', filters=filters, stride=strides, relu=relu)
+
+    def add(self, name):
+        return self._add_node(name, 'add')
+
+    def attention_aggregation(self, kernel_size, name, filters=None, second_weight=False, relu=True, padding='SAME',
+                              biased=False, n_view=None):
+        self._check(kernel_size, padding, biased, 1)
+        if not (second_weight and relu) or filters is not None:
+            raise NotImplementedError('attention_aggregation: only second_weight=True, relu=True, filters=None')
+        return self._add_node(name, 'attention_aggregation')
+
+    @staticmethod
+    def _check(kernel_size, padding, biased, rate):
+        if kernel_size != 3 or padding != 'SAME' or biased or rate != 1:
+            raise NotImplementedError('hot-path 3-D layers are kernel 3, SAME, no bias, rate 1')
+
+    def get_shape_by_name(self, layer_name):
+        n = self.nodes[layer_name]
+        if n.value is None:
+            self._run()
+        v = self.nodes[layer_name].value
+        return tuple(v[0].shape) + (len(v),) if isinstance(v, (list, tuple)) else tuple(v.shape)
+
+    # -- outputs -----------------------------------------------------------------
+    def get_output(self):
+        return self.get_output_by_name(self._last)
+
+    def get_output_by_name(self, layer_name):
+        if layer_name not in self.nodes:
+            raise KeyError(layer_name)
+        if not self._ran or self.nodes[layer_name].value is None:
+            self._wanted.add(layer_name)
+            self._wanted.add(self._last)
+            self._run()
+        return self.nodes[layer_name].value
+
+    # -- execution ---------------------------------------------------------------
+    def _run(self):
+        nodes = self.nodes
+        order = list(nodes.keys())
+        pos = {n: i for i, n in enumerate(order)}
+        consumers = {n: [] for n in order}
+        for n in order:
+            for i in nodes[n].inputs:
+                consumers[i].append(n)
+        remaining = {n: len(consumers[n]) for n in order}
+        done = set(n for n in order if nodes[n].kind == 'input')
+        for n in order:
+            if nodes[n].kind != 'input':
+                nodes[n].value = None
+        dt = act_dtype()
+
+        def release(names):
+            for i in names:
+                remaining[i] -= 1
+                if remaining[i] == 0 and i not in self._wanted and nodes[i].kind != 'input':
+                    nodes[i].value = None
+
+        def act_in(name):
+            v = nodes[name].value
+            if nodes[name].kind == 'input':
+                v = to_act(v)
+                nodes[name].value = v      # cast once
+            return v
+
+        for name in order:
+            node = nodes[name]
+            if name in done:
+                continue
+            if node.kind in ('conv_bn', 'deconv_bn'):
+                x = act_in(node.inputs[0])
+                transposed = node.kind == 'deconv_bn'
+                wname = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
+                raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
+                                        node.params['stride'], transposed, True)
+                # fuse a following add(name, older...) into the normalisation pass
+                fused = None
+                for c in consumers[name]:
+                    cn = nodes[c]
+                    if cn.kind == 'add' and cn.inputs[0] == name and len(cn.inputs) <= 3 and \
+                            all(i in done for i in cn.inputs[1:]):
+                        fused = cn
+                        break
+                others = [c for c in consumers[name] if fused is None or c != fused.name]
+                want_plain = bool(others) or name in self._wanted or fused is None
+                skips = [nodes[i].value for i in fused.inputs[1:]] if fused is not None else []
+                plain, summ = bn_relu_add(raw, stats, node.params['relu'], skips, want_plain, fused is not None, dt)
+                node.value = plain
+                done.add(name)
+                release(node.inputs)
+                if fused is not None:
+                    fused.value = summ
+                    done.add(fused.name)
+                    release(fused.inputs)
+            elif node.kind == 'conv':
+                x = act_in(node.inputs[0])
+                wname = name + '/kernel'
+                raw, _ = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'], node.params['stride'],
+                                    False, False)
+                if node.params['relu']:
+                    raw = torch.relu_(raw)
+                node.value = raw               # fp32 (network outputs are fp32 at the API)
+                done.add(name)
+                release(node.inputs)
+            elif node.kind == 'add':
+                vals = [act_in(i) for i in node.inputs]
+                out = torch.empty_like(vals[0])
+                L.call("atvs_add", L.ptr(vals[0]), L.ptr(vals[1]), L.ptr(out), L.dtype_code(out), out.numel(),
+                       L.stream())
+                for v in vals[2:]:
+                    L.call("atvs_add", L.ptr(out), L.ptr(v), L.ptr(out), L.dtype_code(out), out.numel(), L.stream())
+                node.value = out
+                done.add(name)
+                release(node.inputs)
+            elif node.kind == 'attention_aggregation':
+                node.value = attention_aggregation(nodes[node.inputs[0]].value, name)
+                done.add(name)
+                release(node.inputs)
+            else:
+                raise RuntimeError('unknown layer kind %s' % node.kind)
+        self._ran = True
+
+
+def split_views(cost_volumes):
+    """(B,D,H,W,C,N) (reference layout: view innermost, example.py:150) or a list of N
+    (B,D,H,W,C) tensors -> list of N contiguous activation-dtype tensors."""
+    if isinstance(cost_volumes, (list, tuple)):
+        return [to_act(v) for v in cost_volumes]
+    L.require_cuda(cost_volumes)
+    n = cost_volumes.shape[-1]
+    return [to_act(cost_volumes[..., i]) for i in range(n)]
+
+
+def attention_activations(views, scope):
+    """network.py:282-351: per view the pair [relu(conv(x,W_unique)) | relu(conv(x,W_shared))]
+    as one 8->16 convolution.  Returns act (N,V,16) in the activation dtype."""
+    key = scope + '/attention_activation/weight_unique||weight_shared'
+    cache = V.packed_cache()
+    if key not in cache:
+        wu = V.get_variable(scope + '/attention_activation/weight_unique')
+        ws = V.get_variable(scope + '/attention_activation/weight_shared')
+        cache[key] = torch.cat([wu, ws], dim=-1).contiguous()
+    w = cache[key]
+    c2 = w.shape[-1]
+    dt = views[0].dtype
+    nvox = views[0].numel() // views[0].shape[-1]
+    act = torch.empty((len(views), nvox, c2), dtype=dt, device=views[0].device)
+    for n, x in enumerate(views):
+        raw, _ = conv3d_raw(x, key + '/packed', w, c2, 1, False, False)
+        L.call("atvs_bn_relu_add", L.ptr(raw), None, nvox, c2, BN_EPS, 1, None, None, L.ptr(act[n]), None,
+               L.F32 if dt == torch.float32 else L.BF16, L.stream())
+    return act
+
+
+def attention_aggregation(cost_volumes, scope):
+    """network.py:379-408 -> (B,D,H,W,C) fp32."""
+    views = split_views(cost_volumes)
+    shape = views[0].shape
+    c = shape[-1]
+    nvox = views[0].numel() // c
+    act = attention_activations(views, scope)
+    x = torch.stack([v.reshape(nvox, c) for v in views], dim=0) if len(views) > 1 else views[0].reshape(1, nvox, c)
+    out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
+    L.call("atvs_attention_combine", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(out),
+           L.stream())
+    return out.reshape(shape)

@@ -1,0 +1,84 @@
+"""The multi-view schedule of /root/reference/atvsnet/example.py:144-158 (stage I per source
+view, stage II = AAM1 -> output_conv -> prob2depth) run entirely on the device: the
+filtered cost volumes stay in HBM (no np.stack / feed_dict round trips), and source views
+can be sharded over ranks with one max + one sum all-reduce of the attention partials
+(SURVEY.md section 8(e)).  Stages III/IV (refinement) are outside the current scope."""
+import torch
+
+from . import _lib as L
+from . import network as N
+from .atvsnet import OutputConv, StackedUNet_prob
+from .model import _prob2depth, build_cost_volume
+
+
+def stage1_view(features, cams, depth_num, depth_start, depth_interval, view_i, siamese=True):
+    """TVSNet_base_siamese (model.py:398-417) keeping the 8-ch filtered volume in the activation
+    dtype.  Returns (filtered (B,D,h,w,8), prob logits (B,D,h,w) fp32, depth_view | None)."""
+    dt = N.act_dtype()
+    ref, view = features[:, 0], features[:, view_i]
+    cv = build_cost_volume(ref, view, cams, depth_num, depth_start, depth_interval, ref_id=0, view_id=view_i,
+                           out_dtype=dt)
+    tower = StackedUNet_prob({'data': cv}, outputs=('conv_b2_6_1', 'conv_b2_6_2'))
+    prob = tower.get_output().squeeze(-1)
+    filtered = tower.get_output_by_name('conv_b2_6_1')
+    del cv, tower
+    depth_view = None
+    if siamese:
+        cvv = build_cost_volume(view, ref, cams, depth_num, depth_start, depth_interval, ref_id=view_i, view_id=0,
+                                out_dtype=dt)
+        pv = StackedUNet_prob({'data': cvv}, outputs=('conv_b2_6_2',)).get_output().squeeze(-1)
+        depth_view, _ = _prob2depth(pv, depth_start, depth_interval, 1, False)
+    return filtered, prob, depth_view
+
+
+def aggregate(filtered_views, scope='attention_aggregate', group=None):
+    """AAM (network.py:379-408) over this rank's views; with ``group`` the softmax over views
+    is completed across ranks: all-reduce(max) of the local logit max, then all-reduce(sum) of
+    [numerator || denominator] (V,16) fp32."""
+    if group is None:
+        return N.attention_aggregation(filtered_views, scope)
+    import torch.distributed as dist
+    views = N.split_views(filtered_views)
+    shape = views[0].shape
+    c = shape[-1]
+    nvox = views[0].numel() // c
+    act = N.attention_activations(views, scope)
+    x = torch.stack([v.reshape(nvox, c) for v in views], dim=0)
+    lmax = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
+    L.call("atvs_attention_local_max", L.ptr(act), len(views), nvox, c, L.dtype_code(act), L.ptr(lmax), L.stream())
+    dist.all_reduce(lmax, op=dist.ReduceOp.MAX, group=group)
+    nd = torch.empty((nvox, 2 * c), dtype=torch.float32, device=x.device)
+    L.call("atvs_attention_partial", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(lmax),
+           L.ptr(nd), L.stream())
+    dist.all_reduce(nd, op=dist.ReduceOp.SUM, group=group)
+    out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
+    L.call("atvs_attention_finish", L.ptr(nd), nvox, c, L.ptr(out), L.stream())
+    return out.reshape(shape)
+
+
+def shard_views(n_views, rank, world):
+    """source views 1..N-1 dealt round-robin to ranks."""
+    return [v for v in range(1, n_views) if (v - 1) % world == rank]
+
+
+def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=None, rank=0, world=1):
+    """features (B,N,h,w,F) fp32, cams (B,N,2,4,4) -> dict(depth (B,h,w,1), depth_up (B,4h,4w,1),
+    prob_volume_agg, cost_volume_agg, depth_views).  example.py:144-158 + :109 (x4 upsample)."""
+    L.require_cuda(features, cams)
+    cams = L.f32c(cams)
+    n_views = cams.shape[1]
+    ds = cams[:, 0, 1, 3, 0].contiguous()
+    di = cams[:, 0, 1, 3, 1].contiguous()
+    mine = shard_views(n_views, rank, world) if group is not None else list(range(1, n_views))
+    filtered, depth_views = [], []
+    for view_i in mine:
+        f, _, dv = stage1_view(features, cams, depth_num, ds, di, view_i, siamese)
+        filtered.append(f)
+        depth_views.append(dv)
+    cost_agg = aggregate(filtered, 'attention_aggregate', group)
+    prob_agg = OutputConv({'data': cost_agg}).get_output().squeeze(-1)
+    depth, _ = _prob2depth(prob_agg, ds, di, 1, False)
+    out = dict(depth=depth, prob_volume_agg=prob_agg, cost_volume_agg=cost_agg, depth_views=depth_views)
+    if upsample:
+        out['depth_up'], _ = _prob2depth(prob_agg, ds, di, 4, False)
+    return out

@@ -1,0 +1,80 @@
+"""Variable store keyed by the TF checkpoint variable names.
+
+The reference restores ``tf.global_variables()`` from ``model.ckpt`` (example.py:121-125)
+and its ops find weights through TF variable scopes; here the same names index a dict of
+CUDA tensors.  The released checkpoint is not available offline, so
+``synthetic_weights`` generates seeded He-normal kernels with the reference's names and
+shapes."""
+import numpy as np
+import torch
+
+_STORE = {}
+_PACKED = {}
+
+
+def load_weights(weights, device='cuda'):
+    """weights: dict name -> array (TF layouts), or a path to an .npz with those keys."""
+    if isinstance(weights, str):
+        weights = dict(np.load(weights))
+    _STORE.clear()
+    _PACKED.clear()
+    for k, v in weights.items():
+        _STORE[k] = torch.as_tensor(np.asarray(v, dtype=np.float32)).to(device).contiguous()
+
+
+def get_variable(name):
+    try:
+        return _STORE[name]
+    except KeyError:
+        raise KeyError("variable %r not loaded (call variables.load_weights first)" % name)
+
+
+def has_variable(name):
+    return name in _STORE
+
+
+def packed_cache():
+    return _PACKED
+
+
+def crm_layer_table():
+    """(name, kind, Cin, Cout, stride) for StackedUNet_prob, cnn_wrapper/atvsnet.py:100-192."""
+    t = []
+    for b in range(3):
+        p = 'conv_b%d' % b
+        cin0 = 64 if b == 0 else 8
+        t += [(p + '_1_0', 'conv_bn', cin0, 16, 2), (p + '_2_0', 'conv_bn', 16, 32, 2),
+              (p + '_3_0', 'conv_bn', 32, 64, 2), (p + '_0_1', 'conv_bn', cin0, 8, 1),
+              (p + '_1_1', 'conv_bn', 16, 16, 1), (p + '_2_1', 'conv_bn', 32, 32, 1),
+              (p + '_3_1', 'conv_bn', 64, 64, 1), (p + '_4_0', 'deconv_bn', 64, 32, 2),
+              (p + '_5_0', 'deconv_bn', 32, 16, 2), (p + '_6_0', 'deconv_bn', 16, 8, 2)]
+    t.append(('conv_b2_6_2', 'conv', 8, 1, 1))
+    return t
+
+
+def synthetic_weights(seed=1234, logit_gain=4.0):
+    """Seeded He-normal weights with the checkpoint's names/shapes for the CRM
+    (StackedUNet_prob), AAM1/AAM2 and the output convs.  ``logit_gain`` scales the two 8->1
+    output kernels so that the soft-argmin is peaked (trained-like), SURVEY.md section 8(d)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+
+    def he(shape, fan_in):
+        return (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+
+    for name, kind, cin, cout, _ in crm_layer_table():
+        if kind == 'conv_bn':
+            w[name + '/conv3d/kernel'] = he((3, 3, 3, cin, cout), 27 * cin)
+        elif kind == 'deconv_bn':
+            w[name + '/conv3d_transpose/kernel'] = he((3, 3, 3, cout, cin), 27 * cin / 8.0)
+        else:
+            w[name + '/kernel'] = he((3, 3, 3, cin, cout), 27 * cin) * np.float32(logit_gain)
+        if kind != 'conv':
+            w[name + '/batch_normalization/moving_mean'] = np.zeros((cout,), np.float32)
+            w[name + '/batch_normalization/moving_variance'] = np.ones((cout,), np.float32)
+    for scope, outc in (('attention_aggregate', 'attention_prob_vol'),
+                        ('attention_aggregate_refine', 'attention_prob_vol_refine')):
+        w[scope + '/attention_activation/weight_unique'] = he((3, 3, 3, 8, 8), 27 * 8)
+        w[scope + '/attention_activation/weight_shared'] = he((3, 3, 3, 8, 8), 27 * 8)
+        w[outc + '/kernel'] = he((3, 3, 3, 8, 1), 27 * 8) * np.float32(logit_gain)
+    return w

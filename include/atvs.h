@@ -1,0 +1,140 @@
+/* atvs.h - C ABI of libatvs.so: the B200 (sm_100a) implementation of the A-TVSNet
+ * inference hot path.
+ *
+ * The reference (daiszh/A-TVSNet) has no FFI layer: its boundary for this path is a set
+ * of Python functions building TensorFlow-1.5 graph ops.  Each entry point below states
+ * which reference function (file:line under /root/reference) it replaces; the Python
+ * package `a-tvsnet_b200` re-exposes them under the reference's own names and tensor
+ * layouts (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name
+ *     ends in `_host`; the caller owns every buffer, including workspaces;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*) and keep no
+ *     global mutable state apart from a cache of TMA descriptors keyed by (ptr, shape);
+ *   - return value: 0 = ok, >0 = cudaError_t / CUresult of the failing call,
+ *     <0 = argument error (ATVS_E_*); atvs_last_error() returns a thread-local message;
+ *   - activations are channels-last (B,D,H,W,C), exactly the reference's NDHWC layout;
+ *   - dtype codes: ATVS_F32 = 0, ATVS_BF16 = 1.
+ */
+#ifndef ATVS_H_
+#define ATVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATVS_F32  0
+#define ATVS_BF16 1
+
+#define ATVS_E_SHAPE  (-1)   /* bad shape / alignment                     */
+#define ATVS_E_DTYPE  (-2)   /* unsupported dtype code                    */
+#define ATVS_E_DIV8   (-3)   /* a dimension that must be even / div by 8  */
+#define ATVS_E_NULL   (-4)   /* required pointer is NULL                  */
+#define ATVS_E_UNSUP  (-5)   /* unsupported configuration                 */
+
+typedef void* atvs_stream_t;     /* cudaStream_t */
+
+int         atvs_version(void);                 /* major*10000 + minor*100 + patch        */
+const char* atvs_last_error(void);              /* thread-local, never NULL               */
+int         atvs_device_sm_count(void);         /* SMs of the current device (148 on B200) */
+
+/* ---- get_homographies ------------------------------------------- homography_warping.py:179-227
+ * left_cam/right_cam (B,2,4,4) f32, depth_start/depth_interval (B) f32 -> out (B,D,3,3) f32.
+ * inverse_depth mirrors FLAGS.inverse_depth (homography_warping.py:215).  fp32, fixed op order
+ * (no FMA contraction), bit-identical to oracle/homography_warping.py:get_homographies.       */
+int atvs_get_homographies(const float* left_cam, const float* right_cam, int B, int D,
+                          const float* depth_start, const float* depth_interval,
+                          int inverse_depth, float* out, atvs_stream_t stream);
+
+/* ---- homography_warping (+ interpolate) -------------------- homography_warping.py:230-271, 31-104
+ * image (B,H,W,C) f32, homography (B,3,3) f32 -> out (B,H,W,C) f32, mask (B,H,W) u8 or NULL.
+ * method: 0 = bilinear, 1 = nearest.  C must be a multiple of 4 or equal to 1.                */
+int atvs_homography_warping(const float* image, const float* homography, int B, int H, int W,
+                            int C, int method, float* out, uint8_t* mask, atvs_stream_t stream);
+
+/* ---- homography_warping_by_depth ------------------------------ homography_warping.py:108-176
+ * depth_image (B,H,W) f32 (inverse depth when inverse_depth != 0).                            */
+int atvs_homography_warping_by_depth(const float* image, const float* left_cam,
+                                     const float* right_cam, const float* depth_image, int B,
+                                     int H, int W, int C, int method, int inverse_depth,
+                                     float* out, uint8_t* mask, atvs_stream_t stream);
+
+/* ---- build_cost_volume (fused warp + two-view cost) ------------------------- model.py:157-200
+ * ref/view feature (B,h,w,F) f32, homographies (B,D,3,3) f32 (view), ref_homographies
+ * (B,D,3,3) or NULL (warp_ref=False: the reference half is tile(ref, D)).
+ * mode 0 CONCAT      -> out (B,D,h,w,2F)  = [ref | warp(view)]           (reference layout)
+ * mode 1 WARPED_ONLY -> out (B,D,h,w,F)   = warp(view)
+ * mode 2 L1_MASKED   -> out (B,D,h,w,F)   = |warp(view) - ref| * valid    (model.py:272-280)
+ * out_dtype ATVS_F32 | ATVS_BF16.  F must be a multiple of 4 (8 for bf16).  Warped feature
+ * volumes are never materialised: each plane's slice is streamed straight to `out`.           */
+int atvs_build_cost_volume(const float* ref_feature, const float* view_feature,
+                           const float* homographies, const float* ref_homographies, int B,
+                           int D, int h, int w, int F, int mode, int out_dtype, void* out,
+                           atvs_stream_t stream);
+
+/* ---- 3-D convolution primitives ------------------ network.py:142-215 (conv, conv_bn), 511-550
+ * x (B,D,H,W,Cin) dtype `dtype`; kernel in TF layout: conv [3,3,3,Cin,Cout] f32, transposed
+ * conv [3,3,3,Cout,Cin] f32; stride 1|2 for conv (TF SAME padding), 2 for the transposed conv
+ * (TF SAME: out = 2*in, out[2i+k] += in[i]*w[k]).  No bias.  raw_out (B,Do,Ho,Wo,Cout) f32 is
+ * the PRE-batch-norm result.  stats (2*Cout doubles: sum, sum of squares; caller zeroes it)
+ * receives the per-channel moments of raw_out when not NULL (batch-statistics BN, F4).
+ * atvs_conv3d_fp32: CUDA-core fp32 parity path.  atvs_conv3d_bf16: tcgen05/TMEM implicit GEMM,
+ * bf16 operands, fp32 accumulation; `wpacked` comes from atvs_pack_conv_weights_bf16.         */
+int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int D, int H, int W, int Cin,
+                     int Cout, int stride, int transposed, float* raw_out, double* stats,
+                     atvs_stream_t stream);
+
+size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed);
+int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed,
+                                void* wpacked, atvs_stream_t stream);
+int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
+                     int Cout, int stride, int transposed, float* raw_out, double* stats,
+                     atvs_stream_t stream);
+
+/* ---- batch-norm (batch statistics) + ReLU + skip adds ------ network.py:206-215, 541-550, 696
+ * y = relu((raw - mean) * rsqrt(var + eps)) with mean/var from `stats` over `count` voxels
+ * (biased variance); out_plain = y (may be NULL); out_sum = y + skip1 + skip2 (NULL skips are
+ * omitted; may be NULL).  act_dtype is the dtype of skips and outputs.  n = count * C.          */
+int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps,
+                     int relu, const void* skip1, const void* skip2, void* out_plain,
+                     void* out_sum, int act_dtype, atvs_stream_t stream);
+
+/* ---- elementwise helpers (dtype plumbing for NDHWC volumes) */
+int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n,
+              atvs_stream_t stream);
+int atvs_add(const void* a, const void* b, void* out, int dtype, long long n, atvs_stream_t stream);
+
+/* ---- attention aggregation (AAM) ------------------------------- network.py:282-351, 379-408
+ * act (N,V,2C) `dtype`: per view n the pair [relu(conv(x_n,W_unique)) | relu(conv(x_n,W_shared))]
+ * (from the conv primitives with W_unique||W_shared concatenated on Cout);
+ * x (N,V,C) `dtype`: the per-view cost volumes.  score = softmax_n((u_n - s_n) + sum_m s_m),
+ * out (V,C) f32 = sum_n score_n * x_n.  When num_den != NULL the kernel instead writes the
+ * un-normalised partials [sum_n e^{l_n - gmax} x_n | sum_n e^{l_n - gmax}] (V,2C) f32 with
+ * l_n = u_n - s_n and gmax (V,C) f32 supplied by the caller (multi-GPU source-view sharding);
+ * atvs_attention_local_max produces the per-rank max, atvs_attention_finish divides.          */
+int atvs_attention_combine(const void* act, const void* x, int N, long long V, int C, int dtype,
+                           float* out, atvs_stream_t stream);
+int atvs_attention_local_max(const void* act, int N, long long V, int C, int dtype, float* lmax,
+                             atvs_stream_t stream);
+int atvs_attention_partial(const void* act, const void* x, int N, long long V, int C, int dtype,
+                           const float* gmax, float* num_den, atvs_stream_t stream);
+int atvs_attention_finish(const float* num_den, long long V, int C, float* out,
+                          atvs_stream_t stream);
+
+/* ---- prob2depth / get_propability_map / prob2depth_upsample -------- model.py:80-129, 13-76
+ * prob_volume (B,D,H,W) f32 logits; softmax over D of -logit, expectation against
+ * linspace(start, start+(D-1)*interval, D) -> depth (B,H*up,W*up) f32; prob_map (same shape,
+ * sum of the 4 probabilities around the estimate) or NULL.  up = 1, or 4 for the fused
+ * bilinear (align_corners) x4 logit upsample of model.py:68-76 (never materialised).          */
+int atvs_prob2depth(const float* prob_volume, int B, int D, int H, int W,
+                    const float* depth_start, const float* depth_interval, int up, float* depth,
+                    float* prob_map, atvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATVS_H_ */
