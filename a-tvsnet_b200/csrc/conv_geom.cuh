@@ -12,6 +12,11 @@
 //                    p=0 -> taps (k=0, off 0), (k=2, off -1);  p=1 -> tap (k=1, off 0)
 //                    (out[2i+k] += in[i] * w[k], cropped to [0, 2n)).
 #pragma once
+#ifdef __CUDACC__
+#define ATVS_HD __host__ __device__
+#else
+#define ATVS_HD
+#endif
 
 struct ConvGeom {
     int B, Din, Hin, Win, Cin, Cout;
@@ -24,7 +29,7 @@ struct ConvGeom {
     int kidx[3][3];     // kernel index per tap
 };
 
-static inline int same_pad_before(int n, int k, int s) {
+ATVS_HD static inline int same_pad_before(int n, int k, int s) {
     const int out = (n + s - 1) / s;
     int total = (out - 1) * s + k - n;
     if (total < 0) total = 0;
@@ -32,7 +37,7 @@ static inline int same_pad_before(int n, int k, int s) {
 }
 
 // conv (transposed == 0): one geometry.  deconv: cls in [0, 8) selects the parity class.
-static inline ConvGeom make_conv_geom(int B, int D, int H, int W, int Cin, int Cout, int stride, int transposed,
+ATVS_HD static inline ConvGeom make_conv_geom(int B, int D, int H, int W, int Cin, int Cout, int stride, int transposed,
                                       int cls) {
     ConvGeom g;
     g.B = B; g.Din = D; g.Hin = H; g.Win = W; g.Cin = Cin; g.Cout = Cout;

@@ -1,5 +1,648 @@
-// placeholder until the tcgen05 kernel lands
+// conv_tc.cu - 3-D convolution / transposed convolution as an implicit GEMM on the Blackwell
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA),
+// bf16 operands, fp32 accumulation.  Replaces tf.layers.conv3d / conv3d_transpose of
+// network.py:173-215, 511-550 (cuDNN fp32 in the reference) for the cost-regularisation
+// network and the attention convolutions.
+//
+// Formulation (one CTA = one persistent worker, 6 warps):
+//   GEMM M = 128 output voxels of a (TD,TH,TW) brick, N = Cout (padded to 16/32/64),
+//   K = Cin per filter tap.  For every tap ONE TMA box load of the (shifted) input brick
+//   [TD][TH][TW][Cin] is a K-major A tile (row = voxel, 2*Cin bytes, swizzle = row bytes);
+//   TMA's out-of-bounds zero fill IS the 'SAME' zero padding.  Stride-2 convolutions read
+//   through 8 parity-view tensor maps (in = 2j + off), transposed convolutions run one
+//   launch per output parity class (conv_geom.cuh).  All taps' weights stay resident in
+//   shared memory ([tap][N][Cin] K-major tiles loaded once per CTA by TMA).
+//   warp 0: TMA producer | warp 1: TMEM allocator + single-thread MMA issuer |
+//   warps 2-5: epilogue (tcgen05.ld -> raw fp32 store + per-channel sum / sum-of-squares for
+//   the batch-statistics BN), double-buffered TMEM accumulators.
+//   Cin = 8 (16-byte rows): two taps form one K=16 step (no-swizzle core-matrix layout, the
+//   second tap's tile is the K-adjacent core matrix, LBO = tile size).
 #include "common.cuh"
-extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) { return 16; }
-extern "C" int atvs_pack_conv_weights_bf16(const float*, int, int, int, void*, atvs_stream_t) { atvs_set_error("nyi"); return ATVS_E_UNSUP; }
-extern "C" int atvs_conv3d_bf16(const void*, const void*, int, int, int, int, int, int, int, int, float*, double*, atvs_stream_t) { atvs_set_error("nyi"); return ATVS_E_UNSUP; }
+#include "conv_geom.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <cstring>
+
+namespace {
+
+constexpr int TC_MAX_TAPS = 28;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 27;   // bounded waits: trap instead of hanging the GPU
+
+struct TcTap {
+    int map, ox, oy, oz;
+};
+
+struct TcParams {
+    int ntaps;                 // padded to a multiple of taps-per-stage
+    TcTap taps[TC_MAX_TAPS];
+    int B, Dj, Hj, Wj;         // iteration space (tile origins live here)
+    int Do, Ho, Wo;            // full output extent
+    int os, pz, py, px;        // out = j*os + p
+    int ltd, lth, ltw;         // log2 of the brick dims (TD*TH*TW == 128)
+    int nTD, nTH, nTW;
+    int Cout, coff, ncols;     // real channel count, slab offset, real columns in this slab
+    int nstages;
+    long long ntiles;
+};
+
+struct alignas(64) TcMaps {
+    CUtensorMap a[8];
+    CUtensorMap w;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > TC_SPIN_LIMIT) {
+            printf("atvs conv_tc: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (K-major operand tile):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+// 32 values per lane -> lane L ends with the sum over the warp of v[L] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int CIN>
+struct TcCfg {
+    static constexpr int TPS = (CIN == 8) ? 2 : 1;              // taps per pipeline stage
+    static constexpr int KSTEPS = (CIN >= 16) ? CIN / 16 : 1;   // UMMA K=16 steps per stage
+    static constexpr int TILE_BYTES = 128 * CIN * 2;
+    static constexpr int STAGE_BYTES = TILE_BYTES * TPS;
+    // UMMA layout_type: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
+    static constexpr uint32_t LAYOUT = (CIN == 64) ? 2u : (CIN == 32) ? 4u : (CIN == 16) ? 6u : 0u;
+    static constexpr uint32_t SBO = (CIN == 8) ? 128u : (uint32_t)(8 * CIN * 2);
+};
+
+template <int CIN, int NPAD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams p, float* __restrict__ out,
+            double* __restrict__ stats) {
+    using Cfg = TcCfg<CIN>;
+    constexpr int WTAP_BYTES = NPAD * CIN * 2;
+    constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;
+    const int wbytes = p.ntaps * WTAP_BYTES;
+    uint8_t* asmem = smem + ((wbytes + 1023) & ~1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(asmem + (size_t)p.nstages * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.nstages;
+    uint64_t* tfull = bars + 2 * p.nstages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tfull[0], 1);
+        mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4);
+        mbar_init(&tempty[1], 4);
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nsteps = p.ntaps / Cfg::TPS;
+    const int tiles_per_b = p.nTD * p.nTH * p.nTW;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.w);
+            mbar_expect_tx(wbar, (uint32_t)wbytes);
+            for (int t = 0; t < p.ntaps; ++t) tma_load_2d(wsm + (size_t)t * WTAP_BYTES, &tm.w, 0, t * NPAD, wbar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_b);
+                int r = (int)(tile % tiles_per_b);
+                const int jx0 = (r % p.nTW) << p.ltw;
+                r /= p.nTW;
+                const int jy0 = (r % p.nTH) << p.lth;
+                const int jz0 = (r / p.nTH) << p.ltd;
+                for (int s = 0; s < nsteps; ++s) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], (uint32_t)Cfg::STAGE_BYTES);
+                    uint8_t* dst = asmem + (size_t)stage * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int q = 0; q < Cfg::TPS; ++q) {
+                        const TcTap& tp = p.taps[s * Cfg::TPS + q];
+                        tma_load_5d(dst + q * Cfg::TILE_BYTES, &tm.a[tp.map], 0, jx0 + tp.ox, jy0 + tp.oy, jz0 + tp.oz, b,
+                                    &full[stage]);
+                    }
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            const uint32_t a_lbo = (CIN == 8) ? (uint32_t)Cfg::TILE_BYTES : 16u;
+            const uint32_t b_lbo = (CIN == 8) ? (uint32_t)(NPAD * 16) : 16u;
+            int stage = 0;
+            uint32_t phase = 0;
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(&tempty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + (uint32_t)(acc * NPAD);
+                for (int s = 0; s < nsteps; ++s) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(asmem + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t bbase = smem_u32(wsm + (size_t)s * Cfg::TPS * WTAP_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                        const uint64_t ad = make_desc(abase + ks * 32, a_lbo, Cfg::SBO, Cfg::LAYOUT);
+                        const uint64_t bd = make_desc(bbase + ks * 32, b_lbo, Cfg::SBO, Cfg::LAYOUT);
+                        tc_mma_bf16(dcol, ad, bd, IDESC, (s | ks) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        const int g = warp & 3;
+        const int row = g * 32 + lane;
+        const int tw = row & ((1 << p.ltw) - 1);
+        const int th = (row >> p.ltw) & ((1 << p.lth) - 1);
+        const int td = row >> (p.ltw + p.lth);
+        constexpr int NRED = (2 * NPAD) / 32;       // per-lane running statistics registers
+        float run[NRED];
+#pragma unroll
+        for (int i = 0; i < NRED; ++i) run[i] = 0.f;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const int b = (int)(tile / tiles_per_b);
+            int r = (int)(tile % tiles_per_b);
+            const int jx = ((r % p.nTW) << p.ltw) + tw;
+            r /= p.nTW;
+            const int jy = ((r % p.nTH) << p.lth) + th;
+            const int jz = ((r / p.nTH) << p.ltd) + td;
+            const bool valid = jx < p.Wj && jy < p.Hj && jz < p.Dj;
+            mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            float v[NPAD];
+            const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
+#pragma unroll
+            for (int c = 0; c < NPAD; c += 16) tc_ld16(taddr + c, v + c);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (valid) {
+                const size_t o = ((((size_t)b * p.Do + (jz * p.os + p.pz)) * p.Ho + (jy * p.os + p.py)) * p.Wo +
+                                  (jx * p.os + p.px)) * p.Cout + p.coff;
+                float* op = out + o;
+                if ((p.ncols & 3) == 0 && (p.Cout & 3) == 0) {
+#pragma unroll
+                    for (int c = 0; c < NPAD; c += 4)
+                        if (c < p.ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c)
+                        if (c < p.ncols) op[c] = v[c];
+                }
+            }
+            if (stats != nullptr) {
+                if (!valid) {
+#pragma unroll
+                    for (int c = 0; c < NPAD; ++c) v[c] = 0.f;
+                }
+                if (NPAD == 16) {
+                    float a[32];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        a[c] = v[c];
+                        a[16 + c] = v[c] * v[c];
+                    }
+                    run[0] += warp_transpose_reduce32(a, lane);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NPAD / 32; ++h) {
+                        float q[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) q[c] = v[h * 32 + c] * v[h * 32 + c];
+                        run[2 * h + 1] += warp_transpose_reduce32(q, lane);
+                        run[2 * h] += warp_transpose_reduce32(v + h * 32, lane);
+                    }
+                }
+            }
+        }
+        if (stats != nullptr) {
+            if (NPAD == 16) {
+                const int c = lane & 15;
+                if (c < p.ncols) atomicAdd(&stats[(lane < 16 ? 0 : p.Cout) + p.coff + c], (double)run[0]);
+            } else {
+#pragma unroll
+                for (int h = 0; h < NPAD / 32; ++h) {
+                    const int c = h * 32 + lane;
+                    if (c < p.ncols) {
+                        atomicAdd(&stats[p.coff + c], (double)run[2 * h]);
+                        atomicAdd(&stats[p.Cout + p.coff + c], (double)run[2 * h + 1]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ weight packing
+// packed image: for each class, for each (padded) tap, for each slab: [NPAD][Cin] bf16, K-major.
+__global__ void k_pack_weights(const float* __restrict__ w, int Cin, int Cout, int transposed, int npad, int nslabs,
+                               int ncls, __nv_bfloat16* __restrict__ out) {
+    // one block per (class, slab, tap); taps follow make_conv_geom order
+    const int tps = (Cin == 8) ? 2 : 1;
+    int cls = 0, slab = 0, tap = 0, ntaps_pad = 0;
+    size_t base = 0;
+    {
+        int blk = blockIdx.x;
+        for (cls = 0; cls < ncls; ++cls) {
+            const ConvGeom g = make_conv_geom(1, 2, 2, 2, Cin, Cout, 1, transposed, cls);
+            const int nt = g.nt[0] * g.nt[1] * g.nt[2];
+            ntaps_pad = (nt + tps - 1) / tps * tps;
+            if (blk < ntaps_pad * nslabs) break;
+            blk -= ntaps_pad * nslabs;
+            base += (size_t)ntaps_pad * nslabs * npad * Cin;
+        }
+        if (cls == ncls) return;
+        slab = blk / ntaps_pad;
+        tap = blk % ntaps_pad;
+    }
+    const ConvGeom g = make_conv_geom(1, 2, 2, 2, Cin, Cout, 1, transposed, cls);
+    const int nt = g.nt[0] * g.nt[1] * g.nt[2];
+    int kidx = -1;
+    if (tap < nt) {
+        const int tx = tap % g.nt[2], ty = (tap / g.nt[2]) % g.nt[1], tz = tap / (g.nt[2] * g.nt[1]);
+        kidx = (g.kidx[0][tz] * 3 + g.kidx[1][ty]) * 3 + g.kidx[2][tx];
+    }
+    __nv_bfloat16* o = out + base + ((size_t)slab * ntaps_pad + tap) * npad * Cin;
+    for (int i = threadIdx.x; i < npad * Cin; i += blockDim.x) {
+        const int n = i / Cin, k = i % Cin;
+        const int co = slab * npad + n;
+        float val = 0.f;
+        if (kidx >= 0 && co < Cout)
+            val = transposed ? w[((size_t)kidx * Cout + co) * Cin + k] : w[((size_t)kidx * Cin + k) * Cout + co];
+        o[i] = __float2bfloat16_rn(val);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int cin) {
+    return cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : cin == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
+                     : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+struct SlabPlan {
+    int npad, nslabs;
+};
+
+// pick the N tile: the smallest of {16,32,64} covering Cout whose resident weights fit
+SlabPlan plan_slabs(int Cin, int Cout, int max_taps) {
+    int npad = Cout <= 16 ? 16 : Cout <= 32 ? 32 : 64;
+    const int tps = (Cin == 8) ? 2 : 1;
+    const int tp = (max_taps + tps - 1) / tps * tps;
+    while (npad > 16 && (size_t)tp * npad * Cin * 2 > 120 * 1024) npad >>= 1;
+    return SlabPlan{npad, (Cout + npad - 1) / npad};
+}
+
+int ntaps_padded(int Cin, int transposed, int cls) {
+    const ConvGeom g = make_conv_geom(1, 2, 2, 2, Cin, 16, 1, transposed, cls);
+    const int nt = g.nt[0] * g.nt[1] * g.nt[2];
+    const int tps = (Cin == 8) ? 2 : 1;
+    return (nt + tps - 1) / tps * tps;
+}
+
+template <int CIN, int NPAD>
+int launch_tc(const TcMaps& maps, const TcParams& p, float* out, double* stats, size_t smem, int grid,
+              cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_tc<CIN, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    k_conv3d_tc<CIN, NPAD><<<grid, TC_THREADS, smem, st>>>(maps, p, out, stats);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
+    if (!(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) || Cout < 1 || Cout > 64) return 0;
+    const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
+    size_t elems = 0;
+    const int ncls = transposed ? 8 : 1;
+    for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
+    return elems * 2;
+}
+
+extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed, void* wpacked,
+                                           atvs_stream_t stream) {
+    ATVS_CHECK_ARG(kernel && wpacked, ATVS_E_NULL, "atvs_pack_conv_weights_bf16: NULL pointer");
+    ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
+                   "atvs_pack_conv_weights_bf16: Cin=%d (8, 16, 32 or 64)", Cin);
+    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_pack_conv_weights_bf16: Cout=%d (1..64)", Cout);
+    const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
+    const int ncls = transposed ? 8 : 1;
+    int blocks = 0;
+    for (int c = 0; c < ncls; ++c) blocks += ntaps_padded(Cin, transposed, c) * sp.nslabs;
+    k_pack_weights<<<blocks, 128, 0, (cudaStream_t)stream>>>(kernel, Cin, Cout, transposed, sp.npad, sp.nslabs, ncls,
+                                                            (__nv_bfloat16*)wpacked);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
+                                int Cout, int stride, int transposed, float* raw_out, double* stats,
+                                atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x_bf16 && wpacked && raw_out, ATVS_E_NULL, "atvs_conv3d_bf16: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16: bad shape");
+    ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
+                   "atvs_conv3d_bf16: Cin=%d (8, 16, 32 or 64)", Cin);
+    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_conv3d_bf16: Cout=%d (1..64)", Cout);
+    ATVS_CHECK_ARG(transposed ? stride == 2 : (stride == 1 || stride == 2), ATVS_E_UNSUP,
+                   "atvs_conv3d_bf16: stride=%d transposed=%d", stride, transposed);
+    ATVS_CHECK_ARG(transposed || stride == 1 || ((D | H | W) & 1) == 0, ATVS_E_DIV8,
+                   "atvs_conv3d_bf16: stride-2 convolution needs even D,H,W (got %d,%d,%d)", D, H, W);
+    ATVS_CHECK_ARG(((uintptr_t)x_bf16 & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)raw_out & 15) == 0,
+                   ATVS_E_SHAPE, "atvs_conv3d_bf16: buffers must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode();
+    if (!encode) {
+        atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled entry point not available");
+        return ATVS_E_UNSUP;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
+    const int ncls = transposed ? 8 : 1;
+    const int tps = (Cin == 8) ? 2 : 1;
+    const CUtensorMapSwizzle swz = swizzle_for(Cin);
+    const char* xb = (const char*)x_bf16;
+    size_t wofs = 0;   // element offset into the packed weights
+
+    for (int cls = 0; cls < ncls; ++cls) {
+        const ConvGeom g = make_conv_geom(B, D, H, W, Cin, Cout, stride, transposed, cls);
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        p.B = B; p.Dj = g.Dj; p.Hj = g.Hj; p.Wj = g.Wj;
+        p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
+        p.os = g.os; p.pz = g.p[0]; p.py = g.p[1]; p.px = g.p[2];
+        p.Cout = Cout;
+        // brick shape: 128 voxels, minimise padded volume, prefer a wide x extent
+        {
+            static const int opts[][3] = {{2, 8, 8}, {1, 8, 16}, {4, 4, 8}, {2, 4, 16}, {1, 4, 32}, {4, 8, 4},
+                                          {8, 4, 4}, {1, 16, 8}, {2, 16, 4}, {8, 8, 2}, {16, 4, 2}, {32, 2, 2},
+                                          {8, 16, 1}, {16, 8, 1}, {128, 1, 1}, {1, 1, 128}, {1, 128, 1}, {1, 2, 64}};
+            long long best = -1;
+            int bi = 0;
+            for (int i = 0; i < (int)(sizeof(opts) / sizeof(opts[0])); ++i) {
+                const long long n = (long long)((g.Dj + opts[i][0] - 1) / opts[i][0]) *
+                                    ((g.Hj + opts[i][1] - 1) / opts[i][1]) * ((g.Wj + opts[i][2] - 1) / opts[i][2]);
+                if (best < 0 || n < best) { best = n; bi = i; }
+            }
+            const int TD = opts[bi][0], TH = opts[bi][1], TW = opts[bi][2];
+            auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+            p.ltd = lg(TD); p.lth = lg(TH); p.ltw = lg(TW);
+            p.nTD = (g.Dj + TD - 1) / TD; p.nTH = (g.Hj + TH - 1) / TH; p.nTW = (g.Wj + TW - 1) / TW;
+            p.ntiles = (long long)B * p.nTD * p.nTH * p.nTW;
+        }
+        const int TD = 1 << p.ltd, TH = 1 << p.lth, TW = 1 << p.ltw;
+        // taps
+        int nt = 0;
+        for (int tz = 0; tz < g.nt[0]; ++tz)
+            for (int ty = 0; ty < g.nt[1]; ++ty)
+                for (int tx = 0; tx < g.nt[2]; ++tx) {
+                    const int off[3] = {g.koff[0][tz], g.koff[1][ty], g.koff[2][tx]};
+                    TcTap& t = p.taps[nt++];
+                    if (g.s_in == 2) {
+                        int par[3], ho[3];
+                        for (int a = 0; a < 3; ++a) { par[a] = off[a] & 1; ho[a] = (off[a] - par[a]) / 2; }
+                        t.map = (par[0] * 2 + par[1]) * 2 + par[2];
+                        t.oz = ho[0]; t.oy = ho[1]; t.ox = ho[2];
+                    } else {
+                        t.map = 0; t.oz = off[0]; t.oy = off[1]; t.ox = off[2];
+                    }
+                }
+        while (nt % tps) { p.taps[nt] = p.taps[nt - 1]; ++nt; }   // phantom tap: zero weights
+        p.ntaps = nt;
+
+        // tensor maps over the input
+        TcMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const int nmaps = (g.s_in == 2) ? 8 : 1;
+        for (int m = 0; m < nmaps; ++m) {
+            const int pz = (m >> 2) & 1, py = (m >> 1) & 1, px = m & 1;
+            const int s = g.s_in;
+            cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)(W / s), (cuuint64_t)(H / s), (cuuint64_t)(D / s),
+                                  (cuuint64_t)B};
+            cuuint64_t strides[4] = {(cuuint64_t)Cin * 2 * s, (cuuint64_t)W * Cin * 2 * s,
+                                     (cuuint64_t)H * W * Cin * 2 * s, (cuuint64_t)D * H * W * Cin * 2};
+            cuuint32_t box[5] = {(cuuint32_t)Cin, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TD, 1};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            void* base = (void*)(xb + ((size_t)(pz * H + py) * W + px) * Cin * 2);
+            CUresult r = encode(&maps.a[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled(input, map %d) failed: %d", m, (int)r);
+                return (int)r;
+            }
+        }
+        for (int slab = 0; slab < sp.nslabs; ++slab) {
+            p.coff = slab * sp.npad;
+            p.ncols = (Cout - p.coff < sp.npad) ? Cout - p.coff : sp.npad;
+            {
+                cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)nt * sp.npad};
+                cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+                cuuint32_t box[2] = {(cuuint32_t)Cin, (cuuint32_t)sp.npad};
+                cuuint32_t es[2] = {1, 1};
+                void* base = (void*)((const char*)wpacked + (wofs + (size_t)slab * nt * sp.npad * Cin) * 2);
+                CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+                    return (int)r;
+                }
+            }
+            const size_t wbytes = ((size_t)nt * sp.npad * Cin * 2 + 1023) & ~(size_t)1023;
+            const size_t stage_bytes = (size_t)128 * Cin * 2 * tps;
+            const size_t budget = 200 * 1024;
+            int nst = (int)((budget - wbytes) / stage_bytes);
+            if (nst > 8) nst = 8;
+            if (nst > nt / tps) nst = nt / tps > 2 ? nt / tps : 2;
+            if (nst < 2) {
+                atvs_set_error("atvs_conv3d_bf16: weights do not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
+                return ATVS_E_UNSUP;
+            }
+            p.nstages = nst;
+            const size_t smem = 1024 + wbytes + (size_t)nst * stage_bytes + (2 * nst + 5) * 8 + 16;
+            const int sms = atvs_num_sms();
+            const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+            int rc = 0;
+#define TC_CASE(CI, NP) if (Cin == CI && sp.npad == NP) rc = launch_tc<CI, NP>(maps, p, raw_out, stats, smem, grid, st); else
+            TC_CASE(8, 16) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32) TC_CASE(32, 64)
+            TC_CASE(64, 16) TC_CASE(64, 32) TC_CASE(8, 32) TC_CASE(8, 64) TC_CASE(16, 64) TC_CASE(64, 64)
+            {
+                atvs_set_error("atvs_conv3d_bf16: no kernel for Cin=%d N=%d", Cin, sp.npad);
+                return ATVS_E_UNSUP;
+            }
+#undef TC_CASE
+            if (rc) return rc;
+        }
+        wofs += (size_t)nt * sp.nslabs * sp.npad * Cin;
+    }
+    return 0;
+}

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/atvs.h declares;
+argument validation works without touching a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import atvsnet_b200 as A
+    return A._lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'atvs.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = set(re.findall(r'\b(atvs_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) >= 19
+    for n in sorted(names):
+        assert hasattr(lib, n), 'libatvs.so does not export %s' % n
+    import atvsnet_b200 as A
+    assert names == set(A._lib.EXPORTS)
+
+
+def test_version_and_error_string(lib):
+    assert lib.atvs_version() >= 100
+    assert isinstance(lib.atvs_last_error(), bytes)
+
+
+def test_argument_errors_without_gpu(lib):
+    # NULL pointers / bad shapes are rejected before any CUDA call
+    rc = lib.atvs_get_homographies(None, None, 1, 8, None, None, 1, None, None)
+    assert rc == -4 and b'NULL' in lib.atvs_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.atvs_prob2depth(p, 1, 8, 4, 4, p, p, 3, p, None, None) == -5          # up must be 1 or 4
+    assert lib.atvs_build_cost_volume(p, p, p, None, 1, 8, 4, 4, 6, 0, 0, p, None) == -1  # F % 4
+    assert lib.atvs_conv3d_fp32(p, p, 1, 2, 2, 2, 8, 5, 1, 0, p, None, None) == -5       # Cout
+    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, None, None) == -5      # Cin
+    assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, None, None) == -3      # odd D, stride 2
+    assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64
+    assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2
+    assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    import atvsnet_b200 as A
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        A.prob2depth(torch.zeros(1, 4, 2, 2), 4, torch.zeros(1), torch.ones(1))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        A.get_homographies(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4), 4, torch.zeros(1), torch.ones(1))

@@ -1,0 +1,373 @@
+"""GPU parity tests (-m gpu): every CUDA entry point, called through the C ABI via the Python
+operator layer, against the CPU oracle on the same seeded inputs and against the golden
+fixtures generated from the reference's own sources.
+
+Tolerances: geometry (homographies, warps, fp32 cost volumes) bit-exact; fp32 network path
+<= 2e-4 of max|.| (different fp32 summation order through 31 conv+BN layers); bf16
+tensor-core path: final depth MAE <= 0.1 % of the depth range (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def A():
+    import atvsnet_b200 as A
+    assert torch.cuda.is_available()
+    A._lib.load()
+    return A
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ------------------------------------------------------------------ geometry
+def test_get_homographies_bit_exact(A, golden):
+    from oracle import homography_warping as ohw
+    cams, ds, di = golden['ex0_cams'], golden['ds'], golden['di']
+    for l, r, D in ((0, 1, 128), (0, 4, 128), (3, 0, 16)):
+        H = npy(A.get_homographies(cu(cams[l:l + 1]), cu(cams[r:r + 1]), D, cu(ds), cu(di)))
+        Ho = ohw.get_homographies(cams[l:l + 1], cams[r:r + 1], D, ds, di)
+        assert np.array_equal(H, Ho)
+    assert rel_err(H, golden['ex0_H_3_0']) < 5e-6
+    A.FLAGS.inverse_depth = False
+    try:
+        H = npy(A.get_homographies(cu(cams[0:1]), cu(cams[2:3]), 8, cu(np.float32([2.0])), cu(np.float32([0.5]))))
+    finally:
+        A.FLAGS.inverse_depth = True
+    assert np.array_equal(H, ohw.get_homographies(cams[0:1], cams[2:3], 8, np.float32([2.0]), np.float32([0.5]),
+                                                  inverse_depth=False))
+    # batch of 3 pairs in one call
+    Hb = npy(A.get_homographies(cu(cams[0:3]), cu(cams[1:4]), 5, cu(np.repeat(ds, 3)), cu(np.repeat(di, 3))))
+    assert np.array_equal(Hb, ohw.get_homographies(cams[0:3], cams[1:4], 5, np.repeat(ds, 3), np.repeat(di, 3)))
+
+
+def test_homography_warping_golden_and_oracle(A, golden):
+    img, Hs = golden['warp_img'], golden['warp_H']
+    for d in (0, 3, 7):
+        out, mask = A.homography_warping(cu(img), cu(Hs[:, d]), output_mask=True)
+        assert np.array_equal(npy(out), golden['warp_bilinear_%d' % d])
+        assert np.array_equal(mask.cpu().numpy(), golden['warp_mask_%d' % d])
+    out, mask = A.homography_warping(cu(img[..., :1]), cu(Hs[:, 3]), method='nearest', output_mask=True)
+    assert np.array_equal(npy(out), golden['warp_nearest_3'])
+    assert np.array_equal(mask.cpu().numpy(), golden['warp_nearest_mask_3'])
+    # identity homography: interior copied, last row / column zero (strict x < W-1 rule)
+    eye = np.eye(3, dtype=np.float32)[None]
+    out = npy(A.homography_warping(cu(img), cu(eye)))
+    assert np.array_equal(out[:, :-1, :-1], img[:, :-1, :-1])
+    assert not out[:, -1].any() and not out[:, :, -1].any()
+
+
+def test_homography_warping_edge_cases(A):
+    from oracle import homography_warping as ohw
+    rng = np.random.default_rng(5)
+    img = rng.standard_normal((2, 9, 11, 4)).astype(np.float32)
+    H = np.stack([np.float32([[1, 0, 0.5], [0, 1, -0.25], [0, 0, 1]]),        # sub-pixel shift
+                  np.float32([[0, 0, 0], [0, 0, 0], [0, 0, 0]])])             # degenerate: z == 0 -> +1e-7
+    out, mask = A.homography_warping(cu(img), cu(H), output_mask=True)
+    oo, om_ = ohw.homography_warping(img, H, output_mask=True)
+    assert np.array_equal(npy(out), oo) and np.array_equal(mask.cpu().numpy(), om_)
+    # single-channel (depth map) path, nearest + bilinear
+    d1 = rng.standard_normal((2, 9, 11, 1)).astype(np.float32)
+    for m in ('bilinear', 'nearest'):
+        assert np.array_equal(npy(A.homography_warping(cu(d1), cu(H), method=m)), ohw.homography_warping(d1, H, method=m))
+    # far-away homography: everything invalid -> exact zeros
+    Hf = np.float32([[[1, 0, 1e4], [0, 1, 1e4], [0, 0, 1]]] * 2)
+    out, mask = A.homography_warping(cu(img), cu(Hf), output_mask=True)
+    assert not npy(out).any() and not mask.any()
+    with pytest.raises(RuntimeError):
+        A.homography_warping(torch.zeros(1, 4, 4, 4), torch.zeros(1, 3, 3))      # CPU tensors: no fallback
+
+
+def test_homography_warping_by_depth(A, golden):
+    from oracle import homography_warping as ohw
+    c = golden['warp_cams']
+    for m in ('bilinear', 'nearest'):
+        out, mask = A.homography_warping_by_depth(cu(golden['warp_img']), cu(c[0:1]), cu(c[1:2]),
+                                                  cu(golden['bydepth_depth']), output_mask=True, method=m)
+        oo, om_ = ohw.homography_warping_by_depth(golden['warp_img'], c[0:1], c[1:2], golden['bydepth_depth'],
+                                                  output_mask=True, method=m)
+        assert np.array_equal(npy(out), oo) and np.array_equal(mask.cpu().numpy(), om_)
+
+
+def test_build_cost_volume(A, golden):
+    from oracle import model as om
+    c = golden['warp_cams'][None, :2]
+    ds, di = golden['ds'], golden['di'] * 32
+    ref, view = golden['cv_ref'], golden['warp_img']
+    cv = npy(A.build_cost_volume(cu(ref), cu(view), cu(c), 4, cu(ds), cu(di), 0, 1))
+    assert np.array_equal(cv, om.build_cost_volume(ref, view, c, 4, ds, di, 0, 1))
+    bad = np.abs(cv - golden['cv_concat']).max(axis=-1) > 2e-4 * np.abs(cv).max()
+    assert bad.mean() < 1e-3
+    cv, H = A.build_cost_volume(cu(view), cu(ref), cu(c), 4, cu(ds), cu(di), 1, 0, output_homo=True)
+    assert np.array_equal(npy(cv), om.build_cost_volume(view, ref, c, 4, ds, di, 1, 0))
+    assert H.shape == (1, 4, 3, 3)
+    cv = npy(A.build_cost_volume(cu(ref), cu(view), cu(c), 2, cu(ds), cu(di), 0, 1, warp_ref=True))
+    assert np.array_equal(cv, om.build_cost_volume(ref, view, c, 2, ds, di, 0, 1, warp_ref=True))
+    # bf16 output = fp32 result rounded once
+    cvb = A.build_cost_volume(cu(ref), cu(view), cu(c), 4, cu(ds), cu(di), 0, 1, out_dtype=torch.bfloat16)
+    cvf = A.build_cost_volume(cu(ref), cu(view), cu(c), 4, cu(ds), cu(di), 0, 1)
+    assert torch.equal(cvb, cvf.to(torch.bfloat16))
+    # warped-only and masked-L1 modes (model.py:272-280)
+    wo = npy(A.build_cost_volume(cu(ref), cu(view), cu(c), 4, cu(ds), cu(di), 0, 1, mode='warped_only'))
+    assert np.array_equal(wo, npy(cvf)[..., 8:])
+    l1 = npy(A.build_cost_volume(cu(ref), cu(view), cu(c), 4, cu(ds), cu(di), 0, 1, mode='l1_masked'))
+    from oracle import homography_warping as ohw
+    Hs = ohw.get_homographies(c[:, 0], c[:, 1], 4, ds, di)
+    for d in range(4):
+        w_, m_ = ohw.homography_warping(view, Hs[:, d], output_mask=True)
+        assert np.array_equal(l1[:, d], np.abs(w_ - ref) * m_.astype(np.float32))
+
+
+def test_build_cost_volume_full_size_properties(A):
+    """cfg2 size (D=128, 128x160, F=32): properties that need no oracle run."""
+    D, h, w = 128, 128, 160
+    cams = A.synthetic.orbit_cams(5, h, w, D)[None]
+    f = A.synthetic.smooth_features(2, h, w, 32, seed=1)[None]
+    tc, tf = cu(cams), cu(f)
+    ds, di = tc[:, 0, 1, 3, 0], tc[:, 0, 1, 3, 1]
+    cv = A.build_cost_volume(tf[:, 0], tf[:, 1], tc, D, ds, di, 0, 1)
+    assert cv.shape == (1, D, h, w, 64)
+    assert torch.equal(cv[0, :, :, :, :32], tf[0, 0].expand(D, h, w, 32))           # tiled reference half
+    # linearity in the source feature
+    cv2 = A.build_cost_volume(tf[:, 0], 2.0 * tf[:, 1], tc, D, ds, di, 0, 1)
+    assert torch.equal(cv2[..., 32:], 2.0 * cv[..., 32:])
+    # identical cameras => identity warp on the interior for every plane
+    cvi = A.build_cost_volume(tf[:, 0], tf[:, 1], tc, D, ds, di, 0, 0)
+    assert torch.equal(cvi[0, :, :-1, :-1, 32:], tf[0, 1, :-1, :-1].expand(D, h - 1, w - 1, 32))
+    valid = (cv[..., 32:] != 0).any(dim=-1).float().mean().item()
+    assert 0.7 < valid <= 1.0
+
+
+# ------------------------------------------------------------------ conv primitives
+LAYER_KINDS = [(64, 8, 1, 0), (64, 16, 2, 0), (16, 32, 2, 0), (32, 64, 2, 0), (16, 16, 1, 0), (32, 32, 1, 0),
+               (64, 64, 1, 0), (8, 16, 2, 0), (8, 8, 1, 0), (8, 1, 1, 0), (8, 16, 1, 0),
+               (64, 32, 2, 1), (32, 16, 2, 1), (16, 8, 2, 1)]
+
+
+def _conv_case(cin, cout, stride, transposed, seed, shape=(2, 4, 6, 10)):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(shape + (cin,)).astype(np.float32)
+    wshape = (3, 3, 3, cout, cin) if transposed else (3, 3, 3, cin, cout)
+    w = (rng.standard_normal(wshape) / np.sqrt(27 * cin)).astype(np.float32)
+    return x, w
+
+
+@pytest.mark.parametrize('cin,cout,stride,transposed', LAYER_KINDS)
+def test_conv3d_fp32(A, cin, cout, stride, transposed):
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    x, w = _conv_case(cin, cout, stride, transposed, 1)
+    raw, stats = conv3d_raw(cu(x), 't', cu(w), cout, stride, bool(transposed), True)
+    ref = onet.deconv3d(x, w) if transposed else onet.conv3d(x, w, stride)
+    assert raw.shape == ref.shape
+    assert rel_err(npy(raw), ref) < 2e-5
+    s = stats.cpu().numpy()
+    flat = ref.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(s[:cout], flat.sum(0), rtol=1e-4, atol=1e-3)
+    assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('cin,cout,stride,transposed', LAYER_KINDS)
+def test_conv3d_bf16_tensor_core(A, cin, cout, stride, transposed):
+    """tcgen05 implicit GEMM vs the oracle conv on bf16-rounded operands (so only the fp32
+    accumulation order differs)."""
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    x, w = _conv_case(cin, cout, stride, transposed, 2, shape=(1, 8, 12, 20))
+    xb = torch.from_numpy(x).to(torch.bfloat16)
+    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    A.variables.packed_cache().clear()
+    raw, stats = conv3d_raw(xb.cuda(), 'tc_test_%d_%d_%d_%d' % (cin, cout, stride, transposed), wb.cuda(), cout,
+                            stride, bool(transposed), True)
+    torch.cuda.synchronize()
+    xr = xb.float().numpy()
+    ref = onet.deconv3d(xr, wb.numpy()) if transposed else onet.conv3d(xr, wb.numpy(), stride)
+    assert raw.shape == ref.shape
+    assert rel_err(npy(raw), ref) < 1e-4
+    s = stats.cpu().numpy()
+    flat = ref.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(s[:cout], flat.sum(0), rtol=1e-3, atol=1e-2)
+    assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_conv3d_bf16_ragged_and_batched(A):
+    """brick tiles hanging over every border, odd extents (stride 1 / deconv), batch > 1."""
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    for (cin, cout, stride, tr, shape) in ((16, 16, 1, 0, (2, 3, 5, 7)), (32, 16, 2, 1, (2, 3, 5, 7)),
+                                           (8, 8, 1, 0, (1, 1, 9, 33)), (64, 16, 2, 0, (2, 2, 6, 10)),
+                                           (8, 16, 2, 0, (1, 10, 2, 18))):
+        x, w = _conv_case(cin, cout, stride, tr, 3, shape=shape)
+        xb = torch.from_numpy(x).to(torch.bfloat16)
+        wb = torch.from_numpy(w).to(torch.bfloat16).float()
+        A.variables.packed_cache().clear()
+        raw, _ = conv3d_raw(xb.cuda(), 'rag', wb.cuda(), cout, stride, bool(tr), True)
+        xr = xb.float().numpy()
+        ref = onet.deconv3d(xr, wb.numpy()) if tr else onet.conv3d(xr, wb.numpy(), stride)
+        assert rel_err(npy(raw), ref) < 1e-4, (cin, cout, stride, tr, shape)
+
+
+def test_conv3d_argument_errors(A):
+    from atvsnet_b200.network import conv3d_raw
+    x = torch.zeros(1, 3, 4, 4, 16, dtype=torch.bfloat16, device='cuda')
+    w = torch.zeros(3, 3, 3, 16, 32, device='cuda')
+    A.variables.packed_cache().clear()
+    with pytest.raises(RuntimeError, match='even'):
+        conv3d_raw(x, 'err', w, 32, 2, False, False)          # odd D with stride 2 on the TMA path
+    with pytest.raises(RuntimeError):
+        conv3d_raw(torch.zeros(1, 2, 2, 2, 12, device='cuda'), 'e2', torch.zeros(3, 3, 3, 12, 5, device='cuda'), 5, 1,
+                   False, False)                               # Cout=5 unsupported on the fp32 path
+
+
+def test_bn_relu_add(A):
+    from oracle import network as onet
+    from atvsnet_b200.network import bn_relu_add
+    rng = np.random.default_rng(4)
+    raw = (rng.standard_normal((1, 4, 6, 10, 16)) * 3 + 1).astype(np.float32)
+    s1 = rng.standard_normal(raw.shape).astype(np.float32)
+    s2 = rng.standard_normal(raw.shape).astype(np.float32)
+    flat = raw.reshape(-1, 16).astype(np.float64)
+    stats = torch.from_numpy(np.concatenate([flat.sum(0), (flat ** 2).sum(0)])).cuda()
+    plain, summ = bn_relu_add(cu(raw), stats, True, [cu(s1), cu(s2)], True, True, torch.float32)
+    ref = onet.relu(onet.batch_norm_train(raw))
+    assert rel_err(npy(plain), ref) < 1e-5
+    assert rel_err(npy(summ), ref + s1 + s2) < 1e-5
+    pb, sb = bn_relu_add(cu(raw), stats, True, [cu(s1).bfloat16()], True, True, torch.bfloat16)
+    assert rel_err(npy(pb), ref) < 1e-2 and rel_err(npy(sb), ref + s1) < 1e-2
+
+
+# ------------------------------------------------------------------ networks
+def test_cost_volume_reasoning_fp32_golden(A, golden, gweights):
+    A.variables.load_weights(gweights)
+    A.FLAGS.precision = 'fp32'
+    try:
+        prob, filt = A.cost_volume_reasoning(cu(golden['crm_in']), output_filtered_cost=True)
+        assert rel_err(npy(filt), golden['crm_filtered']) < 5e-4
+        assert rel_err(npy(prob), golden['crm_prob']) < 5e-4
+        only = A.cost_volume_reasoning(cu(golden['crm_in']), output_prob=False)
+        assert rel_err(npy(only), golden['crm_filtered_only']) < 5e-4
+        tower = A.StackedUNet_prob({'data': cu(golden['crm_in'])}, is_training=True, reuse=None)
+        for nm in ('conv_b0_1_0', 'conv_b0_0_1', 'conv_b0_3_1', 'conv_b0_4_0', 'conv_b0_6_0', 'conv_b1_0_0',
+                   'conv_b1_5_0'):
+            assert rel_err(npy(tower.get_output_by_name(nm)), golden['crm_' + nm]) < 5e-4, nm
+    finally:
+        A.FLAGS.precision = 'bf16'
+
+
+def test_cost_volume_reasoning_bf16(A, golden, gweights):
+    A.variables.load_weights(gweights)
+    A.FLAGS.precision = 'bf16'
+    prob, filt = A.cost_volume_reasoning(cu(golden['crm_in']), output_filtered_cost=True)
+    # 31 bf16 layers with batch-stat BN on tiny volumes: loose elementwise bound, tight on average
+    e = np.abs(npy(filt) - golden['crm_filtered'])
+    assert e.mean() < 0.03 * np.abs(golden['crm_filtered']).mean() + 0.03
+    e = np.abs(npy(prob) - golden['crm_prob'])
+    assert e.mean() < 0.05 * np.abs(golden['crm_prob']).std()
+
+
+def test_attention_aggregation(A, golden, gweights):
+    A.variables.load_weights(gweights)
+    xs = golden['aam_in']
+    A.FLAGS.precision = 'fp32'
+    try:
+        keep = A.cost_volume_aggregation(cu(xs), keepchannel=True)
+        assert rel_err(npy(keep), golden['aam1_keep']) < 2e-5
+        assert rel_err(npy(A.cost_volume_aggregation(cu(xs), keepchannel=False)), golden['aam1_prob']) < 2e-5
+        assert rel_err(npy(A.cost_volume_aggregation_refine(cu(xs), keepchannel=True)), golden['aam2_keep']) < 2e-5
+        assert rel_err(npy(A.output_conv(cu(golden['aam1_keep']))), golden['outconv']) < 2e-5
+        assert rel_err(npy(A.output_conv_refine(cu(golden['aam1_keep']))), golden['outconv_refine']) < 2e-5
+        # list-of-views input == stacked (B,D,H,W,C,N) input
+        lst = [cu(xs[..., i]) for i in range(xs.shape[-1])]
+        assert torch.equal(A.cost_volume_aggregation(lst, keepchannel=True), keep)
+        # single view: softmax over one view is 1 -> output == input
+        one = A.cost_volume_aggregation(cu(xs[..., :1]), keepchannel=True)
+        assert rel_err(npy(one), xs[..., 0]) < 1e-6
+    finally:
+        A.FLAGS.precision = 'bf16'
+    keepb = A.cost_volume_aggregation(cu(xs), keepchannel=True)
+    assert rel_err(npy(keepb), golden['aam1_keep']) < 2e-2
+
+
+def test_prob2depth(A, golden):
+    from oracle import model as om
+    vol, ds, di = golden['p2d_vol'], golden['p2d_start'], golden['p2d_interval']
+    est, pm = A.prob2depth(cu(vol), 16, cu(ds), cu(di), out_prob_map=True)
+    assert rel_err(npy(est), golden['p2d_est']) < 2e-6
+    assert (np.abs(npy(pm) - golden['p2d_prob']) > 1e-5).mean() < 1e-3
+    e, eu, p, pu = A.prob2depth_upsample(cu(vol), 16, cu(ds), cu(di), out_prob_map=True)
+    assert eu.shape == (1, 40, 48, 1)
+    assert rel_err(npy(eu), golden['p2d_est_up']) < 2e-6
+    assert (np.abs(npy(pu) - golden['p2d_prob_up']) > 1e-5).mean() < 2e-3
+    # peaked volume -> estimate = that plane's depth; uniform volume -> mid-range
+    D = 32
+    v = np.full((1, D, 4, 5), 30.0, np.float32)
+    v[0, 7] = -30.0
+    est = npy(A.prob2depth(cu(v), D, cu(np.float32([1.0])), cu(np.float32([0.5]))))
+    assert np.allclose(est, 1.0 + 7 * 0.5, rtol=1e-6)
+    est = npy(A.prob2depth(cu(np.zeros((1, D, 4, 5), np.float32)), D, cu(np.float32([1.0])), cu(np.float32([0.5]))))
+    assert np.allclose(est, 1.0 + 0.5 * (D - 1) / 2, rtol=1e-5)
+    # batch of 2 with different ranges
+    rng = np.random.default_rng(0)
+    vb = rng.standard_normal((2, 12, 6, 7)).astype(np.float32)
+    dsb, dib = np.float32([0.5, 2.0]), np.float32([0.1, 0.3])
+    assert rel_err(npy(A.prob2depth(cu(vb), 12, cu(dsb), cu(dib))), om.prob2depth(vb, 12, dsb, dib)) < 2e-6
+
+
+# ------------------------------------------------------------------ end to end (stage I + II)
+def _e2e_inputs(A, D=16, h=16, w=24, nv=3, seed=3):
+    cams = A.synthetic.orbit_cams(nv, h, w, D)[None]
+    feats = A.synthetic.smooth_features(nv, h, w, 32, seed=seed)[None]
+    weights = A.variables.synthetic_weights(seed=11, logit_gain=2.0)
+    return cams, feats, weights
+
+
+def test_tvsnet_base_siamese_fp32(A):
+    from oracle import model as om
+    cams, feats, weights = _e2e_inputs(A)
+    A.variables.load_weights(weights)
+    A.FLAGS.precision = 'fp32'
+    try:
+        ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
+        d, p, f, dv = A.TVSNet_base_siamese(cu(feats), cu(cams), 16, cu(ds), cu(di), view_i=2)
+        do, po, fo, dvo = om.TVSNet_base_siamese(feats, cams, 16, ds, di, 2, weights)
+        assert rel_err(npy(f), fo) < 5e-4 and rel_err(npy(p), po) < 5e-4
+        rng_ = 15 * float(di[0])
+        assert np.abs(npy(d) - do).max() < 1e-3 * rng_ and np.abs(npy(dv) - dvo).max() < 1e-3 * rng_
+    finally:
+        A.FLAGS.precision = 'bf16'
+
+
+def test_multiview_pipeline_fp32_and_bf16(A):
+    from oracle import model as om
+    cams, feats, weights = _e2e_inputs(A)
+    A.variables.load_weights(weights)
+    ref = om.run_multiview_stage12(feats, cams, 16, weights, siamese=True)
+    rng_ = 15 * float(cams[0, 0, 1, 3, 1])
+    A.FLAGS.precision = 'fp32'
+    try:
+        out = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
+    finally:
+        A.FLAGS.precision = 'bf16'
+    assert rel_err(npy(out['cost_volume_agg']), ref['cost_volume_agg']) < 1e-3
+    assert np.abs(npy(out['depth']) - ref['depth_agg_init']).max() < 1e-3 * rng_
+    assert np.abs(npy(out['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * rng_
+    for a, b in zip(out['depth_views'], ref['depth_views']):
+        assert np.abs(npy(a) - b).max() < 1e-3 * rng_
+    # bf16 tensor-core path: mean absolute depth error <= 0.1 % of the depth range
+    outb = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
+    mae = np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_
+    assert mae < 1e-3, mae
+    # the softmax over depth must be peaked enough for that bound to mean something
+    p = torch.softmax(-torch.from_numpy(ref['prob_volume_agg']), dim=1)
+    assert p.max(dim=1).values.mean() > 2.0 / 16

@@ -1,0 +1,119 @@
+"""CPU: host-side logic of the product package that needs no device - variable naming,
+synthetic generators, view sharding, graph recording / fusion plan - and the world_size-2
+gloo check of the sharded attention combine."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import atvsnet_b200 as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_variable_names_match_checkpoint_convention(gweights):
+    w = A.variables.synthetic_weights(seed=1)
+    conv_like = {k: v.shape for k, v in w.items() if 'batch_normalization' not in k}
+    assert set(conv_like) == set(gweights)
+    for k in gweights:
+        assert conv_like[k] == gweights[k].shape, k
+    assert w['conv_b0_1_0/conv3d/kernel'].shape == (3, 3, 3, 64, 16)
+    assert w['conv_b1_4_0/conv3d_transpose/kernel'].shape == (3, 3, 3, 32, 64)       # [.., Cout, Cin]
+    assert w['conv_b2_6_2/kernel'].shape == (3, 3, 3, 8, 1)
+    assert w['attention_aggregate/attention_activation/weight_shared'].shape == (3, 3, 3, 8, 8)
+    n_params = sum(v.size for k, v in w.items() if k.startswith('conv_b') and 'batch_normalization' not in k)
+    assert n_params == 912600
+    assert 'conv_b0_1_0/batch_normalization/moving_mean' in w                          # restored but never read (F4)
+
+
+def test_flags_defaults_follow_reference():
+    assert A.FLAGS.max_d == 128 and A.FLAGS.view_num == 5 and A.FLAGS.batch_size == 1
+    assert A.FLAGS.inverse_depth is True and A.FLAGS.sample_scale == 0.25
+
+
+def test_orbit_rig_and_features():
+    cams = A.synthetic.orbit_cams(5, 128, 160, 128)
+    assert cams.shape == (5, 2, 4, 4) and cams.dtype == np.float32
+    assert np.allclose(cams[0, 0], np.eye(4))
+    for i in range(5):
+        R = cams[i, 0, :3, :3].astype(np.float64)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+        # every camera looks at the pivot: it projects to the principal point
+        P = R @ np.array([0, 0, 5.0]) + cams[i, 0, :3, 3]
+        assert np.allclose(P, [0, 0, 5.0], atol=1e-5)
+    assert np.isclose(cams[0, 1, 3, 0], 0.05) and np.isclose(cams[0, 1, 3, 1], 0.4224 / 128)
+    f = A.synthetic.smooth_features(2, 16, 24, 32, seed=0)
+    assert f.shape == (2, 16, 24, 32) and abs(f.mean()) < 1e-3 and abs(f.std() - 1) < 1e-3
+    assert np.array_equal(f, A.synthetic.smooth_features(2, 16, 24, 32, seed=0))
+
+
+def test_shard_views():
+    assert A.pipeline.shard_views(9, 0, 4) == [1, 5]
+    assert A.pipeline.shard_views(9, 3, 4) == [4, 8]
+    got = sorted(v for r in range(8) for v in A.pipeline.shard_views(9, r, 8))
+    assert got == list(range(1, 9))
+    assert A.pipeline.shard_views(5, 0, 1) == [1, 2, 3, 4]
+
+
+def test_graph_recording_matches_reference_layer_names():
+    t = A.StackedUNet_prob({'data': torch.zeros(1, 8, 8, 8, 64)})      # recording only: nothing runs yet
+    names = list(t.nodes)
+    convs = [n for n in names if t.nodes[n].kind in ('conv_bn', 'deconv_bn', 'conv')]
+    assert len(convs) == 31
+    assert names[-1] == 'conv_b2_6_2' and t.nodes['conv_b2_6_2'].inputs == ['conv_b2_6_1']
+    assert t.nodes['conv_b1_4_1'].inputs == ['conv_b1_4_0', 'conv_b1_2_1', 'conv_b0_2_1']
+    assert t.nodes['conv_b2_5_1'].inputs == ['conv_b2_5_0', 'conv_b2_1_1', 'conv_b0_1_1']
+    assert t.nodes['conv_b1_1_1_concat'].inputs == ['conv_b1_1_0', 'conv_b0_5_0']
+    assert t.nodes['conv_b0_4_0'].params == dict(filters=32, stride=2, relu=True)
+    with pytest.raises(KeyError):
+        t.feed('no_such_layer')
+    u = A.StackedUNet({'data': torch.zeros(1, 8, 8, 8, 64)})
+    assert list(u.nodes)[-1] == 'conv_b2_6_1'
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from gen_common import golden_weights
+    from oracle import network as onet
+    w = golden_weights(7)
+    rng = np.random.default_rng(42)
+    xs = rng.standard_normal((1, 4, 6, 6, 8, 5)).astype(np.float32)          # 5 source views
+    mine = [v - 1 for v in A.pipeline.shard_views(6, rank, world)]
+    wu = w['attention_aggregate/attention_activation/weight_unique']
+    ws = w['attention_aggregate/attention_activation/weight_shared']
+    # local logits l_n = relu(conv_u x_n) - relu(conv_s x_n): the +sum_m s_m term cancels in the softmax
+    l = [torch.from_numpy(onet.relu(onet.conv3d(xs[..., n], wu)) - onet.relu(onet.conv3d(xs[..., n], ws)))
+         for n in mine]
+    lmax = torch.stack(l).max(dim=0).values
+    dist.all_reduce(lmax, op=dist.ReduceOp.MAX)
+    e = [torch.exp(v - lmax) for v in l]
+    num = sum(ei * torch.from_numpy(xs[..., n]) for ei, n in zip(e, mine))
+    den = sum(e)
+    nd = torch.cat([num, den], dim=-1)
+    dist.all_reduce(nd, op=dist.ReduceOp.SUM)
+    out = (nd[..., :8] / nd[..., 8:]).numpy()
+    if rank == 0:
+        ref = onet.AttAggregation_keepchannel({'data': xs}, w).get_output()
+        q.put(float(np.abs(out - ref).max() / np.abs(ref).max()))
+    dist.destroy_process_group()
+
+
+def test_sharded_attention_combine_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err < 1e-5, err
