@@ -19,6 +19,7 @@ SOURCES = {
     "geom.cu": ["--fmad=false"],
     "net_fp32.cu": [],
     "conv_tc.cu": [],
+    "conv_ring.cu": [],
 }
 
 

@@ -1,6 +1,7 @@
 // api.cu - version / error string / device query of the C ABI (include/atvs.h).
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -14,3 +15,7 @@ void atvs_set_error(const char* fmt, ...) {
 extern "C" int atvs_version(void) { return 100; }
 extern "C" const char* atvs_last_error(void) { return g_err; }
 extern "C" int atvs_device_sm_count(void) { return atvs_num_sms(); }
+
+static std::atomic<long long> g_launches{0};
+void atvs_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long atvs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -26,7 +26,12 @@ void atvs_set_error(const char* fmt, ...);
         }                                                                             \
     } while (0)
 
-#define ATVS_LAUNCH_CHECK()  ATVS_CUDA(cudaPeekAtLastError())
+void atvs_count_launch();
+#define ATVS_LAUNCH_CHECK()              \
+    do {                                 \
+        atvs_count_launch();             \
+        ATVS_CUDA(cudaPeekAtLastError()); \
+    } while (0)
 
 static inline int atvs_num_sms() {
     static int n = 0;

@@ -1,0 +1,20 @@
+// conv_ring.cuh - interface of the halo-ring stride-1 convolution kernel (conv_ring.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define RING_HD __host__ __device__
+#else
+#define RING_HD
+#endif
+
+// K=16 MMA steps per output tile: 27 taps x Cin/16, or 3 planes x 5 tap pairs for Cin = 8
+RING_HD static inline int ring_nsteps(int Cin) { return Cin >= 16 ? 27 * (Cin / 16) : 15; }
+
+int ring_npad(int Cin, int Cout);
+size_t ring_weight_bytes(int Cin, int Cout);
+int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
+bool ring_applicable(int B, int D, int H, int W, int stride, int transposed);
+int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+              double* stats, cudaStream_t st);

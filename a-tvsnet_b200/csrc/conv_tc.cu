@@ -17,17 +17,15 @@
 //   the batch-statistics BN), double-buffered TMEM accumulators.
 //   Cin = 8 (16-byte rows): two taps form one K=16 step (no-swizzle core-matrix layout, the
 //   second tap's tile is the K-adjacent core matrix, LBO = tile size).
-#include "common.cuh"
+#include "tc_ptx.cuh"
 #include "conv_geom.cuh"
-#include <cuda.h>
-#include <mutex>
+#include "conv_ring.cuh"
 #include <cstring>
 
 namespace {
 
 constexpr int TC_MAX_TAPS = 28;
 constexpr int TC_THREADS = 192;
-constexpr uint32_t TC_SPIN_LIMIT = 1u << 27;   // bounded waits: trap instead of hanging the GPU
 
 struct TcTap {
     int map, ox, oy, oz;
@@ -50,115 +48,6 @@ struct alignas(64) TcMaps {
     CUtensorMap a[8];
     CUtensorMap w;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > TC_SPIN_LIMIT) {
-            printf("atvs conv_tc: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
-        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor (K-major operand tile):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;
-    return d;
-}
-
-// 32 values per lane -> lane L ends with the sum over the warp of v[L] (31 shuffles)
-__device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane) {
-#pragma unroll
-    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = upper ? v[i] : v[i + n / 2];
-            const float keep = upper ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
 
 template <int CIN>
 struct TcCfg {
@@ -309,68 +198,13 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             const bool valid = jx < p.Wj && jy < p.Hj && jz < p.Dj;
             mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            float v[NPAD];
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
-#pragma unroll
-            for (int c = 0; c < NPAD; c += 16) tc_ld16(taddr + c, v + c);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (valid) {
-                const size_t o = ((((size_t)b * p.Do + (jz * p.os + p.pz)) * p.Ho + (jy * p.os + p.py)) * p.Wo +
-                                  (jx * p.os + p.px)) * p.Cout + p.coff;
-                float* op = out + o;
-                if ((p.ncols & 3) == 0 && (p.Cout & 3) == 0) {
-#pragma unroll
-                    for (int c = 0; c < NPAD; c += 4)
-                        if (c < p.ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < NPAD; ++c)
-                        if (c < p.ncols) op[c] = v[c];
-                }
-            }
-            if (stats != nullptr) {
-                if (!valid) {
-#pragma unroll
-                    for (int c = 0; c < NPAD; ++c) v[c] = 0.f;
-                }
-                if (NPAD == 16) {
-                    float a[32];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        a[c] = v[c];
-                        a[16 + c] = v[c] * v[c];
-                    }
-                    run[0] += warp_transpose_reduce32(a, lane);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < NPAD / 32; ++h) {
-                        float q[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) q[c] = v[h * 32 + c] * v[h * 32 + c];
-                        run[2 * h + 1] += warp_transpose_reduce32(q, lane);
-                        run[2 * h] += warp_transpose_reduce32(v + h * 32, lane);
-                    }
-                }
-            }
+            const size_t o = valid ? ((((size_t)b * p.Do + (jz * p.os + p.pz)) * p.Ho + (jy * p.os + p.py)) * p.Wo +
+                                      (jx * p.os + p.px)) * p.Cout + p.coff : 0;
+            epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + o, p.ncols,
+                                (p.ncols & 3) == 0 && (p.Cout & 3) == 0, stats != nullptr, run);
         }
-        if (stats != nullptr) {
-            if (NPAD == 16) {
-                const int c = lane & 15;
-                if (c < p.ncols) atomicAdd(&stats[(lane < 16 ? 0 : p.Cout) + p.coff + c], (double)run[0]);
-            } else {
-#pragma unroll
-                for (int h = 0; h < NPAD / 32; ++h) {
-                    const int c = h * 32 + lane;
-                    if (c < p.ncols) {
-                        atomicAdd(&stats[p.coff + c], (double)run[2 * h]);
-                        atomicAdd(&stats[p.Cout + p.coff + c], (double)run[2 * h + 1]);
-                    }
-                }
-            }
-        }
+        if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
     }
     tc_fence_before();
     __syncthreads();
@@ -421,23 +255,6 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cin, int Cout, i
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    });
-    return fn;
-}
-
 CUtensorMapSwizzle swizzle_for(int cin) {
     return cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
          : cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -486,7 +303,17 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
     size_t elems = 0;
     const int ncls = transposed ? 8 : 1;
     for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
-    return elems * 2;
+    size_t bytes = (elems * 2 + 255) & ~(size_t)255;          // per-tap TMA image
+    if (!transposed) bytes += ring_weight_bytes(Cin, Cout);    // halo-ring image (stride-1 convolutions)
+    return bytes;
+}
+
+static size_t tap_image_bytes(int Cin, int Cout, int transposed) {
+    const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
+    size_t elems = 0;
+    const int ncls = transposed ? 8 : 1;
+    for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
+    return (elems * 2 + 255) & ~(size_t)255;
 }
 
 extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed, void* wpacked,
@@ -502,6 +329,8 @@ extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cou
     k_pack_weights<<<blocks, 128, 0, (cudaStream_t)stream>>>(kernel, Cin, Cout, transposed, sp.npad, sp.nslabs, ncls,
                                                             (__nv_bfloat16*)wpacked);
     ATVS_LAUNCH_CHECK();
+    if (!transposed)
+        return ring_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
     return 0;
 }
 
@@ -525,6 +354,9 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
         return ATVS_E_UNSUP;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (ring_applicable(B, D, H, W, stride, transposed))
+        return ring_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
+                         stats, st);
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     const int ncls = transposed ? 8 : 1;
     const int tps = (Cin == 8) ? 2 : 1;

@@ -465,6 +465,7 @@ extern "C" int atvs_homography_warping_by_depth(const float* image, const float*
     float* mv = nullptr;
     ATVS_CUDA(cudaMallocAsync(&mv, sizeof(float) * 12 * B, st));
     k_bydepth_setup<<<(B + 63) / 64, 64, 0, st>>>(left_cam, right_cam, B, mv);
+    ATVS_LAUNCH_CHECK();
     int rc = launch_warp(image, mv, depth_image, inverse_depth, true, B, H, W, C, method, out, mask, st);
     ATVS_CUDA(cudaFreeAsync(mv, st));
     return rc;

@@ -22,6 +22,10 @@ from .flags import FLAGS
 
 BN_EPS = 1e-3   # tf.layers.batch_normalization default (network.py:206)
 
+# measurement hook (bench.py): when set to (predicate, sink), conv launches whose weight key
+# satisfies predicate(key) are bracketed by CUDA events on the launching stream.
+PROFILE = None
+
 
 def act_dtype():
     return torch.bfloat16 if FLAGS.precision == 'bf16' else torch.float32
@@ -60,6 +64,10 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats):
         od, oh, ow = -(-D // stride), -(-H // stride), -(-W // stride)
     raw = torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
     stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+    prof = PROFILE is not None and PROFILE[0](wkey)
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     if x.dtype == torch.float32:
         L.call("atvs_conv3d_fp32", L.ptr(x), L.ptr(w), B, D, H, W, cin, cout, stride, int(transposed),
                L.ptr(raw), L.ptr(stats), L.stream())
@@ -67,6 +75,9 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats):
         pk = _packed_weight(wkey, w, cin, cout, int(transposed))
         L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
                L.ptr(raw), L.ptr(stats), L.stream())
+    if prof:
+        e1.record()
+        PROFILE[1].append((wkey, e0, e1, raw.numel() // cout, cin, cout))
     return raw, stats
 
 

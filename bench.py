@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py - depth maps / s of the A-TVSNet inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg3|cfg4] [--precision bf16|fp32] [--no-graph]
+
+One "step" = one depth map of the workload: stage I (TVSNet_base_siamese: fused warp +
+cost volume -> 3-D CNN regularisation -> soft-argmin, forward and reverse direction) for
+every source view, stage II (attention aggregation -> output conv) and the final x4
+upsampled soft-argmin, i.e. example.py:144-158 + :109 with features in.  The 2-D feature
+extractor and the refinement stages III/IV are outside the current scope.
+
+N = 1   : cfg2 (1 ref + 4 src, 640x512 images -> 128x160 features, D = 128).
+N > 1   : independent reference frames data-parallel, one frame stream per rank, no data-path
+          collective ("scaling": "weak");  --workload cfg3 instead shards the 8 source views
+          of ONE 1920x1056, D=256 frame over the ranks with a max + sum NCCL all-reduce.
+--impl reference : the CPU oracle (NumPy/torch-CPU restatement of the TF-1.5 reference, which
+          cannot be installed offline) on the host cores, each step a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_views, H, W, D)   image resolution; features are H/4 x W/4 x 32
+    'cfg2': (5, 512, 640, 128),
+    'cfg3': (9, 1056, 1920, 256),
+    'cfg4': (5, 512, 640, 192),
+}
+METRIC = "depth maps/sec"
+CRM_MAC_PER_VOXEL = 29592
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(workload, frame_seed):
+    import atvsnet_b200 as A
+    nv, H, W, D = WORKLOADS[workload]
+    h, w = H // 4, W // 4
+    cams = A.synthetic.orbit_cams(nv, h, w, D)[None]
+    feats = A.synthetic.smooth_features(nv, h, w, 32, seed=frame_seed)[None]
+    return feats, cams, D
+
+
+# ============================================================================ reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle port (TF 1.5 / py2.7 cannot be
+    installed offline).  Each step = the full stage I+II schedule on a D/8 slab of the planes."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    import atvsnet_b200 as A
+    from oracle import model as om
+    workload = args.workload or 'cfg2'
+    feats, cams, D = make_inputs(workload, 0)
+    Ds = max(8, D // 8)
+    weights = A.variables.synthetic_weights()
+    cores = torch.get_num_threads()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        om.run_multiview_stage12(feats, cams, Ds, weights, siamese=True)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = (Ds / float(D)) / t
+    nv, H, W, _ = WORKLOADS[workload]
+    sample = ("all %d source views, stages I+II, full %dx%d features, depth planes [0,%d) of %d; value = (%d/%d) / "
+              "seconds per step (cost is linear in D)" % (nv - 1, H // 4, W // 4, Ds, D, Ds, D))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "depth maps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: 1 ref + %d src, %dx%d, D=%d, features in" % (workload, nv - 1, W, H, D),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "depth maps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "depth maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ============================================================================ our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import atvsnet_b200 as A
+    from atvsnet_b200 import network as N
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    lib = A._lib.load()
+    A.FLAGS.precision = args.precision
+    workload = args.workload or 'cfg2'
+    sharded = workload == 'cfg3' and world > 1
+    group = dist.group.WORLD if sharded else None
+    A.variables.load_weights(A.variables.synthetic_weights(), device=dev)
+    feats, cams, D = make_inputs(workload, frame_seed=rank if not sharded else 0)
+    nv, H, W, _ = WORKLOADS[workload]
+    h, w = H // 4, W // 4
+    V = D * h * w
+
+    # pinned host buffers (end-to-end path) and resident device inputs (kernel path)
+    feats_h = torch.from_numpy(feats).pin_memory()
+    cams_h = torch.from_numpy(cams).pin_memory()
+    feats_d = torch.empty_like(feats_h, device=dev)
+    cams_d = torch.empty_like(cams_h, device=dev)
+    feats_d.copy_(feats_h)
+    cams_d.copy_(cams_h)
+    depth_h = torch.empty((1, H, W, 1), dtype=torch.float32).pin_memory()
+
+    def step():
+        return A.pipeline.run_multiview(feats_d, cams_d, D, siamese=True, upsample=True, group=group, rank=rank,
+                                        world=world)['depth_up']
+
+    # warm-up (eager): compiles nothing, but sets kernel attributes, packs weights, fills the allocator
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    n0 = lib.atvs_launch_count()
+    out = step()
+    torch.cuda.synchronize()
+    launches_per_step = lib.atvs_launch_count() - n0
+
+    use_graph = not args.no_graph and not sharded
+    graph = None
+    if use_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                out = step()
+        torch.cuda.current_stream().wait_stream(s)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return out
+        return step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = run_step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+
+    # ---------------- timed region 2: end to end from / to pinned host memory ----------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        feats_d.copy_(feats_h, non_blocking=True)
+        cams_d.copy_(cams_h, non_blocking=True)
+        res = run_step()
+        depth_h.copy_(res, non_blocking=True)
+    f1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_e2e = f0.elapsed_time(f1)
+    h2d = feats_h.numel() * 4 + cams_h.numel() * 4
+    d2h = depth_h.numel() * 4
+
+    # ---------------- dominant kernel, timed with CUDA events on its launch stream ----------------
+    roof = None
+    if args.precision == 'bf16':
+        sink = []
+        N.PROFILE = (lambda key: key == 'conv_b0_0_1/conv3d/kernel', sink)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        N.PROFILE = None
+        ts = [a.elapsed_time(b) for (_, a, b, _, _, _) in sink]
+        nvox, cin, cout = sink[0][3], sink[0][4], sink[0][5]
+        t_ms = float(np.mean(ts))
+        flops = 2.0 * 27 * cin * cout * nvox
+        pk = peaks()
+        ach = flops / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_conv3d_tc<64,16> (conv_b0_0_1: 64->8, stride 1, %d voxels)" % nvox,
+                "achieved": ach, "peak": pk['bf16_sustained'], "unit": "TFLOP/s", "frac": ach / pk['bf16_sustained'],
+                "traffic": None, "peak_source": pk['src'] + " (sustained bf16)", "ms_per_launch": t_ms,
+                "launches_timed": len(ts), "algorithmic_flops_per_launch": flops}
+
+    # max over ranks
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    maps_per_step = 1 if sharded else world
+    value = maps_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = maps_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    crm_passes = 2 * (nv - 1)
+    flops_step = 2.0 * CRM_MAC_PER_VOXEL * V * crm_passes + 2.0 * 2 * 27 * 64 * V * (nv - 1) + 2.0 * 216 * V
+    line = {
+        "metric": METRIC, "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == 'bf16' else "f32", "data": "synthetic",
+        "config": {"workload": "%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II "
+                               "+ x4 soft-argmin; FEM and refinement not included" % (workload, nv - 1, W, H, h, w, D),
+                   "frames_per_step": maps_per_step,
+                   "parallelism": ("source views sharded over %d ranks, NCCL max+sum all-reduce" % world) if sharded
+                   else ("dp%d: independent frames per rank, no collective" % world),
+                   "l2": "no explicit flush: every step streams > 3 GB of intermediate volumes (L2 = 126 MB)",
+                   "cuda_graph": graph is not None,
+                   "tensor_flops_per_step": flops_step,
+                   "tensor_tflops_whole_step": flops_step * maps_per_step * args.steps / (ms_total * 1e-3) / 1e12 / world},
+        "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+    }
+    if roof is not None:
+        line["roofline"] = roof
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(workload)
+    print(json.dumps(line))
+
+
+def cpu_baseline(workload):
+    """the oracle port timed on the host cores on a bounded sample (one source view, both
+    directions, D/8 planes)."""
+    import torch
+    import atvsnet_b200 as A
+    from oracle import model as om
+    feats, cams, D = make_inputs(workload, 0)
+    nv = cams.shape[1]
+    Ds = max(8, D // 8)
+    weights = A.variables.synthetic_weights()
+    ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
+    om.TVSNet_base(feats[:, :2, :16, :16], cams, 8, ds, di, 1, weights)          # touch the code paths
+    t0 = time.perf_counter()
+    om.TVSNet_base_siamese(feats, cams, Ds, ds, di, 1, weights)
+    dt = time.perf_counter() - t0
+    # one depth map = (nv-1) such view passes at D/Ds times the planes (+ the aggregation, not sampled)
+    value = 1.0 / (dt * (nv - 1) * (D / float(Ds)))
+    return {"value": value, "unit": "depth maps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "stage I (siamese) for 1 of %d source views on depth planes [0,%d) of %d, full %s feature "
+                      "resolution, %.1f s; scaled by %d views x %d (linear in D); aggregation not sampled"
+                      % (nv - 1, Ds, D, workload, dt, nv - 1, D // Ds)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=None, choices=[None] + list(WORKLOADS))
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29511')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

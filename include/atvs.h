@@ -41,6 +41,7 @@ typedef void* atvs_stream_t;     /* cudaStream_t */
 int         atvs_version(void);                 /* major*10000 + minor*100 + patch        */
 const char* atvs_last_error(void);              /* thread-local, never NULL               */
 int         atvs_device_sm_count(void);         /* SMs of the current device (148 on B200) */
+long long   atvs_launch_count(void);            /* kernels launched by this library so far  */
 
 /* ---- get_homographies ------------------------------------------- homography_warping.py:179-227
  * left_cam/right_cam (B,2,4,4) f32, depth_start/depth_interval (B) f32 -> out (B,D,3,3) f32.

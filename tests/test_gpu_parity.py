@@ -218,6 +218,31 @@ def test_conv3d_bf16_ragged_and_batched(A):
         assert rel_err(npy(raw), ref) < 1e-4, (cin, cout, stride, tr, shape)
 
 
+RING_CASES = [(64, 8, (1, 8, 40, 104)), (8, 8, (1, 8, 40, 104)), (8, 1, (1, 9, 37, 101)), (8, 16, (2, 10, 40, 88)),
+              (16, 16, (1, 33, 37, 29)), (32, 32, (1, 8, 64, 64)), (64, 64, (1, 8, 64, 64)), (32, 64, (1, 6, 80, 72)),
+              (64, 16, (1, 40, 32, 32))]
+
+
+@pytest.mark.parametrize('cin,cout,shape', RING_CASES)
+def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
+    """large stride-1 volumes take the halo-ring kernel (every input plane staged once in smem)."""
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    assert shape[1] * shape[2] * shape[3] >= 32768
+    x, w = _conv_case(cin, cout, 1, 0, 7, shape=shape)
+    xb = torch.from_numpy(x).to(torch.bfloat16)
+    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    A.variables.packed_cache().clear()
+    raw, stats = conv3d_raw(xb.cuda(), 'ring_%d_%d' % (cin, cout), wb.cuda(), cout, 1, False, True)
+    torch.cuda.synchronize()
+    ref = onet.conv3d(xb.float().numpy(), wb.numpy(), 1)
+    assert rel_err(npy(raw), ref) < 1e-4
+    s = stats.cpu().numpy()
+    flat = ref.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(s[:cout], flat.sum(0), rtol=1e-3, atol=5e-2)
+    assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
+
+
 def test_conv3d_argument_errors(A):
     from atvsnet_b200.network import conv3d_raw
     x = torch.zeros(1, 3, 4, 4, 16, dtype=torch.bfloat16, device='cuda')
