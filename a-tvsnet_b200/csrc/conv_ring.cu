@@ -5,13 +5,15 @@
 //   work unit   = a column of output tiles (16 y x 8 x) over a z segment [z0, z0+zlen)
 //   ring slot   = one input z plane with halo: [Cin/8 chunks][18 y][10 x][8 channels] bf16
 //                 (no-swizzle K-major core-matrix layout: 8 consecutive x = one 8-row core
-//                 matrix, next y row = SBO, next 8-channel chunk = LBO), filled by Cin/8 TMA box
-//                 loads (out-of-bounds zero fill = 'SAME' padding);
+//                 matrix, next y row = SBO, next 8-channel chunk = LBO), filled by 4 producer
+//                 warps with 16-byte cp.async (zero fill outside the volume = 'SAME' padding;
+//                 TMA box loads with 16-byte rows measured ~6 cycles per row and were the
+//                 bottleneck), published to the async proxy with fence.proxy.async;
 //   one tile    = 27 taps x Cin/16 tcgen05.mma (M=128, N=16/32/64, K=16) whose A descriptors are
 //                 just shifted start addresses into three consecutive ring planes; a plane is
 //                 released (tcgen05.commit -> mbarrier) when the tile that last needs it retires.
 //   Cin = 8     : one K=16 step covers two taps of the same plane (LBO = distance of the taps).
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 epilogue, double-buffered TMEM.
+//   warps 0-3 producers | warp 4 MMA issuer | warps 5-8 epilogue, double-buffered TMEM.
 #include "tc_ptx.cuh"
 #include "conv_ring.cuh"
 #include <cstring>
@@ -19,9 +21,11 @@
 namespace {
 
 constexpr int RG_TY = 16, RG_TX = 8, RG_HH = 18, RG_WW = 10;
-constexpr int RG_KCH = RG_HH * RG_WW * 16;          // bytes TMA writes per 8-channel chunk plane (2880)
-constexpr int RG_KCH_PAD = (RG_KCH + 127) / 128 * 128;   // chunk plane pitch, 128-byte aligned for TMA
-constexpr int RG_THREADS = 192;
+constexpr int RG_NVOX = RG_HH * RG_WW;              // voxels of one halo plane (180)
+constexpr int RG_KCH_PAD = RG_NVOX * 16 + 16;       // pitch of one 8-channel chunk plane; +16 B keeps the
+                                                    // 8 chunk stores of a voxel on distinct banks
+constexpr int RG_PRODUCERS = 128;
+constexpr int RG_THREADS = 288;
 
 struct RingParams {
     int B, D, H, W;
@@ -35,8 +39,7 @@ struct RingParams {
 template <int CIN>
 struct RingCfg {
     static constexpr int NKC = CIN / 8;
-    static constexpr int SLOT_BYTES = NKC * RG_KCH_PAD;
-    static constexpr int TX_BYTES = NKC * RG_KCH;
+    static constexpr int SLOT_BYTES = (NKC * RG_KCH_PAD + 127) / 128 * 128;
 };
 
 struct Unit {
@@ -58,7 +61,7 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
 
 template <int CIN, int NPAD>
 __global__ void __launch_bounds__(RG_THREADS, 1)
-k_conv3d_ring(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ RingParams p,
+k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats) {
     using Cfg = RingCfg<CIN>;
     constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
@@ -82,7 +85,7 @@ k_conv3d_ring(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     const int R = p.nring;
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], RG_PRODUCERS);
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tfull[0], 1);
@@ -92,7 +95,7 @@ k_conv3d_ring(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -103,27 +106,51 @@ k_conv3d_ring(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            tma_prefetch_desc(&xmap);
+    if (warp < 4) {
+        // ===================== producers: global -> ring planes (cp.async, 16 B per op) =====================
+        const int ptid = threadIdx.x;
+        if (ptid == 0) {
             mbar_expect_tx(wbar, (uint32_t)p.wbytes);
             bulk_copy_g2s(wsm, wimg, (uint32_t)p.wbytes, wbar);
-            uint32_t cnt = 0;
-            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-                const Unit un = decode_unit(p, u);
-                for (int zi = un.z0 - 1; zi <= un.z0 + un.zlen; ++zi, ++cnt) {
-                    const uint32_t slot = cnt % R, par = (cnt / R) & 1;
-                    mbar_wait(&empty[slot], par ^ 1);
-                    mbar_expect_tx(&full[slot], (uint32_t)Cfg::TX_BYTES);
-                    uint8_t* dst = ring + (size_t)slot * Cfg::SLOT_BYTES;
-#pragma unroll
-                    for (int kc = 0; kc < Cfg::NKC; ++kc)
-                        tma_load_5d(dst + kc * RG_KCH_PAD, &xmap, kc * 8, un.x0 - 1, un.y0 - 1, zi, un.b, &full[slot]);
+        }
+        // up to G planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
+        // mbarrier arrive) once plane q+G-1 has been issued.  G <= R-2 keeps the ring deadlock-free.
+        const int G = (R >= 6) ? 4 : 2;
+        uint32_t cnt = 0, published = 0;
+        auto publish_upto = [&](uint32_t upto_excl, int keep) {
+            // wait until at most `keep` groups are pending, then publish planes [published, upto_excl)
+            if (keep >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+            else if (keep == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (; published < upto_excl; ++published) mbar_arrive(&full[published % R]);
+        };
+        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const Unit un = decode_unit(p, u);
+            for (int zi = un.z0 - 1; zi <= un.z0 + un.zlen; ++zi, ++cnt) {
+                const uint32_t slot = cnt % R, par = (cnt / R) & 1;
+                mbar_wait(&empty[slot], par ^ 1);
+                const bool zok = zi >= 0 && zi < p.D;
+                const __nv_bfloat16* zbase = x + (((size_t)un.b * p.D + (zok ? zi : 0)) * p.H) * p.W * CIN;
+                const uint32_t dst0 = smem_u32(ring + (size_t)slot * Cfg::SLOT_BYTES);
+#pragma unroll 4
+                for (int i = ptid; i < Cfg::NKC * RG_NVOX; i += RG_PRODUCERS) {
+                    const int c = i % Cfg::NKC, v = i / Cfg::NKC;
+                    const int yy = v / RG_WW, xx = v - yy * RG_WW;
+                    const int gy = un.y0 - 1 + yy, gx = un.x0 - 1 + xx;
+                    const bool ok = zok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+                    const __nv_bfloat16* src = ok ? zbase + ((size_t)gy * p.W + gx) * CIN + c * 8 : x;
+                    const uint32_t dst = dst0 + (uint32_t)(c * RG_KCH_PAD + v * 16);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
+                                 : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (cnt + 1 - published >= (uint32_t)G) publish_upto(cnt + 2 - G, G - 1);
             }
         }
-    } else if (warp == 1) {
+        if (published < cnt) publish_upto(cnt, 0);
+    } else if (warp == 4) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             mbar_wait(wbar, 0);
@@ -213,7 +240,7 @@ k_conv3d_ring(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -244,14 +271,14 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
 }
 
 template <int CIN, int NPAD>
-int launch_ring(const CUtensorMap& xmap, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
+int launch_ring(const __nv_bfloat16* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
                 size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_ring<CIN, NPAD><<<grid, RG_THREADS, smem, st>>>(xmap, p, wimg, out, stats);
+    k_conv3d_ring<CIN, NPAD><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -284,26 +311,6 @@ bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
 
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
               double* stats, cudaStream_t st) {
-    EncodeTiledFn encode = get_encode();
-    if (!encode) {
-        atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled entry point not available");
-        return ATVS_E_UNSUP;
-    }
-    CUtensorMap xmap;
-    {
-        cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-        cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
-                                 (cuuint64_t)D * H * W * Cin * 2};
-        cuuint32_t box[5] = {8, (cuuint32_t)RG_WW, (cuuint32_t)RG_HH, 1, 1};
-        cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_bf16), dims, strides, box, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            atvs_set_error("atvs_conv3d_bf16(ring): cuTensorMapEncodeTiled failed: %d", (int)r);
-            return (int)r;
-        }
-    }
     const int npad = ring_npad(Cin, Cout);
     const int nslabs = (Cout + npad - 1) / npad;
     const int sms = atvs_num_sms();
@@ -326,7 +333,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         p.nunits = cols * p.nZS;
     }
     p.wbytes = ring_nsteps(Cin) * 2 * npad * 16;
-    const size_t slot = (size_t)(Cin / 8) * RG_KCH_PAD;
+    const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
     const size_t budget = 208 * 1024;
     int nring = (int)((budget - (size_t)((p.wbytes + 127) & ~127)) / slot);
     if (nring > 8) nring = 8;
@@ -342,7 +349,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         p.ncols = (Cout - p.coff < npad) ? Cout - p.coff : npad;
         const uint8_t* wi = (const uint8_t*)wimg + (size_t)slab * p.wbytes;
         int rc = 0;
-#define RG_CASE(CI, NP) if (Cin == CI && npad == NP) rc = launch_ring<CI, NP>(xmap, p, wi, raw_out, stats, smem, grid, st); else
+#define RG_CASE(CI, NP) if (Cin == CI && npad == NP) rc = launch_ring<CI, NP>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, smem, grid, st); else
         RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(8, 64) RG_CASE(16, 16) RG_CASE(16, 32) RG_CASE(16, 64)
         RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(32, 64) RG_CASE(64, 16) RG_CASE(64, 32)
         {

@@ -36,7 +36,10 @@ struct TcParams {
     TcTap taps[TC_MAX_TAPS];
     int B, Dj, Hj, Wj;         // iteration space (tile origins live here)
     int Do, Ho, Wo;            // full output extent
-    int os, pz, py, px;        // out = j*os + p
+    int os;                    // out = j*os + parity
+    int ncls;                  // parity classes merged in this launch (1 for convolutions, 8 for deconv)
+    int cls_tap0[9];           // class c uses taps [cls_tap0[c], cls_tap0[c+1])
+    int cls_par[8][3];         // output parity (z, y, x) of class c
     int ltd, lth, ltw;         // log2 of the brick dims (TD*TH*TW == 128)
     int nTD, nTH, nTW;
     int Cout, coff, ncols;     // real channel count, slab offset, real columns in this slab
@@ -105,8 +108,8 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nsteps = p.ntaps / Cfg::TPS;
     const int tiles_per_b = p.nTD * p.nTH * p.nTW;
+    const long long nwork = p.ntiles * p.ncls;      // work item = (class, tile), class-major
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -116,7 +119,10 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             for (int t = 0; t < p.ntaps; ++t) tma_load_2d(wsm + (size_t)t * WTAP_BYTES, &tm.w, 0, t * NPAD, wbar);
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+                const int cls = (int)(wk / p.ntiles);
+                const long long tile = wk % p.ntiles;
+                const int t0 = p.cls_tap0[cls], nsteps = (p.cls_tap0[cls + 1] - t0) / Cfg::TPS;
                 const int b = (int)(tile / tiles_per_b);
                 int r = (int)(tile % tiles_per_b);
                 const int jx0 = (r % p.nTW) << p.ltw;
@@ -129,7 +135,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                     uint8_t* dst = asmem + (size_t)stage * Cfg::STAGE_BYTES;
 #pragma unroll
                     for (int q = 0; q < Cfg::TPS; ++q) {
-                        const TcTap& tp = p.taps[s * Cfg::TPS + q];
+                        const TcTap& tp = p.taps[t0 + s * Cfg::TPS + q];
                         tma_load_5d(dst + q * Cfg::TILE_BYTES, &tm.a[tp.map], 0, jx0 + tp.ox, jy0 + tp.oy, jz0 + tp.oz, b,
                                     &full[stage]);
                     }
@@ -150,7 +156,9 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             int stage = 0;
             uint32_t phase = 0;
             long long it = 0;
-            for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x, ++it) {
+                const int cls = (int)(wk / p.ntiles);
+                const int t0 = p.cls_tap0[cls], nsteps = (p.cls_tap0[cls + 1] - t0) / Cfg::TPS;
                 const int acc = (int)(it & 1);
                 mbar_wait(&tempty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 tc_fence_after();
@@ -159,7 +167,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t abase = smem_u32(asmem + (size_t)stage * Cfg::STAGE_BYTES);
-                    const uint32_t bbase = smem_u32(wsm + (size_t)s * Cfg::TPS * WTAP_BYTES);
+                    const uint32_t bbase = smem_u32(wsm + (size_t)(t0 + s * Cfg::TPS) * WTAP_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
                         const uint64_t ad = make_desc(abase + ks * 32, a_lbo, Cfg::SBO, Cfg::LAYOUT);
@@ -187,7 +195,10 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
 #pragma unroll
         for (int i = 0; i < NRED; ++i) run[i] = 0.f;
         long long it = 0;
-        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x, ++it) {
+            const int cls = (int)(wk / p.ntiles);
+            const long long tile = wk % p.ntiles;
+            const int pz = p.cls_par[cls][0], py = p.cls_par[cls][1], px = p.cls_par[cls][2];
             const int acc = (int)(it & 1);
             const int b = (int)(tile / tiles_per_b);
             int r = (int)(tile % tiles_per_b);
@@ -199,8 +210,8 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
-            const size_t o = valid ? ((((size_t)b * p.Do + (jz * p.os + p.pz)) * p.Ho + (jy * p.os + p.py)) * p.Wo +
-                                      (jx * p.os + p.px)) * p.Cout + p.coff : 0;
+            const size_t o = valid ? ((((size_t)b * p.Do + (jz * p.os + pz)) * p.Ho + (jy * p.os + py)) * p.Wo +
+                                      (jx * p.os + px)) * p.Cout + p.coff : 0;
             epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + o, p.ncols,
                                 (p.ncols & 3) == 0 && (p.Cout & 3) == 0, stats != nullptr, run);
         }
@@ -364,14 +375,20 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
     const char* xb = (const char*)x_bf16;
     size_t wofs = 0;   // element offset into the packed weights
 
-    for (int cls = 0; cls < ncls; ++cls) {
-        const ConvGeom g = make_conv_geom(B, D, H, W, Cin, Cout, stride, transposed, cls);
+    // transposed convolutions: the 8 output-parity classes share the input, the tile grid and (when the
+    // weights of all 27 taps fit one slab) the resident weight image -> ONE launch walks all classes.
+    const bool merge = transposed && sp.nslabs == 1;
+    const int ngroups = merge ? 1 : ncls;
+    for (int grp = 0; grp < ngroups; ++grp) {
+        const int c0 = merge ? 0 : grp, c1 = merge ? ncls : grp + 1;
+        const ConvGeom g = make_conv_geom(B, D, H, W, Cin, Cout, stride, transposed, c0);
         TcParams p;
         memset(&p, 0, sizeof(p));
         p.B = B; p.Dj = g.Dj; p.Hj = g.Hj; p.Wj = g.Wj;
         p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
-        p.os = g.os; p.pz = g.p[0]; p.py = g.p[1]; p.px = g.p[2];
+        p.os = g.os;
         p.Cout = Cout;
+        p.ncls = c1 - c0;
         // brick shape: 128 voxels, minimise padded volume, prefer a wide x extent
         {
             static const int opts[][3] = {{2, 8, 8}, {1, 8, 16}, {4, 4, 8}, {2, 4, 16}, {1, 4, 32}, {4, 8, 4},
@@ -391,23 +408,29 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
             p.ntiles = (long long)B * p.nTD * p.nTH * p.nTW;
         }
         const int TD = 1 << p.ltd, TH = 1 << p.lth, TW = 1 << p.ltw;
-        // taps
+        // taps of every class in the group, class-major (the packed weights follow the same order)
         int nt = 0;
-        for (int tz = 0; tz < g.nt[0]; ++tz)
-            for (int ty = 0; ty < g.nt[1]; ++ty)
-                for (int tx = 0; tx < g.nt[2]; ++tx) {
-                    const int off[3] = {g.koff[0][tz], g.koff[1][ty], g.koff[2][tx]};
-                    TcTap& t = p.taps[nt++];
-                    if (g.s_in == 2) {
-                        int par[3], ho[3];
-                        for (int a = 0; a < 3; ++a) { par[a] = off[a] & 1; ho[a] = (off[a] - par[a]) / 2; }
-                        t.map = (par[0] * 2 + par[1]) * 2 + par[2];
-                        t.oz = ho[0]; t.oy = ho[1]; t.ox = ho[2];
-                    } else {
-                        t.map = 0; t.oz = off[0]; t.oy = off[1]; t.ox = off[2];
+        for (int cls = c0; cls < c1; ++cls) {
+            const ConvGeom gc = make_conv_geom(B, D, H, W, Cin, Cout, stride, transposed, cls);
+            p.cls_tap0[cls - c0] = nt;
+            for (int a = 0; a < 3; ++a) p.cls_par[cls - c0][a] = gc.p[a];
+            for (int tz = 0; tz < gc.nt[0]; ++tz)
+                for (int ty = 0; ty < gc.nt[1]; ++ty)
+                    for (int tx = 0; tx < gc.nt[2]; ++tx) {
+                        const int off[3] = {gc.koff[0][tz], gc.koff[1][ty], gc.koff[2][tx]};
+                        TcTap& t = p.taps[nt++];
+                        if (gc.s_in == 2) {
+                            int par[3], ho[3];
+                            for (int a = 0; a < 3; ++a) { par[a] = off[a] & 1; ho[a] = (off[a] - par[a]) / 2; }
+                            t.map = (par[0] * 2 + par[1]) * 2 + par[2];
+                            t.oz = ho[0]; t.oy = ho[1]; t.ox = ho[2];
+                        } else {
+                            t.map = 0; t.oz = off[0]; t.oy = off[1]; t.ox = off[2];
+                        }
                     }
-                }
-        while (nt % tps) { p.taps[nt] = p.taps[nt - 1]; ++nt; }   // phantom tap: zero weights
+            while (nt % tps) { p.taps[nt] = p.taps[nt - 1]; ++nt; }   // phantom tap: zero weights
+        }
+        p.cls_tap0[c1 - c0] = nt;
         p.ntaps = nt;
 
         // tensor maps over the input
@@ -452,17 +475,18 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
             const size_t wbytes = ((size_t)nt * sp.npad * Cin * 2 + 1023) & ~(size_t)1023;
             const size_t stage_bytes = (size_t)128 * Cin * 2 * tps;
             const size_t budget = 200 * 1024;
-            int nst = (int)((budget - wbytes) / stage_bytes);
-            if (nst > 8) nst = 8;
-            if (nst > nt / tps) nst = nt / tps > 2 ? nt / tps : 2;
-            if (nst < 2) {
+            if (wbytes + 2 * stage_bytes > budget) {
                 atvs_set_error("atvs_conv3d_bf16: weights do not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
                 return ATVS_E_UNSUP;
             }
+            int nst = (int)((budget - wbytes) / stage_bytes);
+            if (nst > 8) nst = 8;
+            if (nst > nt / tps) nst = nt / tps > 2 ? nt / tps : 2;
             p.nstages = nst;
             const size_t smem = 1024 + wbytes + (size_t)nst * stage_bytes + (2 * nst + 5) * 8 + 16;
             const int sms = atvs_num_sms();
-            const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+            const long long nwork = p.ntiles * p.ncls;
+            const int grid = (int)(nwork < sms ? nwork : sms);
             int rc = 0;
 #define TC_CASE(CI, NP) if (Cin == CI && sp.npad == NP) rc = launch_tc<CI, NP>(maps, p, raw_out, stats, smem, grid, st); else
             TC_CASE(8, 16) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32) TC_CASE(32, 64)

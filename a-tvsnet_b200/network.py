@@ -55,15 +55,21 @@ def _packed_weight(key, w, cin, cout, transposed):
     return cache[key]
 
 
-def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats):
-    """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)]."""
+def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None):
+    """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)].
+    ``stats_buf``: pre-zeroed fp64 buffer of >= 2*Cout elements to accumulate the moments into."""
     B, D, H, W, cin = x.shape
     if transposed:
         od, oh, ow = 2 * D, 2 * H, 2 * W
     else:
         od, oh, ow = -(-D // stride), -(-H // stride), -(-W // stride)
     raw = torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
-    stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+    if not want_stats:
+        stats = None
+    elif stats_buf is not None:
+        stats = stats_buf[:2 * cout]
+    else:
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device)
     prof = PROFILE is not None and PROFILE[0](wkey)
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,6 +209,11 @@ class Network(object):
             if nodes[n].kind != 'input':
                 nodes[n].value = None
         dt = act_dtype()
+        # one zero-filled arena for the batch-norm moments of every conv_bn / deconv_bn layer
+        bn_nodes = [n for n in order if nodes[n].kind in ('conv_bn', 'deconv_bn')]
+        dev = next(v.value.device for v in nodes.values() if v.kind == 'input' and torch.is_tensor(v.value))
+        arena = torch.zeros((max(len(bn_nodes), 1), 128), dtype=torch.float64, device=dev)
+        arena_slot = {n: i for i, n in enumerate(bn_nodes)}
 
         def release(names):
             for i in names:
@@ -226,7 +237,7 @@ class Network(object):
                 transposed = node.kind == 'deconv_bn'
                 wname = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
                 raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
-                                        node.params['stride'], transposed, True)
+                                        node.params['stride'], transposed, True, arena[arena_slot[name]])
                 # fuse a following add(name, older...) into the normalisation pass
                 fused = None
                 for c in consumers[name]:
