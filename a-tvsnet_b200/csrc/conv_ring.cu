@@ -151,11 +151,13 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
         }
         if (published < cnt) publish_upto(cnt, 0);
     } else if (warp == 4) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        {
+            const uint32_t leader = elect_one();
             mbar_wait(wbar, 0);
             tc_fence_after();
-            const uint32_t ring_u32 = smem_u32(ring), w_u32 = smem_u32(wsm);
+            const uint32_t ring_u32 = smem_u32(ring);
+            const uint64_t wdesc0 = make_desc(smem_u32(wsm), B_CHUNK, 128, 0);
             uint32_t cnt = 0;
             long long it = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
@@ -169,43 +171,46 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                     }
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + (uint32_t)(acc * NPAD);
-                    uint32_t first = 1;
-#pragma unroll 1
+                    // descriptors = per-plane base + compile-time offsets (one 64-bit add per operand)
+#pragma unroll
                     for (int dz = 0; dz < 3; ++dz) {
                         const uint32_t pbase = ring_u32 + ((cnt + t + dz) % R) * (uint32_t)Cfg::SLOT_BYTES;
                         if (CIN >= 16) {
+                            const uint64_t abase = make_desc(pbase, RG_KCH_PAD, RG_WW * 16, 0);
+                            const uint64_t bbase = desc_advance(wdesc0, (uint32_t)(dz * 9 * (CIN / 16)) * B_STEP);
 #pragma unroll
                             for (int tp = 0; tp < 9; ++tp) {
-                                const uint32_t aoff = (uint32_t)(((tp / 3) * RG_WW + (tp % 3)) * 16);
-                                const uint32_t wtap = w_u32 + (uint32_t)((dz * 9 + tp) * (CIN / 16)) * B_STEP;
 #pragma unroll
                                 for (int ks = 0; ks < CIN / 16; ++ks) {
-                                    const uint64_t ad = make_desc(pbase + 2 * ks * RG_KCH_PAD + aoff, RG_KCH_PAD, RG_WW * 16, 0);
-                                    const uint64_t bd = make_desc(wtap + ks * B_STEP, B_CHUNK, 128, 0);
-                                    tc_mma_bf16(dcol, ad, bd, IDESC, first ^ 1u);
-                                    first = 0;
+                                    const uint64_t ad = desc_advance(abase, (uint32_t)(2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16));
+                                    const uint64_t bd = desc_advance(bbase, (uint32_t)(tp * (CIN / 16) + ks) * B_STEP);
+                                    if (dz == 0 && tp == 0 && ks == 0) tc_mma_bf16_first(dcol, ad, bd, IDESC, leader);
+                                    else tc_mma_bf16_acc(dcol, ad, bd, IDESC, leader);
                                 }
                             }
                         } else {
+                            const uint64_t bbase = desc_advance(wdesc0, (uint32_t)(dz * 5) * B_STEP);
 #pragma unroll
                             for (int pr = 0; pr < 5; ++pr) {
                                 const int ta = 2 * pr, tb = 2 * pr + 1;
                                 const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
                                 const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
                                 const uint32_t lbo = (tb < 9) ? offb - offa : 16u;
-                                const uint64_t ad = make_desc(pbase + offa, lbo, RG_WW * 16, 0);
-                                const uint64_t bd = make_desc(w_u32 + (uint32_t)(dz * 5 + pr) * B_STEP, B_CHUNK, 128, 0);
-                                tc_mma_bf16(dcol, ad, bd, IDESC, first ^ 1u);
-                                first = 0;
+                                // LBO differs per tap pair: fold it into the constant part of the descriptor
+                                const uint64_t ad = desc_advance(make_desc(pbase, 0, RG_WW * 16, 0), offa) |
+                                                    ((uint64_t)(lbo >> 4) << 16);
+                                const uint64_t bd = desc_advance(bbase, (uint32_t)pr * B_STEP);
+                                if (dz == 0 && pr == 0) tc_mma_bf16_first(dcol, ad, bd, IDESC, leader);
+                                else tc_mma_bf16_acc(dcol, ad, bd, IDESC, leader);
                             }
                         }
                     }
-                    tc_commit(&empty[(cnt + t) % R]);
+                    tc_commit_leader(&empty[(cnt + t) % R], leader);
                     if (t == un.zlen - 1) {
-                        tc_commit(&empty[(cnt + t + 1) % R]);
-                        tc_commit(&empty[(cnt + t + 2) % R]);
+                        tc_commit_leader(&empty[(cnt + t + 1) % R], leader);
+                        tc_commit_leader(&empty[(cnt + t + 2) % R], leader);
                     }
-                    tc_commit(&tfull[acc]);
+                    tc_commit_leader(&tfull[acc], leader);
                 }
                 cnt += (uint32_t)un.zlen + 2;
             }
@@ -215,7 +220,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
         const int g = warp & 3;
         const int row = g * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
-        constexpr int NRED = (2 * NPAD) / 32;
+        constexpr int NRED = 2 * NPAD;
         float run[NRED];
 #pragma unroll
         for (int i = 0; i < NRED; ++i) run[i] = 0.f;

@@ -112,11 +112,12 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
     const long long nwork = p.ntiles * p.ncls;      // work item = (class, tile), class-major
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            tma_prefetch_desc(&tm.w);
-            mbar_expect_tx(wbar, (uint32_t)wbytes);
-            for (int t = 0; t < p.ntaps; ++t) tma_load_2d(wsm + (size_t)t * WTAP_BYTES, &tm.w, 0, t * NPAD, wbar);
+        // ===================== TMA producer (converged warp, elected lane issues) =====================
+        {
+            const uint32_t leader = elect_one();
+            mbar_expect_tx_leader(wbar, (uint32_t)wbytes, leader);
+            for (int t = 0; t < p.ntaps; ++t)
+                tma_load_2d_leader(wsm + (size_t)t * WTAP_BYTES, &tm.w, 0, t * NPAD, wbar, leader);
             int stage = 0;
             uint32_t phase = 0;
             for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
@@ -131,13 +132,13 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                 const int jz0 = (r / p.nTH) << p.ltd;
                 for (int s = 0; s < nsteps; ++s) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], (uint32_t)Cfg::STAGE_BYTES);
+                    mbar_expect_tx_leader(&full[stage], (uint32_t)Cfg::STAGE_BYTES, leader);
                     uint8_t* dst = asmem + (size_t)stage * Cfg::STAGE_BYTES;
 #pragma unroll
                     for (int q = 0; q < Cfg::TPS; ++q) {
                         const TcTap& tp = p.taps[t0 + s * Cfg::TPS + q];
-                        tma_load_5d(dst + q * Cfg::TILE_BYTES, &tm.a[tp.map], 0, jx0 + tp.ox, jy0 + tp.oy, jz0 + tp.oz, b,
-                                    &full[stage]);
+                        tma_load_5d_leader(dst + q * Cfg::TILE_BYTES, &tm.a[tp.map], 0, jx0 + tp.ox, jy0 + tp.oy,
+                                           jz0 + tp.oz, b, &full[stage], leader);
                     }
                     if (++stage == p.nstages) {
                         stage = 0;
@@ -147,12 +148,14 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        {
+            const uint32_t leader = elect_one();
             mbar_wait(wbar, 0);
             tc_fence_after();
             const uint32_t a_lbo = (CIN == 8) ? (uint32_t)Cfg::TILE_BYTES : 16u;
             const uint32_t b_lbo = (CIN == 8) ? (uint32_t)(NPAD * 16) : 16u;
+            const uint64_t wdesc0 = make_desc(smem_u32(wsm), b_lbo, Cfg::SBO, Cfg::LAYOUT);
             int stage = 0;
             uint32_t phase = 0;
             long long it = 0;
@@ -166,21 +169,21 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                 for (int s = 0; s < nsteps; ++s) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t abase = smem_u32(asmem + (size_t)stage * Cfg::STAGE_BYTES);
-                    const uint32_t bbase = smem_u32(wsm + (size_t)(t0 + s * Cfg::TPS) * WTAP_BYTES);
+                    const uint64_t ad0 = make_desc(smem_u32(asmem + (size_t)stage * Cfg::STAGE_BYTES), a_lbo, Cfg::SBO, Cfg::LAYOUT);
+                    const uint64_t bd0 = desc_advance(wdesc0, (uint32_t)((t0 + s * Cfg::TPS) * WTAP_BYTES));
 #pragma unroll
                     for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-                        const uint64_t ad = make_desc(abase + ks * 32, a_lbo, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t bd = make_desc(bbase + ks * 32, b_lbo, Cfg::SBO, Cfg::LAYOUT);
-                        tc_mma_bf16(dcol, ad, bd, IDESC, (s | ks) != 0 ? 1u : 0u);
+                        const uint64_t ad = desc_advance(ad0, ks * 32), bd = desc_advance(bd0, ks * 32);
+                        if (ks == 0 && s == 0) tc_mma_bf16_first(dcol, ad, bd, IDESC, leader);
+                        else tc_mma_bf16_acc(dcol, ad, bd, IDESC, leader);
                     }
-                    tc_commit(&empty[stage]);
+                    tc_commit_leader(&empty[stage], leader);
                     if (++stage == p.nstages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&tfull[acc]);
+                tc_commit_leader(&tfull[acc], leader);
             }
         }
     } else {
@@ -190,7 +193,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
         const int tw = row & ((1 << p.ltw) - 1);
         const int th = (row >> p.ltw) & ((1 << p.lth) - 1);
         const int td = row >> (p.ltw + p.lth);
-        constexpr int NRED = (2 * NPAD) / 32;       // per-lane running statistics registers
+        constexpr int NRED = 2 * NPAD;              // per-thread running moments
         float run[NRED];
 #pragma unroll
         for (int i = 0; i < NRED; ++i) run[i] = 0.f;

@@ -57,6 +57,35 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// leader-predicated variants for a converged producer warp (operands stay in uniform registers)
+__device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "r"(bytes), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_leader(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                   int c4, uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %8, 0;\n\t"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_leader(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                   uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -71,6 +100,45 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The MMA-issuing warp runs converged (all 32 lanes execute the loop, operands are warp-uniform so
+// they live in uniform registers); only the elected lane (`leader` != 0) issues the instruction.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_mma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 q, %4, 0;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_first(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 q, %4, 0;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_leader(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(leader)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -102,6 +170,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     d |= (uint64_t)layout << 61;
     return d;
 }
+
+// descriptor whose start address is advanced by a byte offset (multiple of 16, no carry out of the
+// 14-bit address field: shared memory is < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
 // 32 values per lane -> lane L ends with the sum over the warp of v[L] (31 shuffles)
 __device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane) {
@@ -149,47 +221,26 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_b
                 if (c < ncols) op[c] = v[c];
         }
     }
-    if (want_stats) {
-        if (!valid) {
+    if (want_stats && valid) {
+        // per-THREAD running moments (row = this thread's voxel): no cross-lane traffic per tile
 #pragma unroll
-            for (int c = 0; c < NPAD; ++c) v[c] = 0.f;
-        }
-        if (NPAD == 16) {
-            float a[32];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                a[c] = v[c];
-                a[16 + c] = v[c] * v[c];
-            }
-            run[0] += warp_transpose_reduce32(a, lane);
-        } else {
-#pragma unroll
-            for (int h = 0; h < NPAD / 32; ++h) {
-                float q[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) q[c] = v[h * 32 + c] * v[h * 32 + c];
-                run[2 * h + 1] += warp_transpose_reduce32(q, lane);
-                run[2 * h] += warp_transpose_reduce32(v + h * 32, lane);
-            }
+        for (int c = 0; c < NPAD; ++c) {
+            run[c] += v[c];
+            run[NPAD + c] = fmaf(v[c], v[c], run[NPAD + c]);
         }
     }
 }
 
-// flush the per-lane running statistics: stats[c] += sum, stats[Cout + c] += sum of squares
+// flush the per-thread running statistics (run[0..NPAD) sums, run[NPAD..2NPAD) sums of squares):
+// one transposed warp reduction per 32 values, then stats[c] += sum, stats[Cout + c] += sum of squares
 template <int NPAD>
-__device__ __forceinline__ void flush_stats(double* stats, const float* run, int lane, int Cout, int coff, int ncols) {
-    if (NPAD == 16) {
-        const int c = lane & 15;
-        if (c < ncols) atomicAdd(&stats[(lane < 16 ? 0 : Cout) + coff + c], (double)run[0]);
-    } else {
+__device__ __forceinline__ void flush_stats(double* stats, float* run, int lane, int Cout, int coff, int ncols) {
 #pragma unroll
-        for (int h = 0; h < NPAD / 32; ++h) {
-            const int c = h * 32 + lane;
-            if (c < ncols) {
-                atomicAdd(&stats[coff + c], (double)run[2 * h]);
-                atomicAdd(&stats[Cout + coff + c], (double)run[2 * h + 1]);
-            }
-        }
+    for (int h = 0; h < (2 * NPAD) / 32; ++h) {
+        const float tot = warp_transpose_reduce32(run + h * 32, lane);
+        const int idx = h * 32 + lane;                 // index into [sums | sums of squares]
+        const int c = idx % NPAD;
+        if (c < ncols) atomicAdd(&stats[(idx < NPAD ? 0 : Cout) + coff + c], (double)tot);
     }
 }
 

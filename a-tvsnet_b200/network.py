@@ -211,7 +211,8 @@ class Network(object):
         dt = act_dtype()
         # one zero-filled arena for the batch-norm moments of every conv_bn / deconv_bn layer
         bn_nodes = [n for n in order if nodes[n].kind in ('conv_bn', 'deconv_bn')]
-        dev = next(v.value.device for v in nodes.values() if v.kind == 'input' and torch.is_tensor(v.value))
+        first = next(v.value for v in nodes.values() if v.kind == 'input')
+        dev = (first[0] if isinstance(first, (list, tuple)) else first).device
         arena = torch.zeros((max(len(bn_nodes), 1), 128), dtype=torch.float64, device=dev)
         arena_slot = {n: i for i, n in enumerate(bn_nodes)}
 
