@@ -1,0 +1,10 @@
+// conv_deconv.cuh - interface of the fused 8-class transposed convolution kernel (conv_deconv.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+bool deconv_fused_applicable(int Cin, int Cout);
+size_t deconv_fused_weight_bytes(int Cin, int Cout);
+int deconv_fused_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
+int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+                 double* stats, cudaStream_t st);

@@ -62,7 +62,8 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
 template <int CIN, int NPAD>
 __global__ void __launch_bounds__(RG_THREADS, 1)
 k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingParams p,
-              const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats) {
+              const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
+              const float* __restrict__ bias) {
     using Cfg = RingCfg<CIN>;
     constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
@@ -237,8 +238,14 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                 mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
+                const float* brow = nullptr;
+                if (bias != nullptr && valid) {
+                    const int z = un.z0 + t;
+                    const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
+                    brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + x) * p.Cout + p.coff;
+                }
                 epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + obase + (size_t)t * zstride, p.ncols, vec4,
-                                    stats != nullptr, run);
+                                    stats != nullptr, run, brow);
             }
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
@@ -277,13 +284,13 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
 
 template <int CIN, int NPAD>
 int launch_ring(const __nv_bfloat16* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
-                size_t smem, int grid, cudaStream_t st) {
+                const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_ring<CIN, NPAD><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats);
+    k_conv3d_ring<CIN, NPAD><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -315,7 +322,7 @@ bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
 }
 
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              double* stats, cudaStream_t st) {
+              double* stats, const float* bias, cudaStream_t st) {
     const int npad = ring_npad(Cin, Cout);
     const int nslabs = (Cout + npad - 1) / npad;
     const int sms = atvs_num_sms();
@@ -354,7 +361,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         p.ncols = (Cout - p.coff < npad) ? Cout - p.coff : npad;
         const uint8_t* wi = (const uint8_t*)wimg + (size_t)slab * p.wbytes;
         int rc = 0;
-#define RG_CASE(CI, NP) if (Cin == CI && npad == NP) rc = launch_ring<CI, NP>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, smem, grid, st); else
+#define RG_CASE(CI, NP) if (Cin == CI && npad == NP) rc = launch_ring<CI, NP>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st); else
         RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(8, 64) RG_CASE(16, 16) RG_CASE(16, 32) RG_CASE(16, 64)
         RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(32, 64) RG_CASE(64, 16) RG_CASE(64, 32)
         {

@@ -17,4 +17,4 @@ size_t ring_weight_bytes(int Cin, int Cout);
 int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed);
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              double* stats, cudaStream_t st);
+              double* stats, const float* bias, cudaStream_t st);

@@ -20,6 +20,7 @@
 #include "tc_ptx.cuh"
 #include "conv_geom.cuh"
 #include "conv_ring.cuh"
+#include "conv_deconv.cuh"
 #include <cstring>
 
 namespace {
@@ -66,7 +67,7 @@ struct TcCfg {
 template <int CIN, int NPAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams p, float* __restrict__ out,
-            double* __restrict__ stats) {
+            double* __restrict__ stats, const float* __restrict__ bias) {
     using Cfg = TcCfg<CIN>;
     constexpr int WTAP_BYTES = NPAD * CIN * 2;
     constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
@@ -215,8 +216,13 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
             const size_t o = valid ? ((((size_t)b * p.Do + (jz * p.os + pz)) * p.Ho + (jy * p.os + py)) * p.Wo +
                                       (jx * p.os + px)) * p.Cout + p.coff : 0;
+            const float* brow = nullptr;
+            if (bias != nullptr && valid) {      // convolutions only (os == 1): plane classes first / interior / last
+                const int zc = (jz == 0) ? 0 : (jz == p.Do - 1 ? 2 : 1);
+                brow = bias + ((((size_t)b * 3 + zc) * p.Ho + jy) * p.Wo + jx) * p.Cout + p.coff;
+            }
             epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + o, p.ncols,
-                                (p.ncols & 3) == 0 && (p.Cout & 3) == 0, stats != nullptr, run);
+                                (p.ncols & 3) == 0 && (p.Cout & 3) == 0, stats != nullptr, run, brow);
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
     }
@@ -297,14 +303,14 @@ int ntaps_padded(int Cin, int transposed, int cls) {
 }
 
 template <int CIN, int NPAD>
-int launch_tc(const TcMaps& maps, const TcParams& p, float* out, double* stats, size_t smem, int grid,
-              cudaStream_t st) {
+int launch_tc(const TcMaps& maps, const TcParams& p, float* out, double* stats, const float* bias, size_t smem,
+              int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_tc<CIN, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_tc<CIN, NPAD><<<grid, TC_THREADS, smem, st>>>(maps, p, out, stats);
+    k_conv3d_tc<CIN, NPAD><<<grid, TC_THREADS, smem, st>>>(maps, p, out, stats, bias);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -319,6 +325,7 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
     for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
     size_t bytes = (elems * 2 + 255) & ~(size_t)255;          // per-tap TMA image
     if (!transposed) bytes += ring_weight_bytes(Cin, Cout);    // halo-ring image (stride-1 convolutions)
+    else if (deconv_fused_applicable(Cin, Cout)) bytes += deconv_fused_weight_bytes(Cin, Cout);   // 8-class deconv image
     return bytes;
 }
 
@@ -345,12 +352,33 @@ extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cou
     ATVS_LAUNCH_CHECK();
     if (!transposed)
         return ring_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
+    if (deconv_fused_applicable(Cin, Cout))
+        return deconv_fused_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 1), (cudaStream_t)stream);
     return 0;
 }
+
+static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
+                           int stride, int transposed, const float* plane_bias, float* raw_out, double* stats,
+                           atvs_stream_t stream);
 
 extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
                                 int Cout, int stride, int transposed, float* raw_out, double* stats,
                                 atvs_stream_t stream) {
+    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, transposed, nullptr, raw_out, stats, stream);
+}
+
+extern "C" int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
+                                     int Cout, int stride, const float* plane_bias, float* raw_out, double* stats,
+                                     atvs_stream_t stream) {
+    ATVS_CHECK_ARG(plane_bias, ATVS_E_NULL, "atvs_conv3d_bf16_bias: plane_bias is NULL");
+    ATVS_CHECK_ARG(((uintptr_t)plane_bias & 15) == 0, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: plane_bias must be 16-byte aligned");
+    ATVS_CHECK_ARG((D + stride - 1) / stride >= 2, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: needs at least 2 output planes");
+    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, stats, stream);
+}
+
+static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
+                           int stride, int transposed, const float* plane_bias, float* raw_out, double* stats,
+                           atvs_stream_t stream) {
     ATVS_CHECK_ARG(x_bf16 && wpacked && raw_out, ATVS_E_NULL, "atvs_conv3d_bf16: NULL pointer");
     ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16: bad shape");
     ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
@@ -368,9 +396,12 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
         return ATVS_E_UNSUP;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (transposed && deconv_fused_applicable(Cin, Cout))
+        return deconv_fused(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 1), B, D, H, W, Cin, Cout, raw_out,
+                            stats, st);
     if (ring_applicable(B, D, H, W, stride, transposed))
         return ring_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
-                         stats, st);
+                         stats, plane_bias, st);
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     const int ncls = transposed ? 8 : 1;
     const int tps = (Cin == 8) ? 2 : 1;
@@ -491,7 +522,7 @@ extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, 
             const long long nwork = p.ntiles * p.ncls;
             const int grid = (int)(nwork < sms ? nwork : sms);
             int rc = 0;
-#define TC_CASE(CI, NP) if (Cin == CI && sp.npad == NP) rc = launch_tc<CI, NP>(maps, p, raw_out, stats, smem, grid, st); else
+#define TC_CASE(CI, NP) if (Cin == CI && sp.npad == NP) rc = launch_tc<CI, NP>(maps, p, raw_out, stats, plane_bias, smem, grid, st); else
             TC_CASE(8, 16) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32) TC_CASE(32, 64)
             TC_CASE(64, 16) TC_CASE(64, 32) TC_CASE(8, 32) TC_CASE(8, 64) TC_CASE(16, 64) TC_CASE(64, 64)
             {

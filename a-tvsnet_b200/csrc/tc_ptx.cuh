@@ -202,14 +202,30 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 // per-channel sum / sum of squares folded into per-lane running registers (batch-stat BN).
 template <int NPAD>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_bar, int lane, bool valid, float* op,
-                                              int ncols, bool vec4, bool want_stats, float* run) {
+                                              int ncols, bool vec4, bool want_stats, float* run,
+                                              const float* bias_row = nullptr) {
     float v[NPAD];
 #pragma unroll
     for (int c = 0; c < NPAD; c += 16) tc_ld16(taddr + c, v + c);
     tc_wait_ld();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar);
+    if (lane == 0 && tempty_bar != nullptr) mbar_arrive(tempty_bar);
+    if (bias_row != nullptr && valid) {
+        // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
+        if (vec4) {
+#pragma unroll
+            for (int c = 0; c < NPAD; c += 4)
+                if (c < ncols) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + c));
+                    v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NPAD; ++c)
+                if (c < ncols) v[c] += __ldg(bias_row + c);
+        }
+    }
     if (valid) {
         if (vec4) {
 #pragma unroll

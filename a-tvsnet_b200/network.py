@@ -55,7 +55,51 @@ def _packed_weight(key, w, cin, cout, transposed):
     return cache[key]
 
 
-def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None):
+class SplitCostVolume(object):
+    """The two-view cost volume of model.py:186-195, ``concat([tile(ref, D), warped], -1)``, kept as
+    its two parts: ``ref`` (B,h,w,F) and ``warped`` (B,D,h,w,F).  A convolution over the concatenation
+    is linear in the halves, and the ``tile(ref, D)`` half is the same 2-D result on every interior
+    plane, so the first CRM layers run on the F warped channels only and add the reference part as a
+    per-plane-class bias in their epilogue (atvs_conv3d_bf16_bias).  Halves the dominant layer's work
+    and the volume K1 has to write; results equal the concatenated form up to fp32 summation order."""
+
+    def __init__(self, ref, warped):
+        if warped.dtype != torch.bfloat16:
+            raise ValueError("SplitCostVolume is a bf16 tensor-core path construct")
+        self.ref, self.warped = ref, warped
+        self.shape = tuple(warped.shape[:-1]) + (warped.shape[-1] + ref.shape[-1],)
+        self.device = warped.device
+        self._tiled = {}
+
+    def ref_tiled(self, planes):
+        if planes not in self._tiled:
+            B, h, w, F = self.ref.shape
+            r = to_act(self.ref)
+            self._tiled[planes] = r[:, None].expand(B, planes, h, w, F).contiguous()
+        return self._tiled[planes]
+
+
+def _split_weights(wkey, w, F):
+    cache = V.packed_cache()
+    k = wkey + '/split'
+    if k not in cache:
+        cache[k] = (w[..., :F, :].contiguous(), w[..., F:, :].contiguous())
+    return cache[k]
+
+
+def conv3d_split(cv, wkey, w, cout, stride, stats_buf):
+    """first-layer convolution on a SplitCostVolume: bias from the reference half, main conv on the
+    warped half.  Returns (raw fp32 (B,Do,ho,wo,Cout), moments)."""
+    F = cv.ref.shape[-1]
+    w_ref, w_warp = _split_weights(wkey, w, F)
+    planes = 3 if stride == 1 else 4
+    bias, _ = conv3d_raw(cv.ref_tiled(planes), wkey + '/ref', w_ref, cout, stride, False, False)
+    if stride == 2:                      # planes (interior, last) -> classes (first == interior, interior, last)
+        bias = torch.cat([bias[:, :1], bias[:, :1], bias[:, 1:2]], dim=1).contiguous()
+    return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias)
+
+
+def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None, bias=None):
     """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)].
     ``stats_buf``: pre-zeroed fp64 buffer of >= 2*Cout elements to accumulate the moments into."""
     B, D, H, W, cin = x.shape
@@ -79,8 +123,12 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None)
                L.ptr(raw), L.ptr(stats), L.stream())
     else:
         pk = _packed_weight(wkey, w, cin, cout, int(transposed))
-        L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
-               L.ptr(raw), L.ptr(stats), L.stream())
+        if bias is not None:
+            L.call("atvs_conv3d_bf16_bias", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, L.ptr(bias),
+                   L.ptr(raw), L.ptr(stats), L.stream())
+        else:
+            L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
+                   L.ptr(raw), L.ptr(stats), L.stream())
     if prof:
         e1.record()
         PROFILE[1].append((wkey, e0, e1, raw.numel() // cout, cin, cout))
@@ -212,7 +260,7 @@ class Network(object):
         # one zero-filled arena for the batch-norm moments of every conv_bn / deconv_bn layer
         bn_nodes = [n for n in order if nodes[n].kind in ('conv_bn', 'deconv_bn')]
         first = next(v.value for v in nodes.values() if v.kind == 'input')
-        dev = (first[0] if isinstance(first, (list, tuple)) else first).device
+        dev = (first[0] if isinstance(first, (list, tuple)) else first).device   # tensors and SplitCostVolume have .device
         arena = torch.zeros((max(len(bn_nodes), 1), 128), dtype=torch.float64, device=dev)
         arena_slot = {n: i for i, n in enumerate(bn_nodes)}
 
@@ -224,6 +272,8 @@ class Network(object):
 
         def act_in(name):
             v = nodes[name].value
+            if isinstance(v, SplitCostVolume):
+                return v
             if nodes[name].kind == 'input':
                 v = to_act(v)
                 nodes[name].value = v      # cast once
@@ -237,8 +287,12 @@ class Network(object):
                 x = act_in(node.inputs[0])
                 transposed = node.kind == 'deconv_bn'
                 wname = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
-                raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
-                                        node.params['stride'], transposed, True, arena[arena_slot[name]])
+                if isinstance(x, SplitCostVolume):
+                    raw, stats = conv3d_split(x, wname, V.get_variable(wname), node.params['filters'],
+                                              node.params['stride'], arena[arena_slot[name]])
+                else:
+                    raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
+                                            node.params['stride'], transposed, True, arena[arena_slot[name]])
                 # fuse a following add(name, older...) into the normalisation pass
                 fused = None
                 for c in consumers[name]:

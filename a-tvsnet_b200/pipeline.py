@@ -10,22 +10,33 @@ from . import network as N
 from .atvsnet import OutputConv, StackedUNet_prob
 from .model import _prob2depth, build_cost_volume
 
+# bf16 path: run the first CRM layers on the warped half only (network.SplitCostVolume)
+SPLIT_COST_VOLUME = True
+
 
 def stage1_view(features, cams, depth_num, depth_start, depth_interval, view_i, siamese=True):
     """TVSNet_base_siamese (model.py:398-417) keeping the 8-ch filtered volume in the activation
     dtype.  Returns (filtered (B,D,h,w,8), prob logits (B,D,h,w) fp32, depth_view | None)."""
     dt = N.act_dtype()
     ref, view = features[:, 0], features[:, view_i]
-    cv = build_cost_volume(ref, view, cams, depth_num, depth_start, depth_interval, ref_id=0, view_id=view_i,
-                           out_dtype=dt)
+
+    def cost_volume(r, v, rid, vid):
+        if dt == torch.bfloat16 and SPLIT_COST_VOLUME:
+            # [tile(ref) | warped] kept as its halves: K1 writes only the warped 32 channels
+            warped = build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
+                                       mode='warped_only', out_dtype=dt)
+            return N.SplitCostVolume(r, warped)
+        return build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
+                                 out_dtype=dt)
+
+    cv = cost_volume(ref, view, 0, view_i)
     tower = StackedUNet_prob({'data': cv}, outputs=('conv_b2_6_1', 'conv_b2_6_2'))
     prob = tower.get_output().squeeze(-1)
     filtered = tower.get_output_by_name('conv_b2_6_1')
     del cv, tower
     depth_view = None
     if siamese:
-        cvv = build_cost_volume(view, ref, cams, depth_num, depth_start, depth_interval, ref_id=view_i, view_id=0,
-                                out_dtype=dt)
+        cvv = cost_volume(view, ref, view_i, 0)
         pv = StackedUNet_prob({'data': cvv}, outputs=('conv_b2_6_2',)).get_output().squeeze(-1)
         depth_view, _ = _prob2depth(pv, depth_start, depth_interval, 1, False)
     return filtered, prob, depth_view

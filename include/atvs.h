@@ -95,6 +95,14 @@ int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int tran
 int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
                      int Cout, int stride, int transposed, float* raw_out, double* stats,
                      atvs_stream_t stream);
+/* same convolution plus a depth-invariant term: raw_out[b,z,y,x,:] += plane_bias[b,c(z),y,x,:] with
+ * c(z) = 0 for the first output plane, 2 for the last, 1 otherwise; plane_bias (B,3,Ho,Wo,Cout) f32.
+ * Used for the first CRM layers: the cost volume of model.py:186-195 is [tile(ref, D) | warped], so the
+ * reference half of the convolution is a 2-D result shared by all interior planes (computed once by
+ * running this same primitive on a 3-plane (4 for stride 2) tile of the reference feature).         */
+int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
+                          int Cout, int stride, const float* plane_bias, float* raw_out, double* stats,
+                          atvs_stream_t stream);
 
 /* ---- batch-norm (batch statistics) + ReLU + skip adds ------ network.py:206-215, 541-550, 696
  * y = relu((raw - mean) * rsqrt(var + eps)) with mean/var from `stats` over `count` voxels

@@ -47,7 +47,7 @@ def test_argument_errors_without_gpu(lib):
     # per-tap TMA image + halo-ring image (stride-1 capable weights carry both)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 108 * 2 * 32 * 16
     assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 15 * 2 * 16 * 16
-    assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2
+    assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2 * 2      # per-class image + fused 8-class image
 
 
 def test_ops_refuse_cpu_tensors():

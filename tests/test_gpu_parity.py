@@ -243,6 +243,32 @@ def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
+@pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10))])
+def test_conv3d_split_cost_volume(A, stride, shape):
+    """conv over [tile(ref, D) | warped] == conv(warped) + per-plane-class bias from ref (ring and TMA kernels)."""
+    from oracle import network as onet
+    from atvsnet_b200.network import SplitCostVolume, conv3d_split, conv3d_raw
+    rng = np.random.default_rng(11)
+    B, D, H, W = shape
+    F, cout = 32, 8 if stride == 1 else 16
+    ref = torch.from_numpy(rng.standard_normal((B, H, W, F)).astype(np.float32)).to(torch.bfloat16)
+    warped = torch.from_numpy(rng.standard_normal((B, D, H, W, F)).astype(np.float32)).to(torch.bfloat16)
+    w = torch.from_numpy((rng.standard_normal((3, 3, 3, 2 * F, cout)) / np.sqrt(27 * 2 * F)).astype(np.float32))
+    w = w.to(torch.bfloat16).float()
+    A.variables.packed_cache().clear()
+    stats = torch.zeros(128, dtype=torch.float64, device='cuda')
+    raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
+    full = np.concatenate([np.tile(ref.float().numpy()[:, None], (1, D, 1, 1, 1)), warped.float().numpy()], axis=-1)
+    refo = onet.conv3d(full, w.numpy(), stride)
+    assert raw.shape == refo.shape
+    assert rel_err(npy(raw), refo) < 1e-4
+    flat = refo.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(st.cpu().numpy()[:cout], flat.sum(0), rtol=1e-3, atol=5e-2)
+    # and equals the plain kernel on the materialised concatenation
+    raw2, _ = conv3d_raw(torch.from_numpy(full).to(torch.bfloat16).cuda(), 'split_full', w.cuda(), cout, stride, False, True)
+    assert rel_err(npy(raw), npy(raw2)) < 1e-5
+
+
 def test_conv3d_argument_errors(A):
     from atvsnet_b200.network import conv3d_raw
     x = torch.zeros(1, 3, 4, 4, 16, dtype=torch.bfloat16, device='cuda')
