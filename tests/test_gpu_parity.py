@@ -415,10 +415,32 @@ def test_multiview_pipeline_fp32_and_bf16(A):
     assert np.abs(npy(out['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * rng_
     for a, b in zip(out['depth_views'], ref['depth_views']):
         assert np.abs(npy(a) - b).max() < 1e-3 * rng_
-    # bf16 tensor-core path: mean absolute depth error <= 0.1 % of the depth range
+    # split cost volume path (bf16) runs too at this size; its accuracy is checked at a realistic size below
     outb = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
+    assert np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_ < 5e-3
+
+
+def test_multiview_pipeline_bf16_depth_mae(A):
+    """north_star tolerance: final depth map of the bf16 tensor-core path within a mean absolute error of
+    0.1 % of the depth range of the fp32 reference (CPU oracle), at a volume large enough (64x64x80) for
+    the batch-norm statistics of the deepest level (8x8x10 voxels) to be meaningful."""
+    from oracle import model as om
+    D, h, w = 64, 64, 80
+    cams, feats, weights = _e2e_inputs(A, D=D, h=h, w=w, nv=3)
+    A.variables.load_weights(weights)
+    ref = om.run_multiview_stage12(feats, cams, D, weights, siamese=False)
+    rng_ = (D - 1) * float(cams[0, 0, 1, 3, 1])
+    A.FLAGS.precision = 'bf16'
+    outb = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
     mae = np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_
     assert mae < 1e-3, mae
     # the softmax over depth must be peaked enough for that bound to mean something
     p = torch.softmax(-torch.from_numpy(ref['prob_volume_agg']), dim=1)
-    assert p.max(dim=1).values.mean() > 2.0 / 16
+    assert p.max(dim=1).values.mean() > 4.0 / D
+    # fp32 CUDA path at the same size, against the oracle
+    A.FLAGS.precision = 'fp32'
+    try:
+        outf = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
+    finally:
+        A.FLAGS.precision = 'bf16'
+    assert np.abs(npy(outf['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * rng_
