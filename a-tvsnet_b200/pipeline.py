@@ -12,34 +12,51 @@ from .model import _prob2depth, build_cost_volume
 
 # bf16 path: run the first CRM layers on the warped half only (network.SplitCostVolume)
 SPLIT_COST_VOLUME = True
+# number of CUDA streams the independent stage-I passes are spread over
+CONCURRENT_PASSES = 4
+
+
+def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid):
+    dt = N.act_dtype()
+    if dt == torch.bfloat16 and SPLIT_COST_VOLUME:
+        # [tile(ref) | warped] kept as its halves: K1 writes only the warped 32 channels
+        warped = build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
+                                   mode='warped_only', out_dtype=dt)
+        return N.SplitCostVolume(r, warped)
+    return build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid, out_dtype=dt)
+
+
+def stage1_forward(features, cams, depth_num, depth_start, depth_interval, view_i):
+    """forward half of TVSNet_base_siamese (model.py:409-411): ref <- view_i.  Returns the 8-ch
+    filtered volume (activation dtype) and the prob logits (fp32)."""
+    cv = _cost_volume(features[:, 0], features[:, view_i], cams, depth_num, depth_start, depth_interval, 0, view_i)
+    tower = StackedUNet_prob({'data': cv}, outputs=('conv_b2_6_1', 'conv_b2_6_2'))
+    return tower.get_output_by_name('conv_b2_6_1'), tower.get_output().squeeze(-1)
+
+
+def stage1_reverse(features, cams, depth_num, depth_start, depth_interval, view_i):
+    """reverse half (model.py:413-415): view_i as reference -> depth_view (B,h,w,1)."""
+    cvv = _cost_volume(features[:, view_i], features[:, 0], cams, depth_num, depth_start, depth_interval, view_i, 0)
+    pv = StackedUNet_prob({'data': cvv}, outputs=('conv_b2_6_2',)).get_output().squeeze(-1)
+    return _prob2depth(pv, depth_start, depth_interval, 1, False)[0]
 
 
 def stage1_view(features, cams, depth_num, depth_start, depth_interval, view_i, siamese=True):
     """TVSNet_base_siamese (model.py:398-417) keeping the 8-ch filtered volume in the activation
     dtype.  Returns (filtered (B,D,h,w,8), prob logits (B,D,h,w) fp32, depth_view | None)."""
-    dt = N.act_dtype()
-    ref, view = features[:, 0], features[:, view_i]
-
-    def cost_volume(r, v, rid, vid):
-        if dt == torch.bfloat16 and SPLIT_COST_VOLUME:
-            # [tile(ref) | warped] kept as its halves: K1 writes only the warped 32 channels
-            warped = build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
-                                       mode='warped_only', out_dtype=dt)
-            return N.SplitCostVolume(r, warped)
-        return build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
-                                 out_dtype=dt)
-
-    cv = cost_volume(ref, view, 0, view_i)
-    tower = StackedUNet_prob({'data': cv}, outputs=('conv_b2_6_1', 'conv_b2_6_2'))
-    prob = tower.get_output().squeeze(-1)
-    filtered = tower.get_output_by_name('conv_b2_6_1')
-    del cv, tower
-    depth_view = None
-    if siamese:
-        cvv = cost_volume(view, ref, view_i, 0)
-        pv = StackedUNet_prob({'data': cvv}, outputs=('conv_b2_6_2',)).get_output().squeeze(-1)
-        depth_view, _ = _prob2depth(pv, depth_start, depth_interval, 1, False)
+    filtered, prob = stage1_forward(features, cams, depth_num, depth_start, depth_interval, view_i)
+    depth_view = stage1_reverse(features, cams, depth_num, depth_start, depth_interval, view_i) if siamese else None
     return filtered, prob, depth_view
+
+
+_STREAMS = {}
+
+
+def _side_streams(device, n):
+    key = (device.index, n)
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _STREAMS[key]
 
 
 def aggregate(filtered_views, scope='attention_aggregate', group=None):
@@ -81,11 +98,36 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     ds = cams[:, 0, 1, 3, 0].contiguous()
     di = cams[:, 0, 1, 3, 1].contiguous()
     mine = shard_views(n_views, rank, world) if group is not None else list(range(1, n_views))
-    filtered, depth_views = [], []
-    for view_i in mine:
-        f, _, dv = stage1_view(features, cams, depth_num, ds, di, view_i, siamese)
-        filtered.append(f)
-        depth_views.append(dv)
+    # the 2*(N-1) regularisation passes of stage I are independent: spread them over a few streams so that
+    # the many small kernels of the coarse U-Net levels (40-tile launches) overlap with other passes.
+    tasks = [(v, 'f') for v in mine] + ([(v, 'r') for v in mine] if siamese else [])
+    nstreams = max(1, min(CONCURRENT_PASSES, len(tasks)))
+    main = torch.cuda.current_stream()
+    results = {}
+    if nstreams == 1:
+        for v, kind in tasks:
+            fn = stage1_forward if kind == 'f' else stage1_reverse
+            results[(v, kind)] = fn(features, cams, depth_num, ds, di, v)
+    else:
+        if not N.V.packed_cache():
+            # first call after load_weights: run one pass on the main stream so that the packed bf16 weight
+            # images exist before other streams read them
+            v, kind = tasks.pop(0)
+            results[(v, kind)] = (stage1_forward if kind == 'f' else stage1_reverse)(features, cams, depth_num, ds, di, v)
+        streams = _side_streams(features.device, nstreams)
+        for st in streams:
+            st.wait_stream(main)
+        for i, (v, kind) in enumerate(tasks):
+            with torch.cuda.stream(streams[i % nstreams]):
+                fn = stage1_forward if kind == 'f' else stage1_reverse
+                out = fn(features, cams, depth_num, ds, di, v)
+                for t in (out if isinstance(out, tuple) else (out,)):
+                    t.record_stream(main)
+                results[(v, kind)] = out
+        for st in streams:
+            main.wait_stream(st)
+    filtered = [results[(v, 'f')][0] for v in mine]
+    depth_views = [results[(v, 'r')] for v in mine] if siamese else [None for _ in mine]
     cost_agg = aggregate(filtered, 'attention_aggregate', group)
     prob_agg = OutputConv({'data': cost_agg}).get_output().squeeze(-1)
     depth, _ = _prob2depth(prob_agg, ds, di, 1, False)
