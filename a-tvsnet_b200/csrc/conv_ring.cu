@@ -59,8 +59,15 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
     return r;
 }
 
+// small-channel instances are bound by the latency of the producer / MMA / epilogue handshakes, not by
+// any pipe: two co-resident CTAs per SM overlap those latencies (shared memory and TMEM both allow it)
 template <int CIN, int NPAD>
-__global__ void __launch_bounds__(RG_THREADS, 1)
+struct RingOcc {
+    static constexpr int MINB = (CIN <= 16 && NPAD == 16) ? 2 : 1;
+};
+
+template <int CIN, int NPAD>
+__global__ void __launch_bounds__(RG_THREADS, RingOcc<CIN, NPAD>::MINB)
 k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
               const float* __restrict__ bias) {
@@ -193,10 +200,13 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                             const uint64_t bbase = desc_advance(wdesc0, (uint32_t)(dz * 5) * B_STEP);
 #pragma unroll
                             for (int pr = 0; pr < 5; ++pr) {
-                                const int ta = 2 * pr, tb = 2 * pr + 1;
+                                // tap pairs (0,1) (2,3) (4,5) (6,7) and (7*,8): the 9th tap is paired with a
+                                // second, zero-weighted read of tap 7 so that every operand byte is real data
+                                // (an out-of-plane phantom multiplies uninitialised shared memory by 0 -> NaN)
+                                const int ta = (pr < 4) ? 2 * pr : 7, tb = (pr < 4) ? 2 * pr + 1 : 8;
                                 const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
                                 const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
-                                const uint32_t lbo = (tb < 9) ? offb - offa : 16u;
+                                const uint32_t lbo = offb - offa;
                                 // LBO differs per tap pair: fold it into the constant part of the descriptor
                                 const uint64_t ad = desc_advance(make_desc(pbase, 0, RG_WW * 16, 0), offa) |
                                                     ((uint64_t)(lbo >> 4) << 16);
@@ -271,8 +281,10 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
             tap = step / (Cin / 16);
             k = ((step % (Cin / 16)) * 2 + chunk) * 8 + e;
         } else {
-            const int dz = step / 5, pr = step % 5, tp = 2 * pr + chunk;
-            tap = (tp < 9) ? dz * 9 + tp : -1;
+            const int dz = step / 5, pr = step % 5;
+            // pairs (0,1) (2,3) (4,5) (6,7) (7*,8): chunk 0 of the last pair is a zero-weighted re-read of tap 7
+            const int tp = (pr < 4) ? 2 * pr + chunk : (chunk == 0 ? -1 : 8);
+            tap = (tp >= 0) ? dz * 9 + tp : -1;
             k = e;
         }
         const int co = slab * npad + n;
@@ -333,11 +345,12 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     p.nYT = (H + RG_TY - 1) / RG_TY;
     {   // z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
+        const long long slots = (long long)sms * ((Cin <= 16 && ring_npad(Cin, Cout) == 16) ? 2 : 1);
         long long best = -1;
         int bz = D;
         for (int zs = (D < 4 ? D : 4); zs <= D; ++zs) {
             const long long units = cols * ((D + zs - 1) / zs);
-            const long long cost = ((units + sms - 1) / sms) * (zs + 2);
+            const long long cost = ((units + slots - 1) / slots) * (zs + 2);
             if (best < 0 || cost < best) { best = cost; bz = zs; }
         }
         p.ZS = bz;
@@ -346,7 +359,8 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     }
     p.wbytes = ring_nsteps(Cin) * 2 * npad * 16;
     const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
-    const size_t budget = 208 * 1024;
+    const int minb = (Cin <= 16 && npad == 16) ? 2 : 1;
+    const size_t budget = (minb == 2 ? 100 : 208) * 1024;
     int nring = (int)((budget - (size_t)((p.wbytes + 127) & ~127)) / slot);
     if (nring > 8) nring = 8;
     if (nring < 4) {
@@ -355,7 +369,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     }
     p.nring = nring;
     const size_t smem = 128 + ((p.wbytes + 127) & ~127) + (size_t)nring * slot + (2 * nring + 5) * 8 + 16;
-    const int grid = (int)(p.nunits < sms ? p.nunits : sms);
+    const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
     for (int slab = 0; slab < nslabs; ++slab) {
         p.coff = slab * npad;
         p.ncols = (Cout - p.coff < npad) ? Cout - p.coff : npad;

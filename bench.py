@@ -232,6 +232,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     ms_e2e = f0.elapsed_time(f1)
+    # sanity of what was timed: the depth map must be finite and inside the swept inverse-depth range
+    dmin, dmax = float(cams[0, 0, 1, 3, 0]), float(cams[0, 0, 1, 3, 0] + (D - 1) * cams[0, 0, 1, 3, 1])
+    dm = depth_h.clone()
+    if not bool(torch.isfinite(dm).all()) or float(dm.min()) < dmin - 1e-4 or float(dm.max()) > dmax + 1e-4:
+        raise RuntimeError("bench: depth map not finite / outside the depth sweep [%g, %g]: min %g max %g"
+                           % (dmin, dmax, float(dm.min()), float(dm.max())))
     h2d = feats_h.numel() * 4 + cams_h.numel() * 4
     d2h = depth_h.numel() * 4
 
@@ -289,6 +295,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
+        "output_check": "depth map finite and inside the inverse-depth sweep",
     }
     if roof is not None:
         line["roofline"] = roof
