@@ -1,19 +1,32 @@
 // conv_ring.cu - stride-1 3x3x3 convolution (network.py:173-215 conv_bn, :142 conv) as a
-// tcgen05 implicit GEMM whose A operand is read from a shared-memory RING OF HALO PLANES, so
-// every input voxel is fetched from L2/HBM ~1.4x instead of 27x (once per filter tap).
+// tcgen05 implicit GEMM over a shared-memory RING OF HALO PLANES, z-EXPANDED in the MMA N dimension.
 //
-//   work unit   = a column of output tiles (16 y x 8 x) over a z segment [z0, z0+zlen)
-//   ring slot   = one input z plane with halo: [Cin/8 chunks][18 y][10 x][8 channels] bf16
-//                 (no-swizzle K-major core-matrix layout: 8 consecutive x = one 8-row core
-//                 matrix, next y row = SBO, next 8-channel chunk = LBO), filled by 4 producer
-//                 warps with 16-byte cp.async (zero fill outside the volume = 'SAME' padding;
-//                 TMA box loads with 16-byte rows measured ~6 cycles per row and were the
-//                 bottleneck), published to the async proxy with fence.proxy.async;
-//   one tile    = 27 taps x Cin/16 tcgen05.mma (M=128, N=16/32/64, K=16) whose A descriptors are
-//                 just shifted start addresses into three consecutive ring planes; a plane is
-//                 released (tcgen05.commit -> mbarrier) when the tile that last needs it retires.
-//   Cin = 8     : one K=16 step covers two taps of the same plane (LBO = distance of the taps).
-//   warps 0-3 producers | warp 4 MMA issuer | warps 5-8 epilogue, double-buffered TMEM.
+// What bounds a Cout = 8 convolution on the tensor pipe is the fetch of the A operand (the voxel
+// tile) from shared memory: tools/mma_probe.cu measures  t(M=128, N, K=16) = 32 + N/4 cycles  with both
+// operands in shared memory (A = 4 KB at 128 B/clk, B = 32 N bytes), i.e. N = 16 costs 39 cycles
+// while its math needs 8.  So every fetched A tile has to feed as many output columns as possible.
+// The three z taps of a 3x3x3 kernel see the SAME in-plane tile: input plane i (shifted by the
+// in-plane tap (dy,dx)) contributes to the output planes i-2, i-1, i with the weights dz = 2, 1, 0.
+// One MMA therefore covers three output planes:
+//
+//   accumulators  : a ring of G column groups in TMEM, one group (CP = 8|16|32 columns) per output plane
+//   per input plane: 9 * Cin/16 MMAs (5 tap-pair MMAs for Cin = 8) with N = 3*CP over three consecutive
+//                    groups and B = [w_dz2 | w_dz1 | w_dz0]; the plane is consumed ONCE and its ring
+//                    slot released, an output plane is complete after the input plane behind it
+//   -> 3x fewer MMAs than one accumulator per output plane (N = CP), each ~ the same cost.
+//
+// N must be a multiple of 16: with CP = 8 an odd run of groups is extended by one group that meets
+// zero weights (the next, already drained and zeroed group, or a never-read dummy group behind the
+// ring); runs that wrap around the ring are issued as two MMAs.  Accumulation is always "+=": the
+// epilogue zeroes a group (tcgen05.st) right after reading it.
+//
+//   work unit : a column of 16(y) x 8(x) output tiles over a z segment [z0, z0+zlen)
+//   ring slot : one input z plane with halo, [Cin/8 chunks][18 y][10 x][8 channels] bf16, no-swizzle
+//               K-major core matrices (8 consecutive x = one 8-row core matrix, next y row = SBO, next
+//               8-channel chunk = LBO), filled by 4 producer warps with 16-byte cp.async (zero fill =
+//               'SAME' padding) and published to the async proxy with fence.proxy.async
+//   Cin = 8   : one K=16 step covers two taps of the plane (LBO = distance of the taps)
+//   warps 0-3 producers | warp 4 MMA issuer (converged, elected lane) | warps 5-8 epilogue
 #include "tc_ptx.cuh"
 #include "conv_ring.cuh"
 #include <cstring>
@@ -26,6 +39,7 @@ constexpr int RG_KCH_PAD = RG_NVOX * 16 + 16;       // pitch of one 8-channel ch
                                                     // 8 chunk stores of a voxel on distinct banks
 constexpr int RG_PRODUCERS = 128;
 constexpr int RG_THREADS = 288;
+constexpr int RG_MAXG = 15;
 
 struct RingParams {
     int B, D, H, W;
@@ -36,10 +50,15 @@ struct RingParams {
     long long nunits;
 };
 
-template <int CIN>
+template <int CIN, int CP>
 struct RingCfg {
     static constexpr int NKC = CIN / 8;
     static constexpr int SLOT_BYTES = (NKC * RG_KCH_PAD + 127) / 128 * 128;
+    static constexpr int NSTEPS = (CIN >= 16) ? 9 * (CIN / 16) : 5;     // K=16 MMA steps per input plane
+    static constexpr int G = (CP == 8) ? 15 : 8;                        // accumulator groups in the ring
+    static constexpr int NROWS = (CP == 8) ? 64 : 3 * CP;               // rows of one weight step image
+    static constexpr int STEP_BYTES = 2 * NROWS * 16;
+    static constexpr uint32_t TMEM_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy
 };
 
 struct Unit {
@@ -59,23 +78,72 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
     return r;
 }
 
-// small-channel instances are bound by the latency of the producer / MMA / epilogue handshakes, not by
-// any pipe: two co-resident CTAs per SM overlap those latencies (shared memory and TMEM both allow it)
-template <int CIN, int NPAD>
-struct RingOcc {
-    static constexpr int MINB = (CIN <= 16 && NPAD == 16) ? 2 : 1;
-};
+// input planes of a unit: i in [ibeg, iend], plane i = volume plane z0 - 1 + i; planes outside the volume
+// contribute nothing ('SAME' zero padding) and are skipped by all three roles
+__device__ __forceinline__ int unit_ibeg(const Unit& u) { return u.z0 == 0 ? 1 : 0; }
+__device__ __forceinline__ int unit_iend(const RingParams& p, const Unit& u) {
+    return (u.z0 + u.zlen == p.D) ? u.zlen : u.zlen + 1;
+}
 
-template <int CIN, int NPAD>
-__global__ void __launch_bounds__(RG_THREADS, RingOcc<CIN, NPAD>::MINB)
+// MMA with the descriptors given as (lo, hi) halves: the hi halves are loop constants and the lo halves
+// change by one 32-bit add per instruction
+__device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 ad, {%1, %2};\n\t"
+        "mov.b64 bd, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_st8_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ constexpr uint32_t ring_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// weight-image window (in rows of 8) and MMA N for a run of `len` output planes whose first plane meets
+// the z tap `f` (2, 1 or 0; the following planes meet f-1, ...).
+//   CP = 8 image groups : [w2 0 w1 0 w2 w1 w0 0]      CP >= 16 : [w2 w1 w0]
+template <int CP>
+__device__ __forceinline__ void ring_window(int f, int len, uint32_t& row_off_bytes, uint32_t& idesc) {
+    if (CP == 8) {
+        int grp;
+        if (len == 1) grp = (f == 2) ? 0 : (f == 1 ? 2 : 6);
+        else if (len == 2) grp = (f == 2) ? 4 : 5;
+        else grp = 4;
+        row_off_bytes = (uint32_t)grp * 128u;
+        idesc = ring_idesc(len == 3 ? 32 : 16);
+    } else {
+        row_off_bytes = (uint32_t)(2 - f) * (uint32_t)CP * 16u;
+        idesc = ring_idesc(len * CP);
+    }
+}
+
+template <int CIN, int CP, int MINB>
+__global__ void __launch_bounds__(RG_THREADS, MINB)
 k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
               const float* __restrict__ bias) {
-    using Cfg = RingCfg<CIN>;
-    constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
-    constexpr uint32_t B_CHUNK = NPAD * 16;             // one 8-channel chunk of a weight tile
-    constexpr uint32_t B_STEP = 2 * B_CHUNK;            // one K=16 step
+    using Cfg = RingCfg<CIN, CP>;
+    constexpr int G = Cfg::G;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -85,8 +153,8 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
     uint64_t* full = bars;
     uint64_t* empty = bars + p.nring;
     uint64_t* tfull = bars + 2 * p.nring;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* wbar = tempty + 2;
+    uint64_t* tempty = tfull + RG_MAXG;
+    uint64_t* wbar = tempty + RG_MAXG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,16 +164,16 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
             mbar_init(&full[s], RG_PRODUCERS);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&tfull[0], 1);
-        mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4);
-        mbar_init(&tempty[1], 4);
+        for (int g = 0; g < G; ++g) {
+            mbar_init(&tfull[g], 1);
+            mbar_init(&tempty[g], 4);
+        }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS)
+                     "r"(Cfg::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -113,6 +181,15 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 5) {
+        // accumulation is always "+=": start from zero accumulators
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (uint32_t c = 0; c < Cfg::TMEM_COLS; c += 8) tc_st8_zero(taddr + c);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp < 4) {
         // ===================== producers: global -> ring planes (cp.async, 16 B per op) =====================
@@ -121,12 +198,11 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
             mbar_expect_tx(wbar, (uint32_t)p.wbytes);
             bulk_copy_g2s(wsm, wimg, (uint32_t)p.wbytes, wbar);
         }
-        // up to G planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
-        // mbarrier arrive) once plane q+G-1 has been issued.  G <= R-2 keeps the ring deadlock-free.
-        const int G = (R >= 6) ? 4 : 2;
+        // up to PF planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
+        // mbarrier arrive) once plane q+PF-1 has been issued.  PF <= R-1 keeps the ring deadlock-free.
+        const int PF = (R >= 5) ? 4 : (R >= 3 ? 2 : 1);
         uint32_t cnt = 0, published = 0;
         auto publish_upto = [&](uint32_t upto_excl, int keep) {
-            // wait until at most `keep` groups are pending, then publish planes [published, upto_excl)
             if (keep >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
             else if (keep == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
             else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -136,195 +212,257 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
         };
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const Unit un = decode_unit(p, u);
-            for (int zi = un.z0 - 1; zi <= un.z0 + un.zlen; ++zi, ++cnt) {
+            const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
+            for (int i = ibeg; i <= iend; ++i, ++cnt) {
+                const int zi = un.z0 - 1 + i;
                 const uint32_t slot = cnt % R, par = (cnt / R) & 1;
                 mbar_wait(&empty[slot], par ^ 1);
-                const bool zok = zi >= 0 && zi < p.D;
-                const __nv_bfloat16* zbase = x + (((size_t)un.b * p.D + (zok ? zi : 0)) * p.H) * p.W * CIN;
+                const __nv_bfloat16* zbase = x + (((size_t)un.b * p.D + zi) * p.H) * p.W * CIN;
                 const uint32_t dst0 = smem_u32(ring + (size_t)slot * Cfg::SLOT_BYTES);
 #pragma unroll 4
-                for (int i = ptid; i < Cfg::NKC * RG_NVOX; i += RG_PRODUCERS) {
-                    const int c = i % Cfg::NKC, v = i / Cfg::NKC;
+                for (int j = ptid; j < Cfg::NKC * RG_NVOX; j += RG_PRODUCERS) {
+                    const int c = j % Cfg::NKC, v = j / Cfg::NKC;
                     const int yy = v / RG_WW, xx = v - yy * RG_WW;
                     const int gy = un.y0 - 1 + yy, gx = un.x0 - 1 + xx;
-                    const bool ok = zok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+                    const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
                     const __nv_bfloat16* src = ok ? zbase + ((size_t)gy * p.W + gx) * CIN + c * 8 : x;
                     const uint32_t dst = dst0 + (uint32_t)(c * RG_KCH_PAD + v * 16);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
                                  : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                if (cnt + 1 - published >= (uint32_t)G) publish_upto(cnt + 2 - G, G - 1);
+                if (cnt + 1 - published >= (uint32_t)PF) publish_upto(cnt + 2 - PF, PF - 1);
             }
         }
         if (published < cnt) publish_upto(cnt, 0);
     } else if (warp == 4) {
         // ===================== MMA issuer (converged warp, elected lane issues) =====================
-        {
-            const uint32_t leader = elect_one();
-            mbar_wait(wbar, 0);
-            tc_fence_after();
-            const uint32_t ring_u32 = smem_u32(ring);
-            const uint64_t wdesc0 = make_desc(smem_u32(wsm), B_CHUNK, 128, 0);
-            uint32_t cnt = 0;
-            long long it = 0;
-            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-                const Unit un = decode_unit(p, u);
-                for (int t = 0; t < un.zlen; ++t, ++it) {
-                    const int acc = (int)(it & 1);
-                    mbar_wait(&tempty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
-                    for (int dz = (t == 0 ? 0 : 2); dz < 3; ++dz) {
-                        const uint32_t c = cnt + t + dz;
-                        mbar_wait(&full[c % R], (c / R) & 1);
-                    }
-                    tc_fence_after();
-                    const uint32_t dcol = tmem_base + (uint32_t)(acc * NPAD);
-                    // descriptors = per-plane base + compile-time offsets (one 64-bit add per operand)
-#pragma unroll
-                    for (int dz = 0; dz < 3; ++dz) {
-                        const uint32_t pbase = ring_u32 + ((cnt + t + dz) % R) * (uint32_t)Cfg::SLOT_BYTES;
-                        if (CIN >= 16) {
-                            const uint64_t abase = make_desc(pbase, RG_KCH_PAD, RG_WW * 16, 0);
-                            const uint64_t bbase = desc_advance(wdesc0, (uint32_t)(dz * 9 * (CIN / 16)) * B_STEP);
-#pragma unroll
-                            for (int tp = 0; tp < 9; ++tp) {
-#pragma unroll
-                                for (int ks = 0; ks < CIN / 16; ++ks) {
-                                    const uint64_t ad = desc_advance(abase, (uint32_t)(2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16));
-                                    const uint64_t bd = desc_advance(bbase, (uint32_t)(tp * (CIN / 16) + ks) * B_STEP);
-                                    if (dz == 0 && tp == 0 && ks == 0) tc_mma_bf16_first(dcol, ad, bd, IDESC, leader);
-                                    else tc_mma_bf16_acc(dcol, ad, bd, IDESC, leader);
-                                }
-                            }
-                        } else {
-                            const uint64_t bbase = desc_advance(wdesc0, (uint32_t)(dz * 5) * B_STEP);
-#pragma unroll
-                            for (int pr = 0; pr < 5; ++pr) {
-                                // tap pairs (0,1) (2,3) (4,5) (6,7) and (7*,8): the 9th tap is paired with a
-                                // second, zero-weighted read of tap 7 so that every operand byte is real data
-                                // (an out-of-plane phantom multiplies uninitialised shared memory by 0 -> NaN)
-                                const int ta = (pr < 4) ? 2 * pr : 7, tb = (pr < 4) ? 2 * pr + 1 : 8;
-                                const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
-                                const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
-                                const uint32_t lbo = offb - offa;
-                                // LBO differs per tap pair: fold it into the constant part of the descriptor
-                                const uint64_t ad = desc_advance(make_desc(pbase, 0, RG_WW * 16, 0), offa) |
-                                                    ((uint64_t)(lbo >> 4) << 16);
-                                const uint64_t bd = desc_advance(bbase, (uint32_t)pr * B_STEP);
-                                if (dz == 0 && pr == 0) tc_mma_bf16_first(dcol, ad, bd, IDESC, leader);
-                                else tc_mma_bf16_acc(dcol, ad, bd, IDESC, leader);
-                            }
-                        }
-                    }
-                    tc_commit_leader(&empty[(cnt + t) % R], leader);
-                    if (t == un.zlen - 1) {
-                        tc_commit_leader(&empty[(cnt + t + 1) % R], leader);
-                        tc_commit_leader(&empty[(cnt + t + 2) % R], leader);
-                    }
-                    tc_commit_leader(&tfull[acc], leader);
+        const uint32_t leader = elect_one();
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t ring_u32 = smem_u32(ring);
+        constexpr uint32_t A_HI = (uint32_t)((RG_WW * 16) >> 4) | (1u << 14);          // SBO = next y row
+        constexpr uint32_t B_HI = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = next 8 rows
+        constexpr uint32_t A_LBO = (CIN >= 16) ? ((uint32_t)(RG_KCH_PAD >> 4) << 16) : 0u;
+        const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | ((uint32_t)((Cfg::NROWS * 16) >> 4) << 16);
+        uint32_t cnt = 0;          // input planes consumed (ring position)
+        uint32_t nbase = 0;        // output planes of all previous units (accumulator ring position)
+        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const Unit un = decode_unit(p, u);
+            const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
+            for (int i = ibeg; i <= iend; ++i, ++cnt) {
+                const int tlo = max(0, i - 2), thi = min(un.zlen - 1, i);
+                const int len = thi - tlo + 1, f = i - tlo;
+                // accumulator groups of the run; the group behind it may be touched with zero weights
+                // (CP = 8), so it must have been drained as well
+                const uint32_t nlo = nbase + (uint32_t)tlo;
+                const uint32_t nwait = nbase + (uint32_t)thi + (CP == 8 ? 1u : 0u);
+                mbar_wait(&tempty[nwait % G], ((nwait / G) & 1) ^ 1);
+                if (CP == 8) {
+                    const uint32_t nw2 = nbase + (uint32_t)thi;
+                    mbar_wait(&tempty[nw2 % G], ((nw2 / G) & 1) ^ 1);
                 }
-                cnt += (uint32_t)un.zlen + 2;
+                mbar_wait(&full[cnt % R], (cnt / R) & 1);
+                tc_fence_after();
+                const uint32_t g0 = nlo % G;
+                const int len1 = min(len, G - (int)g0), len2 = len - len1;
+                uint32_t boff1, idesc1, boff2 = 0, idesc2 = 0;
+                ring_window<CP>(f, len1, boff1, idesc1);
+                if (len2 > 0) ring_window<CP>(f - len1, len2, boff2, idesc2);
+                const uint32_t d1 = tmem_base + g0 * (uint32_t)CP, d2 = tmem_base;
+                const uint32_t b1 = b_lo0 + (boff1 >> 4), b2 = b_lo0 + (boff2 >> 4);
+                const uint32_t a_lo0 = ((ring_u32 + (cnt % R) * (uint32_t)Cfg::SLOT_BYTES) >> 4) | A_LBO;
+#pragma unroll
+                for (int s = 0; s < Cfg::NSTEPS; ++s) {
+                    uint32_t aoff;
+                    if (CIN >= 16) {
+                        const int tp = s / (CIN / 16), ks = s % (CIN / 16);
+                        aoff = (uint32_t)((2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16) >> 4);
+                    } else {
+                        // tap pairs (0,1) (2,3) (4,5) (6,7) (7*,8): the 9th tap is paired with a second,
+                        // zero-weighted read of tap 7 so that every operand byte is real data
+                        const int ta = (s < 4) ? 2 * s : 7, tb = (s < 4) ? 2 * s + 1 : 8;
+                        const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
+                        const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
+                        aoff = (offa >> 4) | (((offb - offa) >> 4) << 16);
+                    }
+                    const uint32_t bstep = (uint32_t)(s * Cfg::STEP_BYTES) >> 4;
+                    tc_mma_lohi(d1, a_lo0 + aoff, A_HI, b1 + bstep, B_HI, idesc1, leader);
+                    if (len2 > 0) tc_mma_lohi(d2, a_lo0 + aoff, A_HI, b2 + bstep, B_HI, idesc2, leader);
+                }
+                tc_commit_leader(&empty[cnt % R], leader);
+                // output planes whose last contribution this was
+                if (i - 2 >= 0 && i - 2 < un.zlen) {
+                    const uint32_t n = nbase + (uint32_t)(i - 2);
+                    tc_commit_leader(&tfull[n % G], leader);
+                }
+                if (i == iend) {
+                    for (int t = max(0, i - 1); t < un.zlen; ++t) {
+                        const uint32_t n = nbase + (uint32_t)t;
+                        tc_commit_leader(&tfull[n % G], leader);
+                    }
+                }
             }
+            nbase += (uint32_t)un.zlen;
         }
     } else {
         // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
         const int g = warp & 3;
         const int row = g * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
-        constexpr int NRED = 2 * NPAD;
-        float run[NRED];
+        float run[2 * CP];
 #pragma unroll
-        for (int i = 0; i < NRED; ++i) run[i] = 0.f;
+        for (int k = 0; k < 2 * CP; ++k) run[k] = 0.f;
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
-        long long it = 0;
+        uint32_t n = 0;
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const Unit un = decode_unit(p, u);
-            const int y = un.y0 + ty, x = un.x0 + tx;
-            const bool valid = y < p.H && x < p.W;
-            const size_t obase = valid ? ((((size_t)un.b * p.D + un.z0) * p.H + y) * p.W + x) * p.Cout + p.coff : 0;
+            const int y = un.y0 + ty, xq = un.x0 + tx;
+            const bool valid = y < p.H && xq < p.W;
+            const size_t obase = valid ? ((((size_t)un.b * p.D + un.z0) * p.H + y) * p.W + xq) * p.Cout + p.coff : 0;
             const size_t zstride = (size_t)p.H * p.W * p.Cout;
-            for (int t = 0; t < un.zlen; ++t, ++it) {
-                const int acc = (int)(it & 1);
-                mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
+            for (int t = 0; t < un.zlen; ++t, ++n) {
+                const uint32_t grp = n % G;
+                mbar_wait(&tfull[grp], (n / G) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
-                const float* brow = nullptr;
-                if (bias != nullptr && valid) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + grp * (uint32_t)CP;
+                float v[CP];
+#pragma unroll
+                for (int c = 0; c < CP; c += 8) tc_ld8(taddr + c, v + c);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < CP; c += 8) tc_st8_zero(taddr + c);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[grp]);
+                if (!valid) continue;
+                float* op = out + obase + (size_t)t * zstride;
+                if (bias != nullptr) {
+                    // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
                     const int z = un.z0 + t;
                     const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
-                    brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + x) * p.Cout + p.coff;
+                    const float* brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xq) * p.Cout + p.coff;
+                    if (vec4) {
+#pragma unroll
+                        for (int c = 0; c < CP; c += 4)
+                            if (c < p.ncols) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + c));
+                                v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
+                            }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CP; ++c)
+                            if (c < p.ncols) v[c] += __ldg(brow + c);
+                    }
                 }
-                epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + obase + (size_t)t * zstride, p.ncols, vec4,
-                                    stats != nullptr, run, brow);
+                if (vec4) {
+#pragma unroll
+                    for (int c = 0; c < CP; c += 4)
+                        if (c < p.ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CP; ++c)
+                        if (c < p.ncols) op[c] = v[c];
+                }
+                if (stats != nullptr) {
+                    // per-THREAD running moments (row = this thread's voxel): no cross-lane traffic per tile
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) {
+                        run[c] += v[c];
+                        run[CP + c] = fmaf(v[c], v[c], run[CP + c]);
+                    }
+                }
             }
         }
-        if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
+        if (stats != nullptr) {
+            // [sums | sums of squares] of this thread -> warp totals -> fp64 atomics
+#pragma unroll
+            for (int k = 0; k < 2 * CP; ++k) {
+                float tot = run[k];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                const int c = k % CP;
+                if (lane == 0 && c < p.ncols) atomicAdd(&stats[(k < CP ? 0 : p.Cout) + p.coff + c], (double)tot);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+                     : "memory");
     }
 }
 
-// weight image of one slab: [step][2 chunks][NPAD rows][8 channels] bf16 (see header comment)
-__global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int npad, int nslabs,
+// weight image of one Cout slab: [step][2 chunks][NROWS rows][8 channels] bf16; the rows are groups of
+// CP output channels, each group holding one z tap (or zeros), see ring_window()
+__global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int cp, int nslabs,
                             __nv_bfloat16* __restrict__ out) {
     const int nsteps = ring_nsteps(Cin);
+    const int nrows = (cp == 8) ? 64 : 3 * cp;
     const int slab = blockIdx.x / nsteps, step = blockIdx.x % nsteps;
-    __nv_bfloat16* o = out + ((size_t)slab * nsteps + step) * 2 * npad * 8;
-    for (int i = threadIdx.x; i < 2 * npad * 8; i += blockDim.x) {
-        const int chunk = i / (npad * 8), n = (i / 8) % npad, e = i % 8;
-        int tap, k;
+    __nv_bfloat16* o = out + ((size_t)slab * nsteps + step) * 2 * nrows * 8;
+    for (int i = threadIdx.x; i < 2 * nrows * 8; i += blockDim.x) {
+        const int chunk = i / (nrows * 8), r = (i / 8) % nrows, e = i % 8;
+        const int grp = r / cp, n = r % cp;
+        int dz;
+        if (cp == 8) {
+            const int map[8] = {2, -1, 1, -1, 2, 1, 0, -1};
+            dz = map[grp];
+        } else {
+            dz = 2 - grp;
+        }
+        int tap2d, k;
         if (Cin >= 16) {
-            tap = step / (Cin / 16);
+            tap2d = step / (Cin / 16);
             k = ((step % (Cin / 16)) * 2 + chunk) * 8 + e;
         } else {
-            const int dz = step / 5, pr = step % 5;
             // pairs (0,1) (2,3) (4,5) (6,7) (7*,8): chunk 0 of the last pair is a zero-weighted re-read of tap 7
-            const int tp = (pr < 4) ? 2 * pr + chunk : (chunk == 0 ? -1 : 8);
-            tap = (tp >= 0) ? dz * 9 + tp : -1;
+            tap2d = (step < 4) ? 2 * step + chunk : (chunk == 0 ? -1 : 8);
             k = e;
         }
-        const int co = slab * npad + n;
+        const int co = slab * cp + n;
         float val = 0.f;
-        if (tap >= 0 && co < Cout) val = w[((size_t)tap * Cin + k) * Cout + co];
+        if (dz >= 0 && tap2d >= 0 && co < Cout) val = w[((size_t)(dz * 9 + tap2d) * Cin + k) * Cout + co];
         o[i] = __float2bfloat16_rn(val);
     }
 }
 
-template <int CIN, int NPAD>
+template <int CIN, int CP, int MINB>
 int launch_ring(const __nv_bfloat16* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
                 const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, CP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_ring<CIN, NPAD><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
+    k_conv3d_ring<CIN, CP, MINB><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
 
+size_t ring_slab_bytes(int Cin, int cp) { return (size_t)ring_nsteps(Cin) * 2 * ((cp == 8) ? 64 : 3 * cp) * 16; }
+
 }  // namespace
 
+// columns per output plane: the smallest of {8, 16, 32} covering Cout (more output channels: slabs of 32)
 int ring_npad(int Cin, int Cout) {
-    int npad = Cout <= 16 ? 16 : Cout <= 32 ? 32 : 64;
-    while (npad > 16 && (size_t)ring_nsteps(Cin) * 2 * npad * 16 > 120 * 1024) npad >>= 1;
-    return npad;
+    (void)Cin;
+    return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32;
 }
 
 size_t ring_weight_bytes(int Cin, int Cout) {
-    const int npad = ring_npad(Cin, Cout);
-    const int nslabs = (Cout + npad - 1) / npad;
-    return (size_t)nslabs * ring_nsteps(Cin) * 2 * npad * 16;
+    const int cp = ring_npad(Cin, Cout);
+    const int nslabs = (Cout + cp - 1) / cp;
+    return (size_t)nslabs * ring_slab_bytes(Cin, cp);
 }
 
 int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st) {
-    const int npad = ring_npad(Cin, Cout);
-    const int nslabs = (Cout + npad - 1) / npad;
-    k_pack_ring<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, npad, nslabs, (__nv_bfloat16*)wimg);
+    const int cp = ring_npad(Cin, Cout);
+    const int nslabs = (Cout + cp - 1) / cp;
+    k_pack_ring<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, cp, nslabs, (__nv_bfloat16*)wimg);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -335,17 +473,31 @@ bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
 
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
               double* stats, const float* bias, cudaStream_t st) {
-    const int npad = ring_npad(Cin, Cout);
-    const int nslabs = (Cout + npad - 1) / npad;
+    const int cp = ring_npad(Cin, Cout);
+    const int nslabs = (Cout + cp - 1) / cp;
     const int sms = atvs_num_sms();
     RingParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
     p.nXT = (W + RG_TX - 1) / RG_TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
+    p.wbytes = (int)ring_slab_bytes(Cin, cp);
+    const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
+    const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * 8 + 2 * RG_MAXG + 1) * 8 + 16;
+    // two co-resident CTAs per SM when 2 x (weights + 4 planes) fit: their producer / MMA / epilogue
+    // handshake latencies overlap
+    int minb = (fixed + 4 * slot <= 110 * 1024) ? 2 : 1;
+    const size_t budget = (minb == 2 ? 110 : 220) * 1024;
+    int nring = (int)((budget - fixed) / slot);
+    if (nring > 8) nring = 8;
+    if (nring < 2) {
+        atvs_set_error("atvs_conv3d_bf16(ring): weights do not fit next to 2 ring planes (Cin=%d Cout=%d)", Cin, Cout);
+        return ATVS_E_UNSUP;
+    }
+    p.nring = nring;
     {   // z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
-        const long long slots = (long long)sms * ((Cin <= 16 && ring_npad(Cin, Cout) == 16) ? 2 : 1);
+        const long long slots = (long long)sms * minb;
         long long best = -1;
         int bz = D;
         for (int zs = (D < 4 ? D : 4); zs <= D; ++zs) {
@@ -357,29 +509,22 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         p.nZS = (D + bz - 1) / bz;
         p.nunits = cols * p.nZS;
     }
-    p.wbytes = ring_nsteps(Cin) * 2 * npad * 16;
-    const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
-    const int minb = (Cin <= 16 && npad == 16) ? 2 : 1;
-    const size_t budget = (minb == 2 ? 100 : 208) * 1024;
-    int nring = (int)((budget - (size_t)((p.wbytes + 127) & ~127)) / slot);
-    if (nring > 8) nring = 8;
-    if (nring < 4) {
-        atvs_set_error("atvs_conv3d_bf16(ring): weights do not fit next to 4 ring planes (Cin=%d Cout=%d)", Cin, Cout);
-        return ATVS_E_UNSUP;
-    }
-    p.nring = nring;
-    const size_t smem = 128 + ((p.wbytes + 127) & ~127) + (size_t)nring * slot + (2 * nring + 5) * 8 + 16;
+    const size_t smem = fixed + (size_t)nring * slot;
     const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
     for (int slab = 0; slab < nslabs; ++slab) {
-        p.coff = slab * npad;
-        p.ncols = (Cout - p.coff < npad) ? Cout - p.coff : npad;
+        p.coff = slab * cp;
+        p.ncols = (Cout - p.coff < cp) ? Cout - p.coff : cp;
         const uint8_t* wi = (const uint8_t*)wimg + (size_t)slab * p.wbytes;
         int rc = 0;
-#define RG_CASE(CI, NP) if (Cin == CI && npad == NP) rc = launch_ring<CI, NP>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st); else
-        RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(8, 64) RG_CASE(16, 16) RG_CASE(16, 32) RG_CASE(16, 64)
-        RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(32, 64) RG_CASE(64, 16) RG_CASE(64, 32)
+#define RG_CASE(CI, CPV)                                                                                              \
+    if (Cin == CI && cp == CPV) {                                                                                     \
+        rc = (minb == 2) ? launch_ring<CI, CPV, 2>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st) \
+                         : launch_ring<CI, CPV, 1>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st); \
+    } else
+        RG_CASE(8, 8) RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(16, 8) RG_CASE(16, 16) RG_CASE(16, 32)
+        RG_CASE(32, 8) RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(64, 8) RG_CASE(64, 16) RG_CASE(64, 32)
         {
-            atvs_set_error("atvs_conv3d_bf16(ring): no kernel for Cin=%d N=%d", Cin, npad);
+            atvs_set_error("atvs_conv3d_bf16(ring): no kernel for Cin=%d CP=%d", Cin, cp);
             return ATVS_E_UNSUP;
         }
 #undef RG_CASE

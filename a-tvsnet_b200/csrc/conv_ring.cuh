@@ -9,8 +9,9 @@
 #define RING_HD
 #endif
 
-// K=16 MMA steps per output tile: 27 taps x Cin/16, or 3 planes x 5 tap pairs for Cin = 8
-RING_HD static inline int ring_nsteps(int Cin) { return Cin >= 16 ? 27 * (Cin / 16) : 15; }
+// K=16 MMA steps per input plane: 9 in-plane taps x Cin/16, or 5 tap pairs for Cin = 8 (the three z taps
+// of a step sit side by side in the MMA N dimension)
+RING_HD static inline int ring_nsteps(int Cin) { return Cin >= 16 ? 9 * (Cin / 16) : 5; }
 
 int ring_npad(int Cin, int Cout);
 size_t ring_weight_bytes(int Cin, int Cout);

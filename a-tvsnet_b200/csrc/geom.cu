@@ -297,7 +297,7 @@ constexpr int K1_DCHUNK = 8;
 // float4 kept in registers; every plane's slice goes straight to HBM with streaming stores.
 template <typename OutT, int MODE, bool WARP_REF>
 __global__ void __launch_bounds__(256)
-k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ view, const float* __restrict__ hv,
+k_build_cost_volume_generic(const float* __restrict__ ref, const float* __restrict__ view, const float* __restrict__ hv,
                     const float* __restrict__ hr, int D, int h, int w, int F, OutT* __restrict__ out) {
     const int G = F >> 2;
     const int hw = h * w;
@@ -338,6 +338,92 @@ k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ vie
             wv.z = MUL(fabsf(SUB(wv.z, r.z)), m);
             wv.w = MUL(fabsf(SUB(wv.w, r.w)), m);
             store4(o + g * 4, wv);
+        }
+    }
+}
+
+
+// K1, shared-coordinate version (F/4 = G lanes per pixel, G a power of two <= 32).  The G lanes of a
+// pixel need the SAME sample cell and weights for a plane, and the IEEE divisions of the homography
+// are the expensive part of the kernel: each lane therefore evaluates the homography of a different
+// plane of the 8-plane chunk (lane g -> planes g, g+G, ...), and the loop over planes fetches the
+// cell index and the four area weights from the owning lane with width-G shuffles.
+//   cell: y0*w + x0  |  -1 = outside (output exactly 0, homography_warping.py:39-43,97-99)  |  -2 = not finite
+template <typename OutT>
+__device__ __forceinline__ float blend_out(float wa, float wb, float wc, float wd, float a, float b, float c, float d) {
+    if (sizeof(OutT) == 4) return ADD(ADD(ADD(MUL(wa, a), MUL(wb, b)), MUL(wc, c)), MUL(wd, d));   // oracle order
+    return fmaf(wd, d, fmaf(wc, c, fmaf(wb, b, wa * a)));          // bf16 volume: rounding dominates
+}
+
+template <typename OutT, int MODE, int G>
+__global__ void __launch_bounds__(256)
+k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ view, const float* __restrict__ hv,
+                    int D, int h, int w, OutT* __restrict__ out) {
+    constexpr int F = 4 * G;
+    constexpr int NS = (G >= K1_DCHUNK) ? 1 : K1_DCHUNK / G;      // samples evaluated per lane
+    const int hw = h * w;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < hw * G;
+    const int g = idx % G, pix = live ? idx / G : hw - 1;
+    const int x = pix % w, y = pix / w;
+    const int b = blockIdx.z;
+    const float* viewb = view + (size_t)b * hw * F;
+    constexpr int CO = (MODE == 0) ? 2 * F : F;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE != 1) r = __ldg(reinterpret_cast<const float4*>(ref + ((size_t)b * hw + pix) * F + g * 4));
+    const int d0 = blockIdx.y * K1_DCHUNK;
+    int cell[NS];
+    float wa[NS], wb[NS], wc[NS], wd[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int d = d0 + g + k * G;
+        cell[k] = -1;
+        wa[k] = wb[k] = wc[k] = wd[k] = 0.f;
+        if (g + k * G < K1_DCHUNK && d < D) {
+            float u, v;
+            homography_uv(hv + ((size_t)b * D + d) * 9, x, y, u, v);
+            const Sample s = make_sample(u, v, h, w);
+            cell[k] = s.valid ? s.y0 * w + s.x0 : (s.finite ? -1 : -2);
+            wa[k] = s.wa; wb[k] = s.wb; wc[k] = s.wc; wd[k] = s.wd;
+        }
+    }
+    OutT* o = out + (((size_t)b * D + d0) * hw + pix) * CO + g * 4;
+    const size_t ostride = (size_t)hw * CO;
+#pragma unroll
+    for (int j = 0; j < K1_DCHUNK; ++j) {
+        const int k = (G >= K1_DCHUNK) ? 0 : j / G;
+        const int src = j % G;
+        const int c = __shfl_sync(0xffffffffu, cell[k], src, G);
+        const float a0 = __shfl_sync(0xffffffffu, wa[k], src, G), a1 = __shfl_sync(0xffffffffu, wb[k], src, G);
+        const float a2 = __shfl_sync(0xffffffffu, wc[k], src, G), a3 = __shfl_sync(0xffffffffu, wd[k], src, G);
+        if (d0 + j >= D) break;
+        float4 wv;
+        if (c >= 0) {
+            const float* p = viewb + (size_t)c * F + g * 4;
+            const float4 A = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 Bq = __ldg(reinterpret_cast<const float4*>(p + F));
+            const float4 C = __ldg(reinterpret_cast<const float4*>(p + (size_t)w * F));
+            const float4 Dq = __ldg(reinterpret_cast<const float4*>(p + (size_t)w * F + F));
+            wv = make_float4(blend_out<OutT>(a0, a1, a2, a3, A.x, Bq.x, C.x, Dq.x), blend_out<OutT>(a0, a1, a2, a3, A.y, Bq.y, C.y, Dq.y),
+                             blend_out<OutT>(a0, a1, a2, a3, A.z, Bq.z, C.z, Dq.z), blend_out<OutT>(a0, a1, a2, a3, A.w, Bq.w, C.w, Dq.w));
+        } else {
+            const float z = (c == -1) ? 0.0f : __int_as_float(0x7fc00000);
+            wv = make_float4(z, z, z, z);
+        }
+        if (!live) continue;
+        OutT* oj = o + (size_t)j * ostride;
+        if (MODE == 0) {
+            store4(oj, r);
+            store4(oj + F, wv);
+        } else if (MODE == 1) {
+            store4(oj, wv);
+        } else {
+            const float m = (c >= 0) ? 1.0f : 0.0f;   // model.py:277-278
+            wv.x = MUL(fabsf(SUB(wv.x, r.x)), m);
+            wv.y = MUL(fabsf(SUB(wv.y, r.y)), m);
+            wv.z = MUL(fabsf(SUB(wv.z, r.z)), m);
+            wv.w = MUL(fabsf(SUB(wv.w, r.w)), m);
+            store4(oj, wv);
         }
     }
 }
@@ -410,6 +496,74 @@ k_prob2depth(const float* __restrict__ vol, int B, int D, int H, int W, const fl
     }
 }
 
+
+// K4 at the volume's own resolution: 32 pixels x 8 depth slices per block (warp = slice, lanes =
+// consecutive pixels -> 128-byte coalesced plane reads).  Every slice runs an online softmax over
+// its planes d = slice, slice+8, ...; the 8 partial (max, sum, weighted sum) triples are merged
+// through shared memory.  20480 pixels would otherwise be 80 blocks of serial 128-plane loops.
+constexpr int K4_SLICES = 8;
+__global__ void __launch_bounds__(256)
+k_prob2depth_sliced(const float* __restrict__ vol, int B, int D, long long plane, const float* __restrict__ dstart,
+                    const float* __restrict__ dint, float* __restrict__ depth, float* __restrict__ prob) {
+    __shared__ float sm_m[K4_SLICES][32], sm_s[K4_SLICES][32], sm_w[K4_SLICES][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const long long total = (long long)B * plane;
+    const long long idx = (long long)blockIdx.x * 32 + lane;
+    const bool live = idx < total;
+    const long long pidx = live ? idx : total - 1;
+    const int b = (int)(pidx / plane);
+    const float* vb = vol + (size_t)b * D * plane + (size_t)(pidx - (long long)b * plane);
+    const float ds = dstart[b], di = dint[b];
+    const float de = ADD(ds, MUL(SUB((float)D, 1.0f), di));
+    const float step = DIV(SUB(de, ds), (float)max(D - 1, 1));
+    float m = -INFINITY, s = 0.f, ws = 0.f;
+#pragma unroll 4
+    for (int d = slice; d < D; d += K4_SLICES) {
+        const float t = -__ldg(vb + (size_t)d * plane);
+        if (t > m) {
+            const float sc = expf(m - t);
+            s *= sc;
+            ws *= sc;
+            m = t;
+        }
+        const float e = expf(t - m);
+        s += e;
+        ws += ADD(ds, MUL((float)d, step)) * e;
+    }
+    sm_m[slice][lane] = m;
+    sm_s[slice][lane] = s;
+    sm_w[slice][lane] = ws;
+    __syncthreads();
+    if (slice != 0 || !live) return;
+    float M = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K4_SLICES; ++k) M = fmaxf(M, sm_m[k][lane]);
+    float S = 0.f, WS = 0.f;
+#pragma unroll
+    for (int k = 0; k < K4_SLICES; ++k) {
+        const float mk = sm_m[k][lane];
+        if (mk == -INFINITY) continue;                     // slice without planes (D < 8)
+        const float sc = expf(mk - M);
+        S = fmaf(sm_s[k][lane], sc, S);
+        WS = fmaf(sm_w[k][lane], sc, WS);
+    }
+    const float est = WS / S;
+    depth[idx] = est;
+    if (prob) {
+        const float t = DIV(SUB(est, ds), di);
+        const int l0 = min(max((int)floorf(t), 0), D - 1);
+        const int l1 = min(max(l0 - 1, 0), D - 1);
+        const int r0 = min(max((int)ceilf(t), 0), D - 1);
+        const int r1 = min(max(r0 + 1, 0), D - 1);
+        const float inv = 1.0f / S;
+        float pr = expf(-__ldg(vb + (size_t)l0 * plane) - M) * inv;
+        pr += expf(-__ldg(vb + (size_t)l1 * plane) - M) * inv;
+        pr += expf(-__ldg(vb + (size_t)r0 * plane) - M) * inv;
+        pr += expf(-__ldg(vb + (size_t)r1 * plane) - M) * inv;
+        prob[idx] = pr;
+    }
+}
+
 }  // namespace
 
 // =========================================================================== C ABI
@@ -471,12 +625,32 @@ extern "C" int atvs_homography_warping_by_depth(const float* image, const float*
     return rc;
 }
 
+template <typename OutT, int G>
+static void launch_k1_shared(const float* ref, const float* view, const float* hv, int D, int h, int w, int mode,
+                             OutT* out, dim3 grid, cudaStream_t st) {
+    if (mode == 0) k_build_cost_volume<OutT, 0, G><<<grid, 256, 0, st>>>(ref, view, hv, D, h, w, out);
+    else if (mode == 1) k_build_cost_volume<OutT, 1, G><<<grid, 256, 0, st>>>(ref, view, hv, D, h, w, out);
+    else k_build_cost_volume<OutT, 2, G><<<grid, 256, 0, st>>>(ref, view, hv, D, h, w, out);
+}
+
 template <typename OutT>
 static int launch_k1(const float* ref, const float* view, const float* hv, const float* hr, int B, int D, int h, int w,
                      int F, int mode, OutT* out, cudaStream_t st) {
     const int G = F / 4;
     dim3 grid((unsigned)(((long long)h * w * G + 255) / 256), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
-#define K1_GO(MODE, WR) k_build_cost_volume<OutT, MODE, WR><<<grid, 256, 0, st>>>(ref, view, hv, hr, D, h, w, F, out)
+    if (!hr && (G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32)) {
+        switch (G) {
+            case 1: launch_k1_shared<OutT, 1>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+            case 2: launch_k1_shared<OutT, 2>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+            case 4: launch_k1_shared<OutT, 4>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+            case 8: launch_k1_shared<OutT, 8>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+            case 16: launch_k1_shared<OutT, 16>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+            default: launch_k1_shared<OutT, 32>(ref, view, hv, D, h, w, mode, out, grid, st); break;
+        }
+        ATVS_LAUNCH_CHECK();
+        return 0;
+    }
+#define K1_GO(MODE, WR) k_build_cost_volume_generic<OutT, MODE, WR><<<grid, 256, 0, st>>>(ref, view, hv, hr, D, h, w, F, out)
     if (hr) {
         if (mode == 0) K1_GO(0, true);
         else if (mode == 2) K1_GO(2, true);
@@ -525,7 +699,8 @@ extern "C" int atvs_prob2depth(const float* prob_volume, int B, int D, int H, in
     const unsigned grid = (unsigned)((total + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (up == 1)
-        k_prob2depth<1><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
+        k_prob2depth_sliced<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(prob_volume, B, D, (long long)H * W, depth_start,
+                                                                         depth_interval, depth, prob_map);
     else
         k_prob2depth<4><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
     ATVS_LAUNCH_CHECK();
