@@ -30,11 +30,27 @@
 #include "tc_ptx.cuh"
 #include "conv_ring.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
-constexpr int RG_TY = 16, RG_TX = 8, RG_HH = 18, RG_WW = 10;
-constexpr int RG_NVOX = RG_HH * RG_WW;              // voxels of one halo plane (180)
+#ifdef ATVS_RING_TRACE
+#define TRACE_DECL long long tr_[3][48]; int trn_ = 0; for (int q_ = 0; q_ < 48; ++q_) tr_[0][q_] = tr_[1][q_] = tr_[2][q_] = 0;
+#define TRACE(k) do { if (blockIdx.x == 0 && trn_ < 48) tr_[k][trn_] = clock64(); } while (0)
+#define TRACE_NEXT() do { ++trn_; } while (0)
+#define TRACE_DUMP(name) do { if (blockIdx.x == 0) for (int q_ = 0; q_ < 48 && q_ < trn_; ++q_) printf("%s %d %lld %lld %lld\n", name, q_, tr_[0][q_], tr_[1][q_], tr_[2][q_]); } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(k)
+#define TRACE_NEXT()
+#define TRACE_DUMP(name)
+#endif
+
+// one CTA plane = RG_MT MMA tiles (16 y x 8 x each) side by side in x: every mbarrier handshake of the
+// producer / MMA / epilogue pipeline (~200 cycles each, ~4 per role and plane) then serves 256 voxels
+constexpr int RG_MT = 2;
+constexpr int RG_TY = 16, RG_TX = 8 * RG_MT, RG_HH = RG_TY + 2, RG_WW = RG_TX + 2;
+constexpr int RG_NVOX = RG_HH * RG_WW;              // voxels of one halo plane (324)
 constexpr int RG_KCH_PAD = RG_NVOX * 16 + 16;       // pitch of one 8-channel chunk plane; +16 B keeps the
                                                     // 8 chunk stores of a voxel on distinct banks
 constexpr int RG_PRODUCERS = 128;
@@ -47,6 +63,7 @@ struct RingParams {
     int nXT, nYT, nZS, ZS;
     int nring;
     int wbytes;
+    int dbg;            // ATVS_RING_DEBUG bit mask (tools/conv_probe.py): 1 no loads, 2 no MMAs, 4 no stores, 8 no zeroing
     long long nunits;
 };
 
@@ -58,7 +75,8 @@ struct RingCfg {
     static constexpr int G = (CP == 8) ? 15 : 8;                        // accumulator groups in the ring
     static constexpr int NROWS = (CP == 8) ? 64 : 3 * CP;               // rows of one weight step image
     static constexpr int STEP_BYTES = 2 * NROWS * 16;
-    static constexpr uint32_t TMEM_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy
+    static constexpr uint32_t TILE_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy
+    static constexpr uint32_t TMEM_COLS = RG_MT * TILE_COLS;
 };
 
 struct Unit {
@@ -85,6 +103,18 @@ __device__ __forceinline__ int unit_iend(const RingParams& p, const Unit& u) {
     return (u.z0 + u.zlen == p.D) ? u.zlen : u.zlen + 1;
 }
 
+// warp-converged wait: every lane polls, the vote makes the loop condition (and everything computed
+// after it) provably warp-uniform for the compiler
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (++spins > TC_SPIN_LIMIT) {
+            printf("atvs conv_ring: mbarrier timeout (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
+            __trap();
+        }
+    }
+}
+
 // MMA with the descriptors given as (lo, hi) halves: the hi halves are loop constants and the lo halves
 // change by one 32-bit add per instruction
 __device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -97,6 +127,18 @@ __device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint
         "mov.b64 bd, {%3, %4};\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_mma_lohi1(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 ad, {%1, %2};\n\t"
+        "mov.b64 bd, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
 }
 
@@ -198,113 +240,167 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
             mbar_expect_tx(wbar, (uint32_t)p.wbytes);
             bulk_copy_g2s(wsm, wimg, (uint32_t)p.wbytes, wbar);
         }
+        // this thread's share of a halo plane: items j = ptid + k*128 -> (chunk c, halo voxel v).  The
+        // shared-memory offsets never change and the global offsets change once per unit, so one plane
+        // costs a handful of instructions per item.
+        constexpr int NITEM = (Cfg::NKC * RG_NVOX + RG_PRODUCERS - 1) / RG_PRODUCERS;
         // up to PF planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
         // mbarrier arrive) once plane q+PF-1 has been issued.  PF <= R-1 keeps the ring deadlock-free.
         const int PF = (R >= 5) ? 4 : (R >= 3 ? 2 : 1);
-        uint32_t cnt = 0, published = 0;
-        auto publish_upto = [&](uint32_t upto_excl, int keep) {
+        uint32_t slot = 0, sphase = 0, pslot = 0, pending = 0;
+        const uint32_t ring_u32 = smem_u32(ring);
+        auto publish = [&](int keep) {
+            // wait until at most `keep` groups are pending, then publish every older plane
             if (keep >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
             else if (keep == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
             else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (; published < upto_excl; ++published) mbar_arrive(&full[published % R]);
+            for (; pending > (uint32_t)keep; --pending) {
+                mbar_arrive(&full[pslot]);
+                if (++pslot == (uint32_t)R) pslot = 0;
+            }
         };
+        const size_t zstride_in = (size_t)p.H * p.W * CIN;
+        TRACE_DECL
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const Unit un = decode_unit(p, u);
             const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
-            for (int i = ibeg; i <= iend; ++i, ++cnt) {
-                const int zi = un.z0 - 1 + i;
-                const uint32_t slot = cnt % R, par = (cnt / R) & 1;
-                mbar_wait(&empty[slot], par ^ 1);
-                const __nv_bfloat16* zbase = x + (((size_t)un.b * p.D + zi) * p.H) * p.W * CIN;
-                const uint32_t dst0 = smem_u32(ring + (size_t)slot * Cfg::SLOT_BYTES);
-#pragma unroll 4
-                for (int j = ptid; j < Cfg::NKC * RG_NVOX; j += RG_PRODUCERS) {
-                    const int c = j % Cfg::NKC, v = j / Cfg::NKC;
-                    const int yy = v / RG_WW, xx = v - yy * RG_WW;
-                    const int gy = un.y0 - 1 + yy, gx = un.x0 - 1 + xx;
-                    const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-                    const __nv_bfloat16* src = ok ? zbase + ((size_t)gy * p.W + gx) * CIN + c * 8 : x;
-                    const uint32_t dst = dst0 + (uint32_t)(c * RG_KCH_PAD + v * 16);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
-                                 : "memory");
+            int goff[NITEM];       // element offset inside a z plane, -1 = zero fill, -2 = no item
+#pragma unroll
+            for (int k = 0; k < NITEM; ++k) {
+                const int j = ptid + k * RG_PRODUCERS;
+                const int c = j % Cfg::NKC, v = j / Cfg::NKC;
+                const int vy = v / RG_WW, vx = v - vy * RG_WW;
+                const int gy = un.y0 - 1 + vy, gx = un.x0 - 1 + vx;
+                const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+                goff[k] = (j >= Cfg::NKC * RG_NVOX) ? -2 : (ok ? (gy * p.W + gx) * CIN + c * 8 : -1);
+            }
+            const __nv_bfloat16* zbase = x + ((size_t)un.b * p.D + (un.z0 - 1 + ibeg)) * zstride_in;
+            for (int i = ibeg; i <= iend; ++i, zbase += zstride_in) {
+                mbar_wait(&empty[slot], sphase ^ 1);
+                TRACE(0);
+                const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
+#pragma unroll
+                for (int k = 0; k < NITEM; ++k) {
+                    if (goff[k] != -2 && !(p.dbg & 1)) {
+                        const int j = ptid + k * RG_PRODUCERS;
+                        const uint32_t soff = (uint32_t)((j % Cfg::NKC) * RG_KCH_PAD + (j / Cfg::NKC) * 16);
+                        const bool ok = goff[k] >= 0;
+                        const __nv_bfloat16* src = ok ? zbase + goff[k] : x;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + soff), "l"(src),
+                                     "r"(ok ? 16 : 0)
+                                     : "memory");
+                    }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                if (cnt + 1 - published >= (uint32_t)PF) publish_upto(cnt + 2 - PF, PF - 1);
+                TRACE(1);
+                if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
+                if (++pending >= (uint32_t)PF) publish(PF - 1);
+                TRACE(2);
+                TRACE_NEXT();
             }
         }
-        if (published < cnt) publish_upto(cnt, 0);
+        publish(0);
+        if (ptid == 0) TRACE_DUMP("P");
     } else if (warp == 4) {
         // ===================== MMA issuer (converged warp, elected lane issues) =====================
-        const uint32_t leader = elect_one();
+        // One warp issues every MMA of the CTA, so its instruction stream per plane is what bounds the
+        // small-channel layers: counters are incremental (no divisions), and the steady state (three
+        // live output planes, no ring wrap) is a straight-line block.
+        if (elect_one()) {
         mbar_wait(wbar, 0);
         tc_fence_after();
-        const uint32_t ring_u32 = smem_u32(ring);
         constexpr uint32_t A_HI = (uint32_t)((RG_WW * 16) >> 4) | (1u << 14);          // SBO = next y row
         constexpr uint32_t B_HI = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = next 8 rows
         constexpr uint32_t A_LBO = (CIN >= 16) ? ((uint32_t)(RG_KCH_PAD >> 4) << 16) : 0u;
+        constexpr uint32_t FAST_BOFF = (CP == 8) ? 4u * 128u : 0u;                      // window [w2 w1 w0 (0)]
+        constexpr uint32_t FAST_IDESC = ring_idesc(CP == 8 ? 32 : 3 * CP);
+        const uint32_t a_lo_ring = (smem_u32(ring) >> 4) | A_LBO;
         const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | ((uint32_t)((Cfg::NROWS * 16) >> 4) << 16);
-        uint32_t cnt = 0;          // input planes consumed (ring position)
-        uint32_t nbase = 0;        // output planes of all previous units (accumulator ring position)
+        auto issue_plane = [&](uint32_t dcol, uint32_t a_lo0, uint32_t b_lo, uint32_t idesc) {
+#pragma unroll
+            for (int s = 0; s < Cfg::NSTEPS; ++s) {
+                uint32_t aoff;
+                if (CIN >= 16) {
+                    const int tp = s / (CIN / 16), ks = s % (CIN / 16);
+                    aoff = (uint32_t)((2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16) >> 4);
+                } else {
+                    // tap pairs (0,1) (2,3) (4,5) (6,7) (7*,8): the 9th tap is paired with a second,
+                    // zero-weighted read of tap 7 so that every operand byte is real data
+                    const int ta = (s < 4) ? 2 * s : 7, tb = (s < 4) ? 2 * s + 1 : 8;
+                    const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
+                    const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
+                    aoff = (offa >> 4) | (((offb - offa) >> 4) << 16);
+                }
+#pragma unroll
+                for (int mt = 0; mt < RG_MT; ++mt)
+                    tc_mma_lohi1(dcol + (uint32_t)mt * Cfg::TILE_COLS, a_lo0 + aoff + (uint32_t)(mt * 8), A_HI,
+                                 b_lo + ((uint32_t)(s * Cfg::STEP_BYTES) >> 4), B_HI, idesc);
+            }
+        };
+        TRACE_DECL
+        uint32_t slot = 0, sphase = 0;     // ring position of the next input plane
+        uint32_t gq = 0, gphase = 0;       // accumulator group / phase of output plane t = 0 of the unit
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const Unit un = decode_unit(p, u);
             const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
-            for (int i = ibeg; i <= iend; ++i, ++cnt) {
+            uint32_t gw = gq, gwphase = gphase;   // group / phase of the next output plane to wait for
+            int twaited = -1;
+            uint32_t glo = gq;                    // group of output plane max(0, i - 2)
+            uint32_t gdone = gq;                  // group of the next output plane to complete
+            int tdone = 0;
+            for (int i = ibeg; i <= iend; ++i) {
                 const int tlo = max(0, i - 2), thi = min(un.zlen - 1, i);
-                const int len = thi - tlo + 1, f = i - tlo;
                 // accumulator groups of the run; the group behind it may be touched with zero weights
                 // (CP = 8), so it must have been drained as well
-                const uint32_t nlo = nbase + (uint32_t)tlo;
-                const uint32_t nwait = nbase + (uint32_t)thi + (CP == 8 ? 1u : 0u);
-                mbar_wait(&tempty[nwait % G], ((nwait / G) & 1) ^ 1);
-                if (CP == 8) {
-                    const uint32_t nw2 = nbase + (uint32_t)thi;
-                    mbar_wait(&tempty[nw2 % G], ((nw2 / G) & 1) ^ 1);
+                const int tneed = thi + (CP == 8 ? 1 : 0);
+                while (twaited < tneed) {
+                    mbar_wait(&tempty[gw], gwphase ^ 1);
+                    ++twaited;
+                    if (++gw == (uint32_t)G) { gw = 0; gwphase ^= 1; }
                 }
-                mbar_wait(&full[cnt % R], (cnt / R) & 1);
+                TRACE(0);
+                mbar_wait(&full[slot], sphase);
+                TRACE(1);
                 tc_fence_after();
-                const uint32_t g0 = nlo % G;
-                const int len1 = min(len, G - (int)g0), len2 = len - len1;
-                uint32_t boff1, idesc1, boff2 = 0, idesc2 = 0;
-                ring_window<CP>(f, len1, boff1, idesc1);
-                if (len2 > 0) ring_window<CP>(f - len1, len2, boff2, idesc2);
-                const uint32_t d1 = tmem_base + g0 * (uint32_t)CP, d2 = tmem_base;
-                const uint32_t b1 = b_lo0 + (boff1 >> 4), b2 = b_lo0 + (boff2 >> 4);
-                const uint32_t a_lo0 = ((ring_u32 + (cnt % R) * (uint32_t)Cfg::SLOT_BYTES) >> 4) | A_LBO;
-#pragma unroll
-                for (int s = 0; s < Cfg::NSTEPS; ++s) {
-                    uint32_t aoff;
-                    if (CIN >= 16) {
-                        const int tp = s / (CIN / 16), ks = s % (CIN / 16);
-                        aoff = (uint32_t)((2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16) >> 4);
-                    } else {
-                        // tap pairs (0,1) (2,3) (4,5) (6,7) (7*,8): the 9th tap is paired with a second,
-                        // zero-weighted read of tap 7 so that every operand byte is real data
-                        const int ta = (s < 4) ? 2 * s : 7, tb = (s < 4) ? 2 * s + 1 : 8;
-                        const uint32_t offa = (uint32_t)(((ta / 3) * RG_WW + (ta % 3)) * 16);
-                        const uint32_t offb = (uint32_t)(((tb / 3) * RG_WW + (tb % 3)) * 16);
-                        aoff = (offa >> 4) | (((offb - offa) >> 4) << 16);
-                    }
-                    const uint32_t bstep = (uint32_t)(s * Cfg::STEP_BYTES) >> 4;
-                    tc_mma_lohi(d1, a_lo0 + aoff, A_HI, b1 + bstep, B_HI, idesc1, leader);
-                    if (len2 > 0) tc_mma_lohi(d2, a_lo0 + aoff, A_HI, b2 + bstep, B_HI, idesc2, leader);
-                }
-                tc_commit_leader(&empty[cnt % R], leader);
-                // output planes whose last contribution this was
-                if (i - 2 >= 0 && i - 2 < un.zlen) {
-                    const uint32_t n = nbase + (uint32_t)(i - 2);
-                    tc_commit_leader(&tfull[n % G], leader);
-                }
-                if (i == iend) {
-                    for (int t = max(0, i - 1); t < un.zlen; ++t) {
-                        const uint32_t n = nbase + (uint32_t)t;
-                        tc_commit_leader(&tfull[n % G], leader);
+                const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
+                if (p.dbg & 2) {
+                } else if (thi - tlo == 2 && glo + 3 <= (uint32_t)G) {
+                    issue_plane(tmem_base + glo * (uint32_t)CP, a_lo0, b_lo0 + (FAST_BOFF >> 4), FAST_IDESC);
+                } else {
+                    const int len = thi - tlo + 1, f = i - tlo;
+                    const int len1 = min(len, G - (int)glo), len2 = len - len1;
+                    uint32_t boff, idesc;
+                    ring_window<CP>(f, len1, boff, idesc);
+                    issue_plane(tmem_base + glo * (uint32_t)CP, a_lo0, b_lo0 + (boff >> 4), idesc);
+                    if (len2 > 0) {
+                        ring_window<CP>(f - len1, len2, boff, idesc);
+                        issue_plane(tmem_base, a_lo0, b_lo0 + (boff >> 4), idesc);
                     }
                 }
+                tc_commit(&empty[slot]);
+                if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
+                if (i >= 2 && ++glo == (uint32_t)G) glo = 0;
+                // output planes whose last contribution this was: t <= i - 2, and all of them at the end
+                const int tlast = (i == iend) ? un.zlen - 1 : i - 2;
+                while (tdone <= tlast) {
+                    tc_commit(&tfull[gdone]);
+                    ++tdone;
+                    if (++gdone == (uint32_t)G) gdone = 0;
+                }
+                TRACE(2);
+                TRACE_NEXT();
             }
-            nbase += (uint32_t)un.zlen;
+            gq = gw; gphase = gwphase;
+            if (twaited >= un.zlen) {      // the CP = 8 look-ahead waited for the next unit's first plane
+                gq = (gq == 0) ? (uint32_t)G - 1 : gq - 1;
+                if (gq == (uint32_t)G - 1) gphase ^= 1;
+            }
         }
+        TRACE_DUMP("M");
+        }
+        __syncwarp();
     } else {
         // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
         const int g = warp & 3;
@@ -314,67 +410,86 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
 #pragma unroll
         for (int k = 0; k < 2 * CP; ++k) run[k] = 0.f;
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
-        uint32_t n = 0;
+        uint32_t grp = 0, gphase = 0;
+        TRACE_DECL
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const Unit un = decode_unit(p, u);
-            const int y = un.y0 + ty, xq = un.x0 + tx;
-            const bool valid = y < p.H && xq < p.W;
-            const size_t obase = valid ? ((((size_t)un.b * p.D + un.z0) * p.H + y) * p.W + xq) * p.Cout + p.coff : 0;
+            const int y = un.y0 + ty, xq = un.x0 + tx;          // tile mt covers x = xq + 8 * mt
+            const bool yok = y < p.H;
+            const size_t obase = ((((size_t)un.b * p.D + un.z0) * p.H + (yok ? y : 0)) * p.W) * p.Cout + p.coff;
             const size_t zstride = (size_t)p.H * p.W * p.Cout;
-            for (int t = 0; t < un.zlen; ++t, ++n) {
-                const uint32_t grp = n % G;
-                mbar_wait(&tfull[grp], (n / G) & 1);
+            for (int t = 0; t < un.zlen; ++t) {
+                mbar_wait(&tfull[grp], gphase);
+                TRACE(0);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + grp * (uint32_t)CP;
-                float v[CP];
+                uint64_t* const tempty_bar = &tempty[grp];
+                if (++grp == (uint32_t)G) { grp = 0; gphase ^= 1; }
+                float v[RG_MT][CP];
 #pragma unroll
-                for (int c = 0; c < CP; c += 8) tc_ld8(taddr + c, v + c);
+                for (int mt = 0; mt < RG_MT; ++mt)
+#pragma unroll
+                    for (int c = 0; c < CP; c += 8) tc_ld8(taddr + (uint32_t)mt * Cfg::TILE_COLS + c, v[mt] + c);
                 tc_wait_ld();
+                TRACE(1);
+                if (!(p.dbg & 8)) {
 #pragma unroll
-                for (int c = 0; c < CP; c += 8) tc_st8_zero(taddr + c);
-                tc_wait_st();
+                    for (int mt = 0; mt < RG_MT; ++mt)
+#pragma unroll
+                        for (int c = 0; c < CP; c += 8) tc_st8_zero(taddr + (uint32_t)mt * Cfg::TILE_COLS + c);
+                    tc_wait_st();
+                }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[grp]);
-                if (!valid) continue;
-                float* op = out + obase + (size_t)t * zstride;
-                if (bias != nullptr) {
-                    // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
-                    const int z = un.z0 + t;
-                    const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
-                    const float* brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xq) * p.Cout + p.coff;
+                if (lane == 0) mbar_arrive(tempty_bar);
+                TRACE(2);
+                TRACE_NEXT();
+                if (!yok || (p.dbg & 4)) continue;
+                const int z = un.z0 + t;
+                const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
+#pragma unroll
+                for (int mt = 0; mt < RG_MT; ++mt) {
+                    const int xm = xq + 8 * mt;
+                    if (xm >= p.W) continue;
+                    float* op = out + obase + (size_t)t * zstride + (size_t)xm * p.Cout;
+                    if (bias != nullptr) {
+                        // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
+                        const float* brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xm) * p.Cout + p.coff;
+                        if (vec4) {
+#pragma unroll
+                            for (int c = 0; c < CP; c += 4)
+                                if (c < p.ncols) {
+                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + c));
+                                    v[mt][c] += bv.x; v[mt][c + 1] += bv.y; v[mt][c + 2] += bv.z; v[mt][c + 3] += bv.w;
+                                }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CP; ++c)
+                                if (c < p.ncols) v[mt][c] += __ldg(brow + c);
+                        }
+                    }
                     if (vec4) {
 #pragma unroll
                         for (int c = 0; c < CP; c += 4)
-                            if (c < p.ncols) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + c));
-                                v[c] += bv.x; v[c + 1] += bv.y; v[c + 2] += bv.z; v[c + 3] += bv.w;
-                            }
+                            if (c < p.ncols)
+                                *reinterpret_cast<float4*>(op + c) = make_float4(v[mt][c], v[mt][c + 1], v[mt][c + 2], v[mt][c + 3]);
                     } else {
 #pragma unroll
                         for (int c = 0; c < CP; ++c)
-                            if (c < p.ncols) v[c] += __ldg(brow + c);
+                            if (c < p.ncols) op[c] = v[mt][c];
                     }
-                }
-                if (vec4) {
+                    if (stats != nullptr) {
+                        // per-THREAD running moments (rows = this thread's voxels): no cross-lane traffic per tile
 #pragma unroll
-                    for (int c = 0; c < CP; c += 4)
-                        if (c < p.ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CP; ++c)
-                        if (c < p.ncols) op[c] = v[c];
-                }
-                if (stats != nullptr) {
-                    // per-THREAD running moments (row = this thread's voxel): no cross-lane traffic per tile
-#pragma unroll
-                    for (int c = 0; c < CP; ++c) {
-                        run[c] += v[c];
-                        run[CP + c] = fmaf(v[c], v[c], run[CP + c]);
+                        for (int c = 0; c < CP; ++c) {
+                            run[c] += v[mt][c];
+                            run[CP + c] = fmaf(v[mt][c], v[mt][c], run[CP + c]);
+                        }
                     }
                 }
             }
         }
+        if (warp == 5 && lane == 0) TRACE_DUMP("E");
         if (stats != nullptr) {
             // [sums | sums of squares] of this thread -> warp totals -> fp64 atomics
 #pragma unroll
@@ -482,11 +597,15 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     p.nXT = (W + RG_TX - 1) / RG_TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
     p.wbytes = (int)ring_slab_bytes(Cin, cp);
+    {
+        const char* e = getenv("ATVS_RING_DEBUG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
     const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * 8 + 2 * RG_MAXG + 1) * 8 + 16;
     // two co-resident CTAs per SM when 2 x (weights + 4 planes) fit: their producer / MMA / epilogue
     // handshake latencies overlap
-    int minb = (fixed + 4 * slot <= 110 * 1024) ? 2 : 1;
+    int minb = (cp < 32 && fixed + 3 * slot <= 110 * 1024) ? 2 : 1;
     const size_t budget = (minb == 2 ? 110 : 220) * 1024;
     int nring = (int)((budget - fixed) / slot);
     if (nring > 8) nring = 8;
