@@ -22,6 +22,7 @@ _SIGS = {
     "atvs_conv3d_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_conv3d_bf16_bias": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "atvs_bn_relu_add": [_p, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
+    "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
     "atvs_add": [_p, _p, _p, _i, _ll, _p],
     "atvs_attention_combine": [_p, _p, _i, _ll, _i, _i, _p, _p],

@@ -135,16 +135,56 @@ struct Vec4<__nv_bfloat16> {
     static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+template <typename T>
+struct Vec8 {};
+template <>
+struct Vec8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float4& a, float4& b) {
+        a = *reinterpret_cast<const float4*>(p);
+        b = *(reinterpret_cast<const float4*>(p) + 1);
+    }
+    static __device__ __forceinline__ void st(float* p, float4 a, float4 b) {
+        *reinterpret_cast<float4*>(p) = a;
+        *(reinterpret_cast<float4*>(p) + 1) = b;
+    }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float4& a, float4& b) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
+        const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+        a = make_float4(f0.x, f0.y, f1.x, f1.y);
+        b = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 a, float4 b) {
+        __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x, a.y), q1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x, b.y), q3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 u;
+        u.x = *reinterpret_cast<unsigned*>(&q0); u.y = *reinterpret_cast<unsigned*>(&q1);
+        u.z = *reinterpret_cast<unsigned*>(&q2); u.w = *reinterpret_cast<unsigned*>(&q3);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+
 constexpr int BN_MAXC = 256;
 
+// out = relu((raw - mean) * rsqrt(var + eps))  [+ relu(bn(raw2))] [+ s1] [+ s2]
+//   batch statistics from the fp64 moment sums (network.py:206-212, training=True, no affine).
+//   raw2/stats2: a SECOND raw convolution output joined by the same `add` (network.py:696), so that
+//   a layer whose only consumer is that add never has its normalised tensor written and re-read.
+// 8 elements per thread and iteration when C is a multiple of 8: two 16-byte raw loads, one 16-byte
+// bf16 store.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, long long count, int C, float eps,
-              int relu, const T* __restrict__ s1, const T* __restrict__ s2, T* __restrict__ out_plain,
-              T* __restrict__ out_sum) {
-    __shared__ float sh_inv[BN_MAXC], sh_off[BN_MAXC];
+k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ raw2,
+              const double* __restrict__ stats2, long long count, int C, float eps, int relu,
+              const T* __restrict__ s1, const T* __restrict__ s2, T* __restrict__ out_plain, T* __restrict__ out_sum) {
+    __shared__ float sh_inv[BN_MAXC], sh_off[BN_MAXC], sh_inv2[BN_MAXC], sh_off2[BN_MAXC];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float inv = 1.f, off = 0.f;
+        float inv = 1.f, off = 0.f, inv2 = 1.f, off2 = 0.f;
         if (stats) {
             const double mean = stats[c] / (double)count;
             double var = stats[C + c] / (double)count - mean * mean;
@@ -152,29 +192,58 @@ k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, l
             inv = (float)(1.0 / sqrt(var + (double)eps));
             off = (float)mean * inv;
         }
-        sh_inv[c] = inv;
-        sh_off[c] = off;
+        if (stats2) {
+            const double mean = stats2[c] / (double)count;
+            double var = stats2[C + c] / (double)count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            inv2 = (float)(1.0 / sqrt(var + (double)eps));
+            off2 = (float)mean * inv2;
+        }
+        sh_inv[c] = inv; sh_off[c] = off; sh_inv2[c] = inv2; sh_off2[c] = off2;
     }
     __syncthreads();
     const long long n = count * C;
-    if ((C & 3) == 0) {
+    auto norm4 = [&](float4 r, const float* inv, const float* off, int c) {
+        float4 y;
+        y.x = r.x * inv[c] - off[c];
+        y.y = r.y * inv[c + 1] - off[c + 1];
+        y.z = r.z * inv[c + 2] - off[c + 2];
+        y.w = r.w * inv[c + 3] - off[c + 3];
+        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        return y;
+    };
+    auto add4 = [](float4& y, float4 a) { y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w; };
+    if ((C & 7) == 0) {
+        const long long n8 = n >> 3;
+        const bool pow2 = (C & (C - 1)) == 0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+             i += (long long)gridDim.x * blockDim.x) {
+            const long long e = i << 3;
+            const int c = pow2 ? (int)(e & (C - 1)) : (int)(e % C);
+            float4 ya = norm4(__ldcs(reinterpret_cast<const float4*>(raw + e)), sh_inv, sh_off, c);
+            float4 yb = norm4(__ldcs(reinterpret_cast<const float4*>(raw + e) + 1), sh_inv, sh_off, c + 4);
+            if (out_plain) Vec8<T>::st(out_plain + e, ya, yb);
+            if (out_sum) {
+                if (raw2) {
+                    add4(ya, norm4(__ldcs(reinterpret_cast<const float4*>(raw2 + e)), sh_inv2, sh_off2, c));
+                    add4(yb, norm4(__ldcs(reinterpret_cast<const float4*>(raw2 + e) + 1), sh_inv2, sh_off2, c + 4));
+                }
+                if (s1) { float4 a, b; Vec8<T>::ld(s1 + e, a, b); add4(ya, a); add4(yb, b); }
+                if (s2) { float4 a, b; Vec8<T>::ld(s2 + e, a, b); add4(ya, a); add4(yb, b); }
+                Vec8<T>::st(out_sum + e, ya, yb);
+            }
+        }
+    } else if ((C & 3) == 0) {
         const long long n4 = n >> 2;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
              i += (long long)gridDim.x * blockDim.x) {
             const int c = (int)((i << 2) % C);
-            const float4 r = __ldcs(reinterpret_cast<const float4*>(raw) + i);
-            float4 y;
-            y.x = r.x * sh_inv[c] - sh_off[c];
-            y.y = r.y * sh_inv[c + 1] - sh_off[c + 1];
-            y.z = r.z * sh_inv[c + 2] - sh_off[c + 2];
-            y.w = r.w * sh_inv[c + 3] - sh_off[c + 3];
-            if (relu) {
-                y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-            }
+            float4 y = norm4(__ldcs(reinterpret_cast<const float4*>(raw) + i), sh_inv, sh_off, c);
             if (out_plain) Vec4<T>::st(out_plain + (i << 2), y);
             if (out_sum) {
-                if (s1) { const float4 a = Vec4<T>::ld(s1 + (i << 2)); y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w; }
-                if (s2) { const float4 a = Vec4<T>::ld(s2 + (i << 2)); y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w; }
+                if (raw2) add4(y, norm4(__ldcs(reinterpret_cast<const float4*>(raw2) + i), sh_inv2, sh_off2, c));
+                if (s1) add4(y, Vec4<T>::ld(s1 + (i << 2)));
+                if (s2) add4(y, Vec4<T>::ld(s2 + (i << 2)));
                 Vec4<T>::st(out_sum + (i << 2), y);
             }
         }
@@ -186,6 +255,11 @@ k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, l
             if (relu) y = fmaxf(y, 0.f);
             if (out_plain) Vec4<T>::st1(out_plain + i, y);
             if (out_sum) {
+                if (raw2) {
+                    float y2 = raw2[i] * sh_inv2[c] - sh_off2[c];
+                    if (relu) y2 = fmaxf(y2, 0.f);
+                    y += y2;
+                }
                 if (s1) y += Vec4<T>::ld1(s1 + i);
                 if (s2) y += Vec4<T>::ld1(s2 + i);
                 Vec4<T>::st1(out_sum + i, y);
@@ -328,26 +402,43 @@ extern "C" int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int 
     return 0;
 }
 
-extern "C" int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps, int relu,
-                                const void* skip1, const void* skip2, void* out_plain, void* out_sum, int act_dtype,
-                                atvs_stream_t stream) {
-    ATVS_CHECK_ARG(raw && (out_plain || out_sum), ATVS_E_NULL, "atvs_bn_relu_add: NULL pointer");
-    ATVS_CHECK_ARG(count > 0 && C > 0 && C <= BN_MAXC, ATVS_E_SHAPE, "atvs_bn_relu_add: count=%lld C=%d", count, C);
-    cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = grid_for(count * C / 4 + 1, 256, 8);
+static int bn_relu_add_impl(const float* raw, const double* stats, const float* raw2, const double* stats2, long long count,
+                            int C, float eps, int relu, const void* skip1, const void* skip2, void* out_plain,
+                            void* out_sum, int act_dtype, cudaStream_t st, const char* who) {
+    ATVS_CHECK_ARG(raw && (out_plain || out_sum), ATVS_E_NULL, "%s: NULL pointer", who);
+    ATVS_CHECK_ARG(count > 0 && C > 0 && C <= BN_MAXC, ATVS_E_SHAPE, "%s: count=%lld C=%d", who, count, C);
+    ATVS_CHECK_ARG((C & 3) != 0 || (((uintptr_t)raw | (uintptr_t)raw2 | (uintptr_t)skip1 | (uintptr_t)skip2 |
+                                      (uintptr_t)out_plain | (uintptr_t)out_sum) & 15) == 0,
+                   ATVS_E_SHAPE, "%s: buffers must be 16-byte aligned", who);
+    const unsigned grid = grid_for(count * C / 8 + 1, 256, 8);
     if (act_dtype == ATVS_F32)
-        k_bn_relu_add<float><<<grid, 256, 0, st>>>(raw, stats, count, C, eps, relu, (const float*)skip1,
+        k_bn_relu_add<float><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu, (const float*)skip1,
                                                    (const float*)skip2, (float*)out_plain, (float*)out_sum);
     else if (act_dtype == ATVS_BF16)
-        k_bn_relu_add<__nv_bfloat16><<<grid, 256, 0, st>>>(raw, stats, count, C, eps, relu,
+        k_bn_relu_add<__nv_bfloat16><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu,
                                                            (const __nv_bfloat16*)skip1, (const __nv_bfloat16*)skip2,
                                                            (__nv_bfloat16*)out_plain, (__nv_bfloat16*)out_sum);
     else {
-        atvs_set_error("atvs_bn_relu_add: act_dtype %d", act_dtype);
+        atvs_set_error("%s: act_dtype %d", who, act_dtype);
         return ATVS_E_DTYPE;
     }
     ATVS_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps, int relu,
+                                const void* skip1, const void* skip2, void* out_plain, void* out_sum, int act_dtype,
+                                atvs_stream_t stream) {
+    return bn_relu_add_impl(raw, stats, nullptr, nullptr, count, C, eps, relu, skip1, skip2, out_plain, out_sum, act_dtype,
+                            (cudaStream_t)stream, "atvs_bn_relu_add");
+}
+
+extern "C" int atvs_bn_relu_add_pair(const float* raw_a, const double* stats_a, const float* raw_b, const double* stats_b,
+                                     long long count, int C, float eps, int relu, const void* skip, void* out_plain_a,
+                                     void* out_sum, int act_dtype, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(raw_b && out_sum, ATVS_E_NULL, "atvs_bn_relu_add_pair: NULL pointer");
+    return bn_relu_add_impl(raw_a, stats_a, raw_b, stats_b, count, C, eps, relu, skip, nullptr, out_plain_a, out_sum,
+                            act_dtype, (cudaStream_t)stream, "atvs_bn_relu_add_pair");
 }
 
 extern "C" int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, atvs_stream_t stream) {

@@ -146,6 +146,25 @@ def bn_relu_add(raw, stats, relu, skips, want_plain, want_sum, dtype):
     return plain, summ
 
 
+class _PendingRaw(object):
+    """raw convolution output + moments of a conv_bn layer whose only consumer is an `add` led by a
+    later layer: normalised inside that layer's fused pass (atvs_bn_relu_add_pair)."""
+    __slots__ = ('raw', 'stats', 'relu')
+
+    def __init__(self, raw, stats, relu):
+        self.raw, self.stats, self.relu = raw, stats, relu
+
+
+def bn_relu_add_pair(raw_a, stats_a, pend, relu, skip, want_plain, dtype):
+    count = raw_a.numel() // raw_a.shape[-1]
+    plain = torch.empty(raw_a.shape, dtype=dtype, device=raw_a.device) if want_plain else None
+    summ = torch.empty(raw_a.shape, dtype=dtype, device=raw_a.device)
+    L.call("atvs_bn_relu_add_pair", L.ptr(raw_a), L.ptr(stats_a), L.ptr(pend.raw), L.ptr(pend.stats), count,
+           raw_a.shape[-1], BN_EPS, int(relu), L.ptr(skip), L.ptr(plain), L.ptr(summ),
+           L.F32 if dtype == torch.float32 else L.BF16, L.stream())
+    return plain, summ
+
+
 class _Node(object):
     __slots__ = ('name', 'kind', 'inputs', 'params', 'value')
 
@@ -274,6 +293,10 @@ class Network(object):
             v = nodes[name].value
             if isinstance(v, SplitCostVolume):
                 return v
+            if isinstance(v, _PendingRaw):     # deferred normalisation that no fused add picked up
+                v, _ = bn_relu_add(v.raw, v.stats, v.relu, [], True, False, dt)
+                nodes[name].value = v
+                return v
             if nodes[name].kind == 'input':
                 v = to_act(v)
                 nodes[name].value = v      # cast once
@@ -293,6 +316,19 @@ class Network(object):
                 else:
                     raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
                                             node.params['stride'], transposed, True, arena[arena_slot[name]])
+                # a layer that only feeds an `add` led by a LATER conv layer is normalised inside that
+                # layer's fused pass: keep its raw output and moments until then
+                cons = consumers[name]
+                if (len(cons) == 1 and name not in self._wanted and nodes[cons[0]].kind == 'add'
+                        and nodes[cons[0]].inputs[0] != name and len(nodes[cons[0]].inputs) <= 3
+                        and nodes[nodes[cons[0]].inputs[0]].kind in ('conv_bn', 'deconv_bn')
+                        and pos[nodes[cons[0]].inputs[0]] > pos[name]
+                        and not any(isinstance(nodes[i].value, _PendingRaw) for i in nodes[cons[0]].inputs)
+                        and nodes[nodes[cons[0]].inputs[0]].params['relu'] == node.params['relu']):
+                    node.value = _PendingRaw(raw, stats, node.params['relu'])
+                    done.add(name)
+                    release(node.inputs)
+                    continue
                 # fuse a following add(name, older...) into the normalisation pass
                 fused = None
                 for c in consumers[name]:
@@ -304,7 +340,13 @@ class Network(object):
                 others = [c for c in consumers[name] if fused is None or c != fused.name]
                 want_plain = bool(others) or name in self._wanted or fused is None
                 skips = [nodes[i].value for i in fused.inputs[1:]] if fused is not None else []
-                plain, summ = bn_relu_add(raw, stats, node.params['relu'], skips, want_plain, fused is not None, dt)
+                pend = [v for v in skips if isinstance(v, _PendingRaw)]
+                if pend:
+                    rest = [v for v in skips if not isinstance(v, _PendingRaw)]
+                    plain, summ = bn_relu_add_pair(raw, stats, pend[0], node.params['relu'], rest[0] if rest else None,
+                                                   want_plain, dt)
+                else:
+                    plain, summ = bn_relu_add(raw, stats, node.params['relu'], skips, want_plain, fused is not None, dt)
                 node.value = plain
                 done.add(name)
                 release(node.inputs)

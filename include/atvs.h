@@ -112,6 +112,15 @@ int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int
                      int relu, const void* skip1, const void* skip2, void* out_plain,
                      void* out_sum, int act_dtype, atvs_stream_t stream);
 
+/* `add` of TWO freshly convolved layers (network.py:696 over two conv_bn / deconv_bn outputs, e.g.
+ * conv_b1_0_0 = add(conv_b0_6_0, conv_b0_0_1), cnn_wrapper/atvsnet.py:128-131):
+ * out_sum = relu(bn(raw_a)) + relu(bn(raw_b)) + skip, each raw tensor with its own batch statistics;
+ * out_plain_a = relu(bn(raw_a)) (may be NULL).  Saves writing and re-reading the normalised raw_b.  */
+int atvs_bn_relu_add_pair(const float* raw_a, const double* stats_a, const float* raw_b,
+                          const double* stats_b, long long count, int C, float eps, int relu,
+                          const void* skip, void* out_plain_a, void* out_sum, int act_dtype,
+                          atvs_stream_t stream);
+
 /* ---- elementwise helpers (dtype plumbing for NDHWC volumes) */
 int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n,
               atvs_stream_t stream);

@@ -269,6 +269,29 @@ def test_conv3d_split_cost_volume(A, stride, shape):
     assert rel_err(npy(raw), npy(raw2)) < 1e-5
 
 
+def test_bn_relu_add_pair(A):
+    """add of two freshly convolved layers, each with its own batch statistics, in one pass."""
+    from oracle import network as onet
+    from atvsnet_b200.network import bn_relu_add_pair, _PendingRaw
+    rng = np.random.default_rng(5)
+    for C, shape in ((8, (1, 4, 6, 10)), (16, (1, 3, 5, 7)), (12, (1, 2, 3, 5))):
+        ra = (rng.standard_normal(shape + (C,)) * 2 + 0.5).astype(np.float32)
+        rb = (rng.standard_normal(shape + (C,)) * 0.7 - 1).astype(np.float32)
+        sk = rng.standard_normal(ra.shape).astype(np.float32)
+
+        def moments(r):
+            f = r.reshape(-1, C).astype(np.float64)
+            return torch.from_numpy(np.concatenate([f.sum(0), (f ** 2).sum(0)])).cuda()
+        ref_a, ref_b = onet.relu(onet.batch_norm_train(ra)), onet.relu(onet.batch_norm_train(rb))
+        plain, summ = bn_relu_add_pair(cu(ra), moments(ra), _PendingRaw(cu(rb), moments(rb), True), True, cu(sk), True,
+                                       torch.float32)
+        assert rel_err(npy(plain), ref_a) < 1e-5
+        assert rel_err(npy(summ), ref_a + ref_b + sk) < 1e-5
+        _, sb = bn_relu_add_pair(cu(ra), moments(ra), _PendingRaw(cu(rb), moments(rb), True), True, None, False,
+                                 torch.bfloat16)
+        assert rel_err(npy(sb), ref_a + ref_b) < 1e-2
+
+
 def test_conv3d_argument_errors(A):
     from atvsnet_b200.network import conv3d_raw
     x = torch.zeros(1, 3, 4, 4, 16, dtype=torch.bfloat16, device='cuda')
