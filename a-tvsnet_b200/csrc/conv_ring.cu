@@ -606,9 +606,11 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     // two co-resident CTAs per SM when 2 x (weights + 4 planes) fit: their producer / MMA / epilogue
     // handshake latencies overlap
     int minb = (cp < 32 && fixed + 3 * slot <= 110 * 1024) ? 2 : 1;
+    if (const char* e = getenv("ATVS_RING_MINB")) minb = atoi(e) == 1 ? 1 : minb;
     const size_t budget = (minb == 2 ? 110 : 220) * 1024;
     int nring = (int)((budget - fixed) / slot);
     if (nring > 8) nring = 8;
+    if (const char* e = getenv("ATVS_RING_R")) nring = atoi(e) < nring ? atoi(e) : nring;
     if (nring < 2) {
         atvs_set_error("atvs_conv3d_bf16(ring): weights do not fit next to 2 ring planes (Cin=%d Cout=%d)", Cin, Cout);
         return ATVS_E_UNSUP;

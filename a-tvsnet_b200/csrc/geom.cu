@@ -11,6 +11,7 @@
 // floor() cells and validity masks are bit-identical to the oracle; only the last blend may
 // differ by rounding of the products (it does not: same order, no FMA).
 #include "common.cuh"
+#include <cstdlib>
 
 #define MUL(a, b) __fmul_rn((a), (b))
 #define ADD(a, b) __fadd_rn((a), (b))
@@ -362,10 +363,14 @@ k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ vie
     constexpr int F = 4 * G;
     constexpr int NS = (G >= K1_DCHUNK) ? 1 : K1_DCHUNK / G;      // samples evaluated per lane
     const int hw = h * w;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = idx < hw * G;
-    const int g = idx % G, pix = live ? idx / G : hw - 1;
-    const int x = pix % w, y = pix / w;
+    // a block is a 2-D patch of 8 x (256/G/8) pixels: neighbouring rows share their bilinear corner
+    // rows in L1 instead of re-fetching them from L2
+    constexpr int PPB = 256 / G, PH = (PPB >= 8) ? PPB / 8 : 1, PW = PPB / PH;
+    const int ptx = (w + PW - 1) / PW;
+    const int pl = threadIdx.x / G, g = threadIdx.x % G;
+    const int x = (blockIdx.x % ptx) * PW + pl % PW, y = (blockIdx.x / ptx) * PH + pl / PW;
+    const bool live = x < w && y < h;
+    const int pix = live ? y * w + x : hw - 1;
     const int b = blockIdx.z;
     const float* viewb = view + (size_t)b * hw * F;
     constexpr int CO = (MODE == 0) ? 2 * F : F;
@@ -425,6 +430,120 @@ k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ vie
             wv.w = MUL(fabsf(SUB(wv.w, r.w)), m);
             store4(oj, wv);
         }
+    }
+}
+
+
+// K1 for bf16 cost volumes: the source feature map is first rounded to bf16 (one tiny pass; the
+// volume it feeds is bf16 anyway), so that a bilinear corner of 8 channels is ONE 16-byte load and a
+// pixel needs F/8 lanes: half the L1 wavefronts, shuffles and instructions per output byte of the
+// fp32-source kernel, and 16-byte streaming stores.  Same sample sharing scheme (lane g evaluates the
+// homography of planes g, g+G8, ... of the 8-plane chunk).
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+    // bf16 -> fp32 is a 16-bit shift: one SHL for the low half, one AND for the high half
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+    u.z = *reinterpret_cast<unsigned*>(&c); u.w = *reinterpret_cast<unsigned*>(&d);
+    return u;
+}
+
+template <int MODE, int G8>
+__global__ void __launch_bounds__(256)
+k_build_cost_volume_h(const float* __restrict__ ref, const __nv_bfloat16* __restrict__ view, const float* __restrict__ hv,
+                      int D, int h, int w, __nv_bfloat16* __restrict__ out) {
+    constexpr int F = 8 * G8;
+    constexpr int NS = (G8 >= K1_DCHUNK) ? 1 : K1_DCHUNK / G8;
+    const int hw = h * w;
+    // a block is a 2-D patch of 8 x (256/G8/8) pixels (vertical reuse of the corner rows in L1)
+    constexpr int PPB = 256 / G8, PH = (PPB >= 8) ? PPB / 8 : 1, PW = PPB / PH;
+    const int ptx = (w + PW - 1) / PW;
+    const int pl = threadIdx.x / G8, g = threadIdx.x % G8;
+    const int x = (blockIdx.x % ptx) * PW + pl % PW, y = (blockIdx.x / ptx) * PH + pl / PW;
+    const bool live = x < w && y < h;
+    const int pix = live ? y * w + x : hw - 1;
+    const int b = blockIdx.z;
+    const __nv_bfloat16* viewb = view + (size_t)b * hw * F;
+    constexpr int CO = (MODE == 0) ? 2 * F : F;
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = 0.f;
+    if (MODE != 1) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(ref + ((size_t)b * hw + pix) * F + g * 8));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(ref + ((size_t)b * hw + pix) * F + g * 8 + 4));
+        r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+    }
+    const int d0 = blockIdx.y * K1_DCHUNK;
+    // cell: y0*w + x0, or -1 when the sample is outside (weights 0 -> output exactly 0) / not finite
+    // (weights NaN -> output NaN, as the reference's arithmetic would give): the plane loop is branch-free
+    int cell[NS];
+    float wa[NS], wb[NS], wc[NS], wd[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int d = d0 + g + k * G8;
+        cell[k] = -1;
+        wa[k] = wb[k] = wc[k] = wd[k] = 0.f;
+        if (g + k * G8 < K1_DCHUNK && d < D) {
+            float u, v;
+            homography_uv(hv + ((size_t)b * D + d) * 9, x, y, u, v);
+            const Sample s = make_sample(u, v, h, w);
+            cell[k] = s.valid ? s.y0 * w + s.x0 : -1;
+            const float bad = s.finite ? 0.f : __int_as_float(0x7fc00000);
+            wa[k] = s.valid ? s.wa : bad; wb[k] = s.valid ? s.wb : bad;
+            wc[k] = s.valid ? s.wc : bad; wd[k] = s.valid ? s.wd : bad;
+        }
+    }
+    const __nv_bfloat16* vbase = viewb + g * 8;
+    const int rowpitch = w * F;
+    __nv_bfloat16* oj = out + (((size_t)b * D + d0) * hw + pix) * CO + g * 8;
+    const size_t ostride = (size_t)hw * CO;
+    const uint4 rpk = pack8(r);
+#pragma unroll
+    for (int j = 0; j < K1_DCHUNK; ++j, oj += ostride) {
+        const int k = (G8 >= K1_DCHUNK) ? 0 : j / G8;
+        const int src = j % G8;
+        const int c = __shfl_sync(0xffffffffu, cell[k], src, G8);
+        const float a0 = __shfl_sync(0xffffffffu, wa[k], src, G8), a1 = __shfl_sync(0xffffffffu, wb[k], src, G8);
+        const float a2 = __shfl_sync(0xffffffffu, wc[k], src, G8), a3 = __shfl_sync(0xffffffffu, wd[k], src, G8);
+        if (d0 + j >= D) break;
+        const __nv_bfloat16* p = vbase + (ptrdiff_t)max(c, 0) * F;
+        float A[8], Bq[8], C[8], Dq[8], wv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p)), A);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p + F)), Bq);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p + rowpitch)), C);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p + rowpitch + F)), Dq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = fmaf(a3, Dq[i], fmaf(a2, C[i], fmaf(a1, Bq[i], a0 * A[i])));
+        if (!live) continue;
+        if (MODE == 0) {
+            __stcs(reinterpret_cast<uint4*>(oj), rpk);
+            __stcs(reinterpret_cast<uint4*>(oj + F), pack8(wv));
+        } else if (MODE == 1) {
+            __stcs(reinterpret_cast<uint4*>(oj), pack8(wv));
+        } else {
+            const float m = (c >= 0) ? 1.0f : 0.0f;   // model.py:277-278
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[i] = fabsf(wv[i] - r[i]) * m;
+            __stcs(reinterpret_cast<uint4*>(oj), pack8(wv));
+        }
+    }
+}
+
+__global__ void k_f32_to_bf16(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&lo);
+        pk.y = *reinterpret_cast<unsigned*>(&hi);
+        reinterpret_cast<uint2*>(d)[i] = pk;
     }
 }
 
@@ -497,70 +616,103 @@ k_prob2depth(const float* __restrict__ vol, int B, int D, int H, int W, const fl
 }
 
 
-// K4 at the volume's own resolution: 32 pixels x 8 depth slices per block (warp = slice, lanes =
-// consecutive pixels -> 128-byte coalesced plane reads).  Every slice runs an online softmax over
-// its planes d = slice, slice+8, ...; the 8 partial (max, sum, weighted sum) triples are merged
-// through shared memory.  20480 pixels would otherwise be 80 blocks of serial 128-plane loops.
+// K4 at the volume's own resolution: a block is 8 depth slices (warps) x 32 lanes, a lane owns VEC
+// consecutive pixels (VEC = 4: 16-byte plane reads).  Every slice runs an online softmax over its planes
+// d = slice, slice+8, ... in batches of 4 planes (4 independent loads in flight, ONE rescale of the
+// running sums per batch); the 8 partial (max, sum, weighted sum) triples are merged through shared memory.
 constexpr int K4_SLICES = 8;
+constexpr float K4_LOG2E = 1.4426950408889634f;
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_prob2depth_sliced(const float* __restrict__ vol, int B, int D, long long plane, const float* __restrict__ dstart,
                     const float* __restrict__ dint, float* __restrict__ depth, float* __restrict__ prob) {
-    __shared__ float sm_m[K4_SLICES][32], sm_s[K4_SLICES][32], sm_w[K4_SLICES][32];
+    __shared__ float sm_m[K4_SLICES][32 * VEC], sm_s[K4_SLICES][32 * VEC], sm_w[K4_SLICES][32 * VEC];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const long long total = (long long)B * plane;
-    const long long idx = (long long)blockIdx.x * 32 + lane;
+    const long long total = (long long)B * plane;                 // VEC == 4 requires plane % 4 == 0
+    const long long idx = ((long long)blockIdx.x * 32 + lane) * VEC;
     const bool live = idx < total;
-    const long long pidx = live ? idx : total - 1;
+    const long long pidx = live ? idx : total - VEC;
     const int b = (int)(pidx / plane);
     const float* vb = vol + (size_t)b * D * plane + (size_t)(pidx - (long long)b * plane);
     const float ds = dstart[b], di = dint[b];
     const float de = ADD(ds, MUL(SUB((float)D, 1.0f), di));
     const float step = DIV(SUB(de, ds), (float)max(D - 1, 1));
-    float m = -INFINITY, s = 0.f, ws = 0.f;
-#pragma unroll 4
-    for (int d = slice; d < D; d += K4_SLICES) {
-        const float t = -__ldg(vb + (size_t)d * plane);
-        if (t > m) {
-            const float sc = expf(m - t);
-            s *= sc;
-            ws *= sc;
-            m = t;
+    float m[VEC], s[VEC], ws[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { m[v] = -INFINITY; s[v] = 0.f; ws[v] = 0.f; }
+    for (int d = slice; d < D; d += 4 * K4_SLICES) {
+        float t[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int dq = d + q * K4_SLICES;
+            if (dq < D) {
+                if (VEC == 4) {
+                    const float4 r = __ldcs(reinterpret_cast<const float4*>(vb + (size_t)dq * plane));
+                    t[q][0] = -r.x; t[q][1 % VEC] = -r.y; t[q][2 % VEC] = -r.z; t[q][3 % VEC] = -r.w;
+                } else {
+                    t[q][0] = -__ldcs(vb + (size_t)dq * plane);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t[q][v] = -INFINITY;
+            }
         }
-        const float e = expf(t - m);
-        s += e;
-        ws += ADD(ds, MUL((float)d, step)) * e;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float mn = fmaxf(fmaxf(fmaxf(t[0][v], t[1][v]), fmaxf(t[2][v], t[3][v])), m[v]);
+            const float sc = exp2f((m[v] - mn) * K4_LOG2E);        // m = -inf at the start: exp2(-inf) = 0
+            float sa = s[v] * sc, wa = ws[v] * sc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float e = exp2f((t[q][v] - mn) * K4_LOG2E);  // padded planes: exp2(-inf) = 0
+                sa += e;
+                wa = fmaf(ADD(ds, MUL((float)(d + q * K4_SLICES), step)), e, wa);
+            }
+            m[v] = mn; s[v] = sa; ws[v] = wa;
+        }
     }
-    sm_m[slice][lane] = m;
-    sm_s[slice][lane] = s;
-    sm_w[slice][lane] = ws;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        sm_m[slice][lane * VEC + v] = m[v];
+        sm_s[slice][lane * VEC + v] = s[v];
+        sm_w[slice][lane * VEC + v] = ws[v];
+    }
     __syncthreads();
-    if (slice != 0 || !live) return;
+    // 32*VEC pixels of the block are finalised by the first 32*VEC threads
+    const int pl = threadIdx.x;
+    if (pl >= 32 * VEC) return;
+    const long long oidx = (long long)blockIdx.x * 32 * VEC + pl;
+    if (oidx >= total) return;
     float M = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < K4_SLICES; ++k) M = fmaxf(M, sm_m[k][lane]);
+    for (int k = 0; k < K4_SLICES; ++k) M = fmaxf(M, sm_m[k][pl]);
     float S = 0.f, WS = 0.f;
 #pragma unroll
     for (int k = 0; k < K4_SLICES; ++k) {
-        const float mk = sm_m[k][lane];
+        const float mk = sm_m[k][pl];
         if (mk == -INFINITY) continue;                     // slice without planes (D < 8)
-        const float sc = expf(mk - M);
-        S = fmaf(sm_s[k][lane], sc, S);
-        WS = fmaf(sm_w[k][lane], sc, WS);
+        const float sc = exp2f((mk - M) * K4_LOG2E);
+        S = fmaf(sm_s[k][pl], sc, S);
+        WS = fmaf(sm_w[k][pl], sc, WS);
     }
     const float est = WS / S;
-    depth[idx] = est;
+    depth[oidx] = est;
     if (prob) {
-        const float t = DIV(SUB(est, ds), di);
+        const int ob = (int)(oidx / plane);
+        const float* vo = vol + (size_t)ob * D * plane + (size_t)(oidx - (long long)ob * plane);
+        const float dso = dstart[ob], dio = dint[ob];
+        const float t = DIV(SUB(est, dso), dio);
         const int l0 = min(max((int)floorf(t), 0), D - 1);
         const int l1 = min(max(l0 - 1, 0), D - 1);
         const int r0 = min(max((int)ceilf(t), 0), D - 1);
         const int r1 = min(max(r0 + 1, 0), D - 1);
         const float inv = 1.0f / S;
-        float pr = expf(-__ldg(vb + (size_t)l0 * plane) - M) * inv;
-        pr += expf(-__ldg(vb + (size_t)l1 * plane) - M) * inv;
-        pr += expf(-__ldg(vb + (size_t)r0 * plane) - M) * inv;
-        pr += expf(-__ldg(vb + (size_t)r1 * plane) - M) * inv;
-        prob[idx] = pr;
+        float pr = expf(-__ldg(vo + (size_t)l0 * plane) - M) * inv;
+        pr += expf(-__ldg(vo + (size_t)l1 * plane) - M) * inv;
+        pr += expf(-__ldg(vo + (size_t)r0 * plane) - M) * inv;
+        pr += expf(-__ldg(vo + (size_t)r1 * plane) - M) * inv;
+        prob[oidx] = pr;
     }
 }
 
@@ -639,6 +791,8 @@ static int launch_k1(const float* ref, const float* view, const float* hv, const
     const int G = F / 4;
     dim3 grid((unsigned)(((long long)h * w * G + 255) / 256), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
     if (!hr && (G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32)) {
+        const int ppb = 256 / G, ph = ppb >= 8 ? ppb / 8 : 1, pw = ppb / ph;
+        grid.x = (unsigned)(((w + pw - 1) / pw) * ((h + ph - 1) / ph));
         switch (G) {
             case 1: launch_k1_shared<OutT, 1>(ref, view, hv, D, h, w, mode, out, grid, st); break;
             case 2: launch_k1_shared<OutT, 2>(ref, view, hv, D, h, w, mode, out, grid, st); break;
@@ -681,6 +835,30 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
     if (out_dtype == ATVS_F32)
         return launch_k1<float>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
                                 (float*)out, st);
+    if (out_dtype == ATVS_BF16 && !ref_homographies && F % 8 == 0 && (F == 8 || F == 16 || F == 32 || F == 64 || F == 128) &&
+        getenv("ATVS_K1_F32SRC") == nullptr) {
+        // bf16 volume: gather from a bf16 copy of the source feature map (stream-ordered scratch)
+        __nv_bfloat16* vb = nullptr;
+        const long long n = (long long)B * h * w * F;
+        ATVS_CUDA(cudaMallocAsync(&vb, sizeof(__nv_bfloat16) * n, st));
+        k_f32_to_bf16<<<(unsigned)((n / 4 + 255) / 256 < 2048 ? (n / 4 + 255) / 256 : 2048), 256, 0, st>>>(view_feature, vb, n / 4);
+        ATVS_LAUNCH_CHECK();
+        const int G8 = F / 8;
+        const int ppb = 256 / G8, ph = ppb >= 8 ? ppb / 8 : 1, pw = ppb / ph;
+        dim3 grid((unsigned)(((w + pw - 1) / pw) * ((h + ph - 1) / ph)), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
+        __nv_bfloat16* o = (__nv_bfloat16*)out;
+#define K1H(M, G) k_build_cost_volume_h<M, G><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o)
+#define K1H_G(M) do { switch (G8) { case 1: K1H(M, 1); break; case 2: K1H(M, 2); break; case 4: K1H(M, 4); break; \
+                                     case 8: K1H(M, 8); break; default: K1H(M, 16); break; } } while (0)
+        if (mode == 0) K1H_G(0);
+        else if (mode == 1) K1H_G(1);
+        else K1H_G(2);
+#undef K1H_G
+#undef K1H
+        ATVS_LAUNCH_CHECK();
+        ATVS_CUDA(cudaFreeAsync(vb, st));
+        return 0;
+    }
     if (out_dtype == ATVS_BF16)
         return launch_k1<__nv_bfloat16>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
                                         (__nv_bfloat16*)out, st);
@@ -699,8 +877,15 @@ extern "C" int atvs_prob2depth(const float* prob_volume, int B, int D, int H, in
     const unsigned grid = (unsigned)((total + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (up == 1)
-        k_prob2depth_sliced<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(prob_volume, B, D, (long long)H * W, depth_start,
-                                                                         depth_interval, depth, prob_map);
+    {
+        const long long plane = (long long)H * W;
+        if (plane % 4 == 0 && total >= 262144 && (((uintptr_t)prob_volume) & 15) == 0)
+            k_prob2depth_sliced<4><<<(unsigned)((total + 127) / 128), 256, 0, st>>>(prob_volume, B, D, plane, depth_start,
+                                                                                  depth_interval, depth, prob_map);
+        else
+            k_prob2depth_sliced<1><<<(unsigned)((total + 31) / 32), 256, 0, st>>>(prob_volume, B, D, plane, depth_start,
+                                                                                depth_interval, depth, prob_map);
+    }
     else
         k_prob2depth<4><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
     ATVS_LAUNCH_CHECK();
