@@ -20,6 +20,7 @@ SOURCES = {
     "net_fp32.cu": [],
     "conv_tc.cu": [],
     "conv_ring.cu": [],
+    "conv_ring_s2.cu": [],
     "conv_deconv.cu": [],
 }
 

@@ -27,7 +27,7 @@
 //               'SAME' padding) and published to the async proxy with fence.proxy.async
 //   Cin = 8   : one K=16 step covers two taps of the plane (LBO = distance of the taps)
 //   warps 0-3 producers | warp 4 MMA issuer (converged, elected lane) | warps 5-8 epilogue
-#include "tc_ptx.cuh"
+#include "ring_common.cuh"
 #include "conv_ring.cuh"
 #include <cstring>
 #include <cstdlib>
@@ -101,64 +101,6 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
 __device__ __forceinline__ int unit_ibeg(const Unit& u) { return u.z0 == 0 ? 1 : 0; }
 __device__ __forceinline__ int unit_iend(const RingParams& p, const Unit& u) {
     return (u.z0 + u.zlen == p.D) ? u.zlen : u.zlen + 1;
-}
-
-// warp-converged wait: every lane polls, the vote makes the loop condition (and everything computed
-// after it) provably warp-uniform for the compiler
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        if (++spins > TC_SPIN_LIMIT) {
-            printf("atvs conv_ring: mbarrier timeout (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
-            __trap();
-        }
-    }
-}
-
-// MMA with the descriptors given as (lo, hi) halves: the hi halves are loop constants and the lo halves
-// change by one 32-bit add per instruction
-__device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t leader) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\t"
-        "setp.ne.b32 q, %6, 0;\n\t"
-        "setp.eq.b32 p, 0, 0;\n\t"
-        "mov.b64 ad, {%1, %2};\n\t"
-        "mov.b64 bd, {%3, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_mma_lohi1(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                             uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
-        "setp.eq.b32 p, 0, 0;\n\t"
-        "mov.b64 ad, {%1, %2};\n\t"
-        "mov.b64 bd, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_st8_zero(uint32_t taddr) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__host__ __device__ constexpr uint32_t ring_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // weight-image window (in rows of 8) and MMA N for a run of `len` output planes whose first plane meets
@@ -626,6 +568,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
             const long long cost = ((units + slots - 1) / slots) * (zs + 2);
             if (best < 0 || cost < best) { best = cost; bz = zs; }
         }
+        if (const char* e = getenv("ATVS_RING_ZS")) bz = atoi(e) > 0 && atoi(e) <= D ? atoi(e) : bz;
         p.ZS = bz;
         p.nZS = (D + bz - 1) / bz;
         p.nunits = cols * p.nZS;

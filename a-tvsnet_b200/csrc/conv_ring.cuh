@@ -19,3 +19,11 @@ int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t s
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed);
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
               double* stats, const float* bias, cudaStream_t st);
+
+// stride-2 variant (conv_ring_s2.cu)
+bool ring_s2_supported(int Cin, int Cout);
+size_t ring_s2_weight_bytes(int Cin, int Cout);
+int ring_s2_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
+bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout);
+int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+                 double* stats, const float* bias, cudaStream_t st);

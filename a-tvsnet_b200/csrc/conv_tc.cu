@@ -324,7 +324,7 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
     const int ncls = transposed ? 8 : 1;
     for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
     size_t bytes = (elems * 2 + 255) & ~(size_t)255;          // per-tap TMA image
-    if (!transposed) bytes += ring_weight_bytes(Cin, Cout);    // halo-ring image (stride-1 convolutions)
+    if (!transposed) bytes += ring_weight_bytes(Cin, Cout) + ring_s2_weight_bytes(Cin, Cout);   // halo-ring images (stride 1 | 2)
     else if (deconv_fused_applicable(Cin, Cout)) bytes += deconv_fused_weight_bytes(Cin, Cout);   // 8-class deconv image
     return bytes;
 }
@@ -350,8 +350,13 @@ extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cou
     k_pack_weights<<<blocks, 128, 0, (cudaStream_t)stream>>>(kernel, Cin, Cout, transposed, sp.npad, sp.nslabs, ncls,
                                                             (__nv_bfloat16*)wpacked);
     ATVS_LAUNCH_CHECK();
-    if (!transposed)
-        return ring_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
+    if (!transposed) {
+        int rc = ring_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
+        if (rc == 0 && ring_s2_supported(Cin, Cout))
+            rc = ring_s2_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout),
+                              (cudaStream_t)stream);
+        return rc;
+    }
     if (deconv_fused_applicable(Cin, Cout))
         return deconv_fused_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 1), (cudaStream_t)stream);
     return 0;
@@ -399,6 +404,9 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
     if (transposed && deconv_fused_applicable(Cin, Cout))
         return deconv_fused(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 1), B, D, H, W, Cin, Cout, raw_out,
                             stats, st);
+    if (!transposed && stride == 2 && ring_s2_applicable(B, D, H, W, Cin, Cout))
+        return ring_s2_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout), B, D, H,
+                            W, Cin, Cout, raw_out, stats, plane_bias, st);
     if (ring_applicable(B, D, H, W, stride, transposed))
         return ring_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
                          stats, plane_bias, st);

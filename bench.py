@@ -257,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
         pk = peaks()
         ach = flops / (t_ms * 1e-3) / 1e12
         roof = {"bound": "tensor",
-                "kernel": "k_conv3d_ring<%d,16> (conv_b0_0_1, %d->8 stride 1 on %d voxels%s)"
+                "kernel": "k_conv3d_ring<%d,8,2> (conv_b0_0_1, %d->8 stride 1 on %d voxels%s)"
                           % (cin, cin, nvox, "; the 32 tiled-reference channels enter as an epilogue bias" if cin == 32 else ""),
                 "achieved": ach, "peak": pk['bf16_sustained'], "unit": "TFLOP/s", "frac": ach / pk['bf16_sustained'],
                 "traffic": None, "peak_source": pk['src'] + " (sustained bf16)", "ms_per_launch": t_ms,

