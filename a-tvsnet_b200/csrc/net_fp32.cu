@@ -350,6 +350,96 @@ k_attention(const T* __restrict__ act, const T* __restrict__ x, int N, long long
     }
 }
 
+
+// AAM on the RAW attention convolutions: act_raw (N,V,2C) fp32 is the un-activated output of the one
+// 8->16 convolution per view ([W_unique | W_shared], network.py:313-344); the ReLU is applied while
+// loading, so the activations are never written back and re-read, and one thread owns 8 channels of a
+// voxel (16/32-byte loads).  Same three modes as k_attention.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_attention_raw(const float* __restrict__ act, const T* __restrict__ x, int N, long long V, int C,
+                const float* __restrict__ gmax, float* __restrict__ out) {
+    const int G = C >> 3;
+    const long long total = V * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long v = idx / G;
+        const int c0 = (int)(idx % G) << 3;
+        float a[ATT_MAXN][8];
+        float S[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S[q] = 0.f;
+#pragma unroll
+        for (int n = 0; n < ATT_MAXN; ++n) {
+            if (n < N) {
+                const float* ar = act + ((size_t)n * V + v) * (2 * C);
+                float4 u0, u1, s0, s1;
+                Vec8<float>::ld(ar + c0, u0, u1);
+                Vec8<float>::ld(ar + C + c0, s0, s1);
+                const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float sq = fmaxf(ss[q], 0.f);
+                    a[n][q] = fmaxf(uu[q], 0.f) - sq;
+                    if (MODE == 0) S[q] = (n == 0) ? sq : S[q] + sq;
+                }
+            }
+        }
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float mm = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < ATT_MAXN; ++n)
+                if (n < N) {
+                    a[n][q] += S[q];
+                    mm = fmaxf(mm, a[n][q]);
+                }
+            m[q] = mm;
+        }
+        if (MODE == 1) {
+            Vec8<float>::st(out + v * C + c0, make_float4(m[0], m[1], m[2], m[3]), make_float4(m[4], m[5], m[6], m[7]));
+            continue;
+        }
+        if (MODE == 2) {
+            float4 g0, g1;
+            Vec8<float>::ld(gmax + v * C + c0, g0, g1);
+            m[0] = g0.x; m[1] = g0.y; m[2] = g0.z; m[3] = g0.w; m[4] = g1.x; m[5] = g1.y; m[6] = g1.z; m[7] = g1.w;
+        }
+        float den[8], res[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { den[q] = 0.f; res[q] = 0.f; }
+#pragma unroll
+        for (int n = 0; n < ATT_MAXN; ++n)
+            if (n < N) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    a[n][q] = expf(a[n][q] - m[q]);
+                    den[q] += a[n][q];
+                }
+            }
+#pragma unroll
+        for (int n = 0; n < ATT_MAXN; ++n)
+            if (n < N) {
+                float4 x0, x1;
+                Vec8<T>::ld(x + ((size_t)n * V + v) * C + c0, x0, x1);
+                const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) res[q] += (MODE == 0 ? a[n][q] / den[q] : a[n][q]) * xx[q];
+            }
+        if (MODE == 2) {
+            Vec8<float>::st(out + v * (2 * C) + c0, make_float4(res[0], res[1], res[2], res[3]),
+                            make_float4(res[4], res[5], res[6], res[7]));
+            Vec8<float>::st(out + v * (2 * C) + C + c0, make_float4(den[0], den[1], den[2], den[3]),
+                            make_float4(den[4], den[5], den[6], den[7]));
+        } else {
+            Vec8<float>::st(out + v * C + c0, make_float4(res[0], res[1], res[2], res[3]),
+                            make_float4(res[4], res[5], res[6], res[7]));
+        }
+    }
+}
+
 __global__ void k_attention_finish(const float* __restrict__ nd, long long V, int C, float* __restrict__ out) {
     const long long total = V * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -513,6 +603,30 @@ extern "C" int atvs_attention_partial(const void* act, const void* x, int N, lon
                                       const float* gmax, float* num_den, atvs_stream_t stream) {
     ATVS_CHECK_ARG(gmax, ATVS_E_NULL, "atvs_attention_partial: gmax is NULL");
     return launch_att<2>(act, x, N, V, C, dtype, gmax, num_den, (cudaStream_t)stream, "atvs_attention_partial");
+}
+
+extern "C" int atvs_attention_raw(const float* act_raw, const void* x, int N, long long V, int C, int x_dtype, int mode,
+                                  const float* gmax, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(act_raw && out && (mode == 1 || x) && (mode != 2 || gmax), ATVS_E_NULL, "atvs_attention_raw: NULL pointer");
+    ATVS_CHECK_ARG(N > 0 && N <= ATT_MAXN && V > 0 && C > 0 && C % 8 == 0, ATVS_E_SHAPE, "atvs_attention_raw: N=%d V=%lld C=%d",
+                   N, V, C);
+    ATVS_CHECK_ARG(mode >= 0 && mode <= 2, ATVS_E_UNSUP, "atvs_attention_raw: mode %d", mode);
+    ATVS_CHECK_ARG((((uintptr_t)act_raw | (uintptr_t)x | (uintptr_t)gmax | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_attention_raw: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = grid_for(V * (C / 8), 256, 8);
+#define ATT_RAW(T, M) k_attention_raw<T, M><<<grid, 256, 0, st>>>(act_raw, (const T*)x, N, V, C, gmax, out)
+    if (x_dtype == ATVS_F32 || mode == 1) {
+        if (mode == 0) ATT_RAW(float, 0); else if (mode == 1) ATT_RAW(float, 1); else ATT_RAW(float, 2);
+    } else if (x_dtype == ATVS_BF16) {
+        if (mode == 0) ATT_RAW(__nv_bfloat16, 0); else ATT_RAW(__nv_bfloat16, 2);
+    } else {
+        atvs_set_error("atvs_attention_raw: x_dtype %d", x_dtype);
+        return ATVS_E_DTYPE;
+    }
+#undef ATT_RAW
+    ATVS_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int atvs_attention_finish(const float* num_den, long long V, int C, float* out, atvs_stream_t stream) {

@@ -99,7 +99,7 @@ def conv3d_split(cv, wkey, w, cout, stride, stats_buf):
     return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias)
 
 
-def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None, bias=None):
+def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None, bias=None, out=None):
     """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)].
     ``stats_buf``: pre-zeroed fp64 buffer of >= 2*Cout elements to accumulate the moments into."""
     B, D, H, W, cin = x.shape
@@ -107,7 +107,7 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None,
         od, oh, ow = 2 * D, 2 * H, 2 * W
     else:
         od, oh, ow = -(-D // stride), -(-H // stride), -(-W // stride)
-    raw = torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
+    raw = out if out is not None else torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
     if not want_stats:
         stats = None
     elif stats_buf is not None:
@@ -393,25 +393,43 @@ def split_views(cost_volumes):
     return [to_act(cost_volumes[..., i]) for i in range(n)]
 
 
-def attention_activations(views, scope):
-    """network.py:282-351: per view the pair [relu(conv(x,W_unique)) | relu(conv(x,W_shared))]
-    as one 8->16 convolution.  Returns act (N,V,16) in the activation dtype."""
+def _attention_weights(scope):
     key = scope + '/attention_activation/weight_unique||weight_shared'
     cache = V.packed_cache()
     if key not in cache:
         wu = V.get_variable(scope + '/attention_activation/weight_unique')
         ws = V.get_variable(scope + '/attention_activation/weight_shared')
         cache[key] = torch.cat([wu, ws], dim=-1).contiguous()
-    w = cache[key]
+    return key, cache[key]
+
+
+def attention_activations_raw(views, scope):
+    """network.py:282-351: per view the pair [conv(x,W_unique) | conv(x,W_shared)] as one 8->16
+    convolution, NOT yet activated: raw fp32 (N,V,16).  The ReLU is applied by the combine kernel."""
+    key, w = _attention_weights(scope)
     c2 = w.shape[-1]
-    dt = views[0].dtype
+    B, D, H, W_, _ = views[0].shape
     nvox = views[0].numel() // views[0].shape[-1]
-    act = torch.empty((len(views), nvox, c2), dtype=dt, device=views[0].device)
+    raw = torch.empty((len(views), nvox, c2), dtype=torch.float32, device=views[0].device)
     for n, x in enumerate(views):
-        raw, _ = conv3d_raw(x, key + '/packed', w, c2, 1, False, False)
-        L.call("atvs_bn_relu_add", L.ptr(raw), None, nvox, c2, BN_EPS, 1, None, None, L.ptr(act[n]), None,
-               L.F32 if dt == torch.float32 else L.BF16, L.stream())
+        conv3d_raw(x, key + '/packed', w, c2, 1, False, False, out=raw[n].view(B, D, H, W_, c2))
+    return raw
+
+
+def attention_activations(views, scope):
+    """activated pairs [relu(conv(x,W_unique)) | relu(conv(x,W_shared))] (N,V,16) in the activation dtype."""
+    raw = attention_activations_raw(views, scope)
+    dt = views[0].dtype
+    act = torch.empty(raw.shape, dtype=dt, device=raw.device)
+    L.call("atvs_bn_relu_add", L.ptr(raw), None, raw.shape[0] * raw.shape[1], raw.shape[2], BN_EPS, 1, None, None,
+           L.ptr(act), None, L.F32 if dt == torch.float32 else L.BF16, L.stream())
     return act
+
+
+def stack_views(views):
+    c = views[0].shape[-1]
+    nvox = views[0].numel() // c
+    return torch.stack([v.reshape(nvox, c) for v in views], dim=0) if len(views) > 1 else views[0].reshape(1, nvox, c)
 
 
 def attention_aggregation(cost_volumes, scope):
@@ -420,9 +438,14 @@ def attention_aggregation(cost_volumes, scope):
     shape = views[0].shape
     c = shape[-1]
     nvox = views[0].numel() // c
-    act = attention_activations(views, scope)
-    x = torch.stack([v.reshape(nvox, c) for v in views], dim=0) if len(views) > 1 else views[0].reshape(1, nvox, c)
+    x = stack_views(views)
     out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_combine", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(out),
-           L.stream())
+    if c % 8 == 0:
+        raw = attention_activations_raw(views, scope)
+        L.call("atvs_attention_raw", L.ptr(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 0, None, L.ptr(out),
+               L.stream())
+    else:
+        act = attention_activations(views, scope)
+        L.call("atvs_attention_combine", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(out),
+               L.stream())
     return out.reshape(shape)

@@ -13,7 +13,7 @@ from .model import _prob2depth, build_cost_volume
 # bf16 path: run the first CRM layers on the warped half only (network.SplitCostVolume)
 SPLIT_COST_VOLUME = True
 # number of CUDA streams the independent stage-I passes are spread over
-CONCURRENT_PASSES = 4
+CONCURRENT_PASSES = int(__import__('os').environ.get('ATVS_PASSES', '4'))
 
 
 def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid):
@@ -70,14 +70,14 @@ def aggregate(filtered_views, scope='attention_aggregate', group=None):
     shape = views[0].shape
     c = shape[-1]
     nvox = views[0].numel() // c
-    act = N.attention_activations(views, scope)
-    x = torch.stack([v.reshape(nvox, c) for v in views], dim=0)
+    raw = N.attention_activations_raw(views, scope)
+    x = N.stack_views(views)
     lmax = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_local_max", L.ptr(act), len(views), nvox, c, L.dtype_code(act), L.ptr(lmax), L.stream())
+    L.call("atvs_attention_raw", L.ptr(raw), None, len(views), nvox, c, L.dtype_code(x), 1, None, L.ptr(lmax), L.stream())
     dist.all_reduce(lmax, op=dist.ReduceOp.MAX, group=group)
     nd = torch.empty((nvox, 2 * c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_partial", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(lmax),
-           L.ptr(nd), L.stream())
+    L.call("atvs_attention_raw", L.ptr(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
+           L.stream())
     dist.all_reduce(nd, op=dist.ReduceOp.SUM, group=group)
     out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
     L.call("atvs_attention_finish", L.ptr(nd), nvox, c, L.ptr(out), L.stream())
