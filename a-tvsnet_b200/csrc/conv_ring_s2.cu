@@ -425,7 +425,7 @@ bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout) {
     // +0.25 ms per depth map), so it is opt-in (ATVS_RING_S2_CIN=32)
     const char* e = getenv("ATVS_RING_S2_CIN");
     if (e ? atoi(e) != Cin : Cin > 16) return false;
-    return ring_s2_supported(Cin, Cout) && ((D | H | W) & 1) == 0 && (long long)(D / 2) * (H / 2) * (W / 2) >= 32768 &&
+    return ring_s2_supported(Cin, Cout) && ((D | H | W) & 1) == 0 && (long long)(D / 2) * (H / 2) * (W / 2) >= 131072 &&
            getenv("ATVS_NO_RING_S2") == nullptr;
 }
 

@@ -247,8 +247,8 @@ def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
-S2_RING_CASES = [(8, 16, (1, 16, 64, 80)), (32, 16, (1, 8, 128, 96)), (16, 32, (2, 10, 72, 56)), (8, 8, (1, 6, 130, 98)),
-                 (32, 64, (1, 4, 128, 160)), (16, 16, (1, 34, 66, 34))]
+S2_RING_CASES = [(8, 16, (1, 32, 128, 160)), (32, 16, (1, 16, 128, 192)), (16, 32, (2, 20, 144, 112)), (8, 8, (1, 12, 260, 196)),
+                 (32, 64, (1, 8, 256, 160)), (16, 16, (1, 68, 132, 68))]
 
 
 @pytest.mark.parametrize('cin,cout,shape', S2_RING_CASES)
