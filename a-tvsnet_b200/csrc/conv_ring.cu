@@ -525,7 +525,8 @@ int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t s
 }
 
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
-    return !transposed && stride == 1 && (long long)D * H * W >= 32768 && H >= 8 && W >= 8;
+    const long long minvox = getenv("ATVS_RING_MINVOX") ? atoll(getenv("ATVS_RING_MINVOX")) : 65536;
+    return !transposed && stride == 1 && (long long)D * H * W >= minvox && H >= 8 && W >= 8;
 }
 
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,

@@ -237,8 +237,12 @@ def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
     xb = torch.from_numpy(x).to(torch.bfloat16)
     wb = torch.from_numpy(w).to(torch.bfloat16).float()
     A.variables.packed_cache().clear()
-    raw, stats = conv3d_raw(xb.cuda(), 'ring_%d_%d' % (cin, cout), wb.cuda(), cout, 1, False, True)
-    torch.cuda.synchronize()
+    os.environ['ATVS_RING_MINVOX'] = '32768'       # the default dispatch threshold is 65536 voxels
+    try:
+        raw, stats = conv3d_raw(xb.cuda(), 'ring_%d_%d' % (cin, cout), wb.cuda(), cout, 1, False, True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ['ATVS_RING_MINVOX']
     ref = onet.conv3d(xb.float().numpy(), wb.numpy(), 1)
     assert rel_err(npy(raw), ref) < 1e-4
     s = stats.cpu().numpy()
