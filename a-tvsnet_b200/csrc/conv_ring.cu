@@ -56,12 +56,13 @@ constexpr int RG_KCH_PAD = RG_NVOX * 16 + 16;       // pitch of one 8-channel ch
 constexpr int RG_PRODUCERS = 128;
 constexpr int RG_THREADS = 288;
 constexpr int RG_MAXG = 15;
+constexpr int RG_MAXR = 16;      // ring slots (mbarrier pairs)
 
 struct RingParams {
     int B, D, H, W;
     int Cout, coff, ncols;
     int nXT, nYT, nZS, ZS;
-    int nring;
+    int nring, pf;      // ring slots, planes of cp.async in flight per producer thread (pf <= nring - 1, <= 8)
     int wbytes;
     int dbg;            // ATVS_RING_DEBUG bit mask (tools/conv_probe.py): 1 no loads, 2 no MMAs, 4 no stores, 8 no zeroing
     long long nunits;
@@ -188,12 +189,16 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
         constexpr int NITEM = (Cfg::NKC * RG_NVOX + RG_PRODUCERS - 1) / RG_PRODUCERS;
         // up to PF planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
         // mbarrier arrive) once plane q+PF-1 has been issued.  PF <= R-1 keeps the ring deadlock-free.
-        const int PF = (R >= 5) ? 4 : (R >= 3 ? 2 : 1);
+        const int PF = p.pf;
         uint32_t slot = 0, sphase = 0, pslot = 0, pending = 0;
         const uint32_t ring_u32 = smem_u32(ring);
         auto publish = [&](int keep) {
             // wait until at most `keep` groups are pending, then publish every older plane
-            if (keep >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+            if (keep >= 7) asm volatile("cp.async.wait_group 7;" ::: "memory");
+            else if (keep == 6) asm volatile("cp.async.wait_group 6;" ::: "memory");
+            else if (keep == 5) asm volatile("cp.async.wait_group 5;" ::: "memory");
+            else if (keep == 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+            else if (keep == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
             else if (keep == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
             else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -545,7 +550,7 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         p.dbg = e ? atoi(e) : 0;
     }
     const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
-    const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * 8 + 2 * RG_MAXG + 1) * 8 + 16;
+    const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * RG_MAXR + 2 * RG_MAXG + 1) * 8 + 16;
     // two co-resident CTAs per SM when 2 x (weights + 4 planes) fit: their producer / MMA / epilogue
     // handshake latencies overlap
     int minb = (cp < 32 && fixed + 3 * slot <= 110 * 1024) ? 2 : 1;
@@ -555,13 +560,22 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
     if (const char* e = getenv("ATVS_RING_MINB")) minb = atoi(e) == 1 ? 1 : minb;
     const size_t budget = (minb == 2 ? 110 : 220) * 1024;
     int nring = (int)((budget - fixed) / slot);
-    if (nring > 8) nring = 8;
-    if (const char* e = getenv("ATVS_RING_R")) nring = atoi(e) < nring ? atoi(e) : nring;
+    {
+        int cap = 8;
+        if (const char* e = getenv("ATVS_RING_R")) cap = atoi(e) < RG_MAXR ? (atoi(e) > 1 ? atoi(e) : 2) : RG_MAXR;
+        if (nring > cap) nring = cap;
+    }
     if (nring < 2) {
         atvs_set_error("atvs_conv3d_bf16(ring): weights do not fit next to 2 ring planes (Cin=%d Cout=%d)", Cin, Cout);
         return ATVS_E_UNSUP;
     }
     p.nring = nring;
+    p.pf = (nring >= 5) ? 4 : (nring >= 3 ? 2 : 1);
+    if (const char* e = getenv("ATVS_RING_PF")) {
+        const int v = atoi(e);
+        if (v >= 1) p.pf = v < nring - 1 ? (v < 8 ? v : 8) : (nring - 1 < 8 ? nring - 1 : 8);
+        if (p.pf < 1) p.pf = 1;
+    }
     {   // z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
         const long long slots = (long long)sms * minb;

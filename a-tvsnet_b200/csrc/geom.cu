@@ -12,6 +12,7 @@
 // differ by rounding of the products (it does not: same order, no FMA).
 #include "common.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 #define MUL(a, b) __fmul_rn((a), (b))
 #define ADD(a, b) __fadd_rn((a), (b))
@@ -716,6 +717,147 @@ k_prob2depth_sliced(const float* __restrict__ vol, int B, int D, long long plane
     }
 }
 
+// 2^x on the SFU (MUFU.EX2, ~2 ulp, denormal results flushed): the soft-argmin weights are >= 2^-126 or irrelevant
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// K4 fused with the x4 logit upsampling (model.py:68-76 + :80-109).  The kernel is instruction bound (D*16*h*w
+// interpolations + exponentials against 4*D*h*w bytes), so it is organised to minimise instructions per output:
+//   block  : 8 depth slices (warps) x 32 lanes, one output row Y; lane k owns the 4 output pixels X = 4k..4k+3
+//   texels : those 4 pixels read source columns {k-1, k, k+1} only (x0 = floor(X*(W-1)/(4W-1)) is k-1 or k), so a
+//            plane costs 6 loads per lane (3 columns x 2 rows) instead of 16; 4 planes = 24 loads in flight
+//   softmax: batched online softmax per output (ONE rescale per 4 planes), slices merged through shared memory
+// TF's lerp order (top = tl + (tr-tl)*fx, bot likewise, top + (bot-top)*fy) is kept, each "a + b*c" as one FMA.
+template <int UP>
+__global__ void __launch_bounds__(256)
+k_prob2depth_up_sliced(const float* __restrict__ vol, int B, int D, int H, int W, const float* __restrict__ dstart,
+                       const float* __restrict__ dint, float* __restrict__ depth, float* __restrict__ prob) {
+    static_assert(UP == 4, "column ownership is derived for x4");
+    __shared__ float sm_m[K4_SLICES][128], sm_s[K4_SLICES][128], sm_w[K4_SLICES][128];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int Ho = H * UP, Wo = W * UP;
+    const int xb = (W + 31) / 32;
+    const int bx = blockIdx.x % xb;
+    const int Y = (blockIdx.x / xb) % Ho, b = blockIdx.x / (xb * Ho);
+    const int k = min(bx * 32 + lane, W - 1);
+    const size_t plane = (size_t)H * W;
+    const float* vb = vol + (size_t)b * D * plane;
+    const float sy = DIV((float)(H - 1), (float)(Ho - 1)), sx = DIV((float)(W - 1), (float)(Wo - 1));
+    const float srcy = MUL((float)Y, sy);
+    const int y0 = (int)floorf(srcy);
+    const int y1 = min(y0 + 1, H - 1);
+    const float fy = SUB(srcy, (float)y0);
+    float fx[4];
+    bool hi[4];                       // x0 == k (else k-1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float srcx = MUL((float)(4 * k + j), sx);
+        const int x0 = (int)floorf(srcx);
+        fx[j] = SUB(srcx, (float)x0);
+        hi[j] = x0 >= k;
+    }
+    const int c0 = max(k - 1, 0), c2 = min(k + 1, W - 1);
+    const float* r0 = vb + (size_t)y0 * W + (size_t)slice * plane;
+    const float* r1 = vb + (size_t)y1 * W + (size_t)slice * plane;
+    const size_t bstep = (size_t)K4_SLICES * plane;
+    const float ds = dstart[b], di = dint[b];
+    const float de = ADD(ds, MUL(SUB((float)D, 1.0f), di));
+    const float step = DIV(SUB(de, ds), (float)max(D - 1, 1));
+    float m[4], s[4], ws[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = -INFINITY; s[j] = 0.f; ws[j] = 0.f; }
+    // one batch of 4 planes; FULL = all four planes exist (no per-plane predicates in the steady state)
+    auto batch = [&](int d, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        float a[4][2][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const size_t off = (FULL || d + q * K4_SLICES < D) ? (size_t)q * bstep : 0;
+            a[q][0][0] = __ldg(r0 + off + c0); a[q][0][1] = __ldg(r0 + off + k); a[q][0][2] = __ldg(r0 + off + c2);
+            a[q][1][0] = __ldg(r1 + off + c0); a[q][1][1] = __ldg(r1 + off + k); a[q][1][2] = __ldg(r1 + off + c2);
+        }
+        float dep[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dep[q] = ADD(ds, MUL((float)(d + q * K4_SLICES), step));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float tl = hi[j] ? a[q][0][1] : a[q][0][0], tr = hi[j] ? a[q][0][2] : a[q][0][1];
+                const float bl = hi[j] ? a[q][1][1] : a[q][1][0], br = hi[j] ? a[q][1][2] : a[q][1][1];
+                const float top = fmaf(tr - tl, fx[j], tl), bot = fmaf(br - bl, fx[j], bl);
+                const float v = fmaf(top - bot, fy, -top);                    // -(top + (bot - top) * fy)
+                t[q] = (FULL || d + q * K4_SLICES < D) ? v : -INFINITY;
+            }
+            const float mn = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), m[j]);
+            const float mnl = mn * K4_LOG2E;
+            const float sc = ex2_approx(fmaf(m[j], K4_LOG2E, -mnl));          // m = -inf at the start: 2^-inf = 0
+            float sa = s[j] * sc, wa = ws[j] * sc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float e = ex2_approx(fmaf(t[q], K4_LOG2E, -mnl));
+                sa += e;
+                wa = fmaf(dep[q], e, wa);
+            }
+            m[j] = mn; s[j] = sa; ws[j] = wa;
+        }
+    };
+    for (int d = slice; d < D; d += 4 * K4_SLICES, r0 += 4 * bstep, r1 += 4 * bstep) {
+        if (d + 3 * K4_SLICES < D) batch(d, std::true_type());
+        else batch(d, std::false_type());
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sm_m[slice][lane * 4 + j] = m[j]; sm_s[slice][lane * 4 + j] = s[j]; sm_w[slice][lane * 4 + j] = ws[j];
+    }
+    __syncthreads();
+    const int pl = threadIdx.x;
+    const int X = bx * 128 + pl;
+    if (pl >= 128 || X >= Wo) return;
+    float M = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < K4_SLICES; ++q) M = fmaxf(M, sm_m[q][pl]);
+    float S = 0.f, WS = 0.f;
+#pragma unroll
+    for (int q = 0; q < K4_SLICES; ++q) {
+        const float mk = sm_m[q][pl];
+        if (mk == -INFINITY) continue;                     // slice without planes (D < 8)
+        const float sc = exp2f((mk - M) * K4_LOG2E);
+        S = fmaf(sm_s[q][pl], sc, S);
+        WS = fmaf(sm_w[q][pl], sc, WS);
+    }
+    const float est = WS / S;
+    const size_t oidx = ((size_t)b * Ho + Y) * Wo + X;
+    depth[oidx] = est;
+    if (prob) {
+        const float srcx = MUL((float)X, sx);
+        const int x0 = (int)floorf(srcx), x1 = min(x0 + 1, W - 1);
+        const float gx = SUB(srcx, (float)x0);
+        const float t = DIV(SUB(est, ds), di);
+        const int l0 = min(max((int)floorf(t), 0), D - 1);
+        const int l1 = min(max(l0 - 1, 0), D - 1);
+        const int q0 = min(max((int)ceilf(t), 0), D - 1);
+        const int q1 = min(max(q0 + 1, 0), D - 1);
+        const float inv = 1.0f / S;
+        auto logit = [&](int d) -> float {
+            const float* p0 = vb + (size_t)d * plane + (size_t)y0 * W;
+            const float* p1 = vb + (size_t)d * plane + (size_t)y1 * W;
+            const float tl = __ldg(p0 + x0), tr = __ldg(p0 + x1), bl = __ldg(p1 + x0), br = __ldg(p1 + x1);
+            const float top = fmaf(tr - tl, gx, tl), bot = fmaf(br - bl, gx, bl);
+            return fmaf(bot - top, fy, top);
+        };
+        float pr = expf(-logit(l0) - M) * inv;
+        pr += expf(-logit(l1) - M) * inv;
+        pr += expf(-logit(q0) - M) * inv;
+        pr += expf(-logit(q1) - M) * inv;
+        prob[oidx] = pr;
+    }
+}
+
 }  // namespace
 
 // =========================================================================== C ABI
@@ -887,7 +1029,15 @@ extern "C" int atvs_prob2depth(const float* prob_volume, int B, int D, int H, in
                                                                                 depth_interval, depth, prob_map);
     }
     else
-        k_prob2depth<4><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
+    {
+        const int Ho = H * 4;
+        const long long blocks = (long long)B * Ho * ((W + 31) / 32);
+        if (blocks <= 0x7fffffffLL && getenv("ATVS_K4_SIMPLE") == nullptr)
+            k_prob2depth_up_sliced<4><<<(unsigned)blocks, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval,
+                                                                       depth, prob_map);
+        else
+            k_prob2depth<4><<<grid, 256, 0, st>>>(prob_volume, B, D, H, W, depth_start, depth_interval, depth, prob_map);
+    }
     ATVS_LAUNCH_CHECK();
     return 0;
 }

@@ -263,6 +263,13 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": None, "peak_source": pk['src'] + " (sustained bf16)", "ms_per_launch": t_ms,
                 "launches_timed": len(ts), "algorithmic_flops_per_launch": flops}
 
+    # ---------------- the HBM-bound kernels of the path (K1, K4) on this workload's shapes ----------------
+    kernels = None
+    if rank == 0 and args.precision == 'bf16':
+        kernels = hbm_kernel_lines(A, feats_d, cams_d, D, h, w, res if res is not None else out)
+        if roof is not None:
+            roof["traffic"], roof["traffic_source"] = ncu_traffic("k_conv3d_ring<32, 8, 2>")
+
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -299,9 +306,86 @@ def run_ours(args, rank, world, local_rank):
     }
     if roof is not None:
         line["roofline"] = roof
+    if kernels is not None:
+        line["hbm_kernels"] = kernels
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(workload)
     print(json.dumps(line))
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed
+    `ncu --set full` capture of this round (profiles/*_traffic.json, written by tools/ncu_traffic.py)."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
+        try:
+            for row in json.load(open(f)):
+                if kernel_substr in row['kernel']:
+                    return row['dram_bytes'], os.path.relpath(f, ROOT)
+        except Exception:
+            pass
+    return None, None
+
+
+def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
+    """K1 (fused homography + bilinear + cost slice, bf16 warped-only as the step uses it) and K4 (soft-argmin
+    with the fused x4 logit upsample) timed alone with CUDA events on the current stream; algorithmic bytes
+    per SURVEY.md 8(d) over the measured HBM copy peak."""
+    import torch
+    pk = peaks()
+    ds, di = cams_d[:, 0, 1, 3, 0].contiguous(), cams_d[:, 0, 1, 3, 1].contiguous()
+    F = feats_d.shape[-1]
+    V = D * h * w
+    logits = torch.randn(1, D, h, w, device=feats_d.device)
+
+    def k1():
+        return A.build_cost_volume(feats_d[:, 0], feats_d[:, 1], cams_d, D, ds, di, 0, 1, mode='warped_only',
+                                   out_dtype=torch.bfloat16)
+
+    def k4up():
+        return A.model._prob2depth(logits, ds, di, 4, False)
+
+    def k4():
+        return A.model._prob2depth(logits, ds, di, 1, False)
+
+    def timed(fn, iters=10):
+        # CUDA-graph replay of `iters` back-to-back launches, CUDA events around the replay on the replay stream
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(iters):
+                    fn()
+        torch.cuda.current_stream().wait_stream(st)
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3 / iters
+
+    out = {}
+    for name, fn, nbytes, note in (
+            ("K1 k_build_cost_volume_h (bf16, warped-only)", k1, 4 * h * w * F + 2 * V * F,
+             "reads the fp32 source feature map once, writes the (D,h,w,32) bf16 slice"),
+            ("K4 k_prob2depth_up_sliced<4> (x4 upsample fused)", k4up, 4 * V + 4 * 16 * h * w,
+             "reads the low-res logits once, writes the 4h x 4w depth map"),
+            ("K4 k_prob2depth_sliced (volume resolution)", k4, 4 * V + 4 * h * w, "reads the logits once")):
+        t = timed(fn)
+        out[name] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk['hbm'], "unit": "GB/s",
+                     "frac": nbytes / t / 1e9 / pk['hbm'], "algorithmic_bytes": nbytes, "us_per_launch": t * 1e6,
+                     "note": note + "; graph replay of 10 launches, CUDA events (K1 includes its 2 helper kernels: homographies, fp32->bf16 source)"}
+    return out
 
 
 def cpu_baseline(workload):
@@ -330,7 +414,7 @@ def cpu_baseline(workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=None, choices=[None] + list(WORKLOADS))

@@ -463,6 +463,14 @@ def test_prob2depth(A, golden):
     rl, rpl = om.prob2depth(vl, 21, dsb, dib, out_prob_map=True)
     assert rel_err(npy(el), rl) < 2e-6
     assert (np.abs(npy(pl) - rpl) > 1e-5).mean() < 1e-3
+    # fused x4 upsampling, sliced kernel: batch of 2, ragged output rows (4*7 = 28 < 32 lanes), D = 21 / 37 / 3
+    for D_, hh, ww in ((21, 9, 7), (37, 12, 19), (3, 5, 40)):
+        vu = (rng.standard_normal((2, D_, hh, ww)) * 3).astype(np.float32)
+        e, eu, p, pu = A.prob2depth_upsample(cu(vu), D_, cu(dsb), cu(dib), out_prob_map=True)
+        re_, reu, rp, rpu = om.prob2depth_upsample(vu, D_, dsb, dib, out_prob_map=True)
+        assert eu.shape == (2, 4 * hh, 4 * ww, 1)
+        assert rel_err(npy(eu), reu) < 2e-6 and rel_err(npy(e), re_) < 2e-6
+        assert (np.abs(npy(pu) - rpu) > 1e-5).mean() < 2e-3
 
 
 # ------------------------------------------------------------------ end to end (stage I + II)

@@ -1,0 +1,49 @@
+"""launch each hot-path kernel of cfg2 once between cudaProfilerStart/Stop (for `ncu --profile-from-start off`):
+K1 (bf16 warped-only + fp32 concat), the dominant CRM convs, the fused BN pass, K2 combine, K4 (plain and x4)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import atvsnet_b200 as A
+from atvsnet_b200 import network as N
+from atvsnet_b200.network import conv3d_raw
+
+D, h, w, F = 128, 128, 160, 32
+cams = torch.from_numpy(A.synthetic.orbit_cams(2, h, w, D)[None]).cuda()
+feats = torch.from_numpy(A.synthetic.smooth_features(2, h, w, F, seed=1)[None]).cuda()
+ds, di = cams[:, 0, 1, 3, 0].contiguous(), cams[:, 0, 1, 3, 1].contiguous()
+vol = torch.randn(1, D, h, w, device='cuda')
+
+
+def convs():
+    outs = []
+    for (cin, cout, stride, tr, shape) in ((32, 8, 1, False, (D, h, w)), (8, 8, 1, False, (D, h, w)), (32, 16, 2, False, (D, h, w)),
+                                           (8, 16, 2, False, (D, h, w)), (16, 8, 2, True, (D // 2, h // 2, w // 2)),
+                                           (8, 16, 1, False, (D, h, w))):
+        x = torch.randn(1, *shape, cin, device='cuda').to(torch.bfloat16)
+        wt = (torch.randn(3, 3, 3, cout, cin, device='cuda') if tr else torch.randn(3, 3, 3, cin, cout, device='cuda')) * 0.05
+        outs.append((x, wt, cout, stride, tr))
+    return outs
+
+
+cs = convs()
+
+
+def run():
+    A.build_cost_volume(feats[:, 0], feats[:, 1], cams, D, ds, di, 0, 1, mode='warped_only', out_dtype=torch.bfloat16)
+    A.build_cost_volume(feats[:, 0], feats[:, 1], cams, D, ds, di, 0, 1, mode='concat', out_dtype=torch.float32)
+    raws = []
+    for i, (x, wt, cout, stride, tr) in enumerate(cs):
+        raws.append(conv3d_raw(x, 'once%d' % i, wt, cout, stride, tr, True))
+    raw, st = raws[1]
+    N.bn_relu_add(raw, st, True, [], True, False, torch.bfloat16)
+    N.bn_relu_add_pair(raw, st, N._PendingRaw(raws[0][0], raws[0][1], True), True, None, False, torch.bfloat16)
+    A.prob2depth(vol, D, ds, di)
+    A.prob2depth_upsample(vol, D, ds, di)
+
+
+run()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+run()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
