@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.environ.get("ATVS_LIB") or os.path.join(_HERE, "libatvs.so")
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 _SIGS = {
@@ -20,10 +20,10 @@ _SIGS = {
     "atvs_build_cost_volume": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_conv3d_fp32": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_pack_conv_weights_bf16": [_p, _i, _i, _i, _p, _p],
-    "atvs_conv3d_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
-    "atvs_conv3d_bf16_bias": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
-    "atvs_bn_relu_add": [_p, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
-    "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
+    "atvs_conv3d_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "atvs_conv3d_bf16_bias": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
+    "atvs_bn_relu_add": [_p, _i, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
+    "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
     "atvs_add": [_p, _p, _p, _i, _ll, _p],
     "atvs_attention_combine": [_p, _p, _i, _ll, _i, _i, _p, _p],

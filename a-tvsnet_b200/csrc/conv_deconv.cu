@@ -23,6 +23,7 @@ struct DcParams {
     int B, Dj, Hj, Wj;             // input extent (= iteration space)
     int ltd, lth, ltw, nTD, nTH, nTW;
     int Cout, ncols;
+    int raw16;                     // raw output dtype: 0 fp32, 1 saturated fp16
     int nstages;
     int sh_off[8][3];              // shift s reads input voxel j + sh_off[s]
     int sh_first[9];               // pairs of shift s are [sh_first[s], sh_first[s+1])
@@ -171,7 +172,7 @@ k_deconv3d_tc(const __grid_constant__ DcMaps tm, const __grid_constant__ DcParam
         float run[2 * NPAD];
 #pragma unroll
         for (int i = 0; i < 2 * NPAD; ++i) run[i] = 0.f;
-        const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
+        const int vec = raw_vec_mode(out, p.ncols, p.Cout, 0);
         const int Do = 2 * p.Dj, Ho = 2 * p.Hj, Wo = 2 * p.Wj;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -191,8 +192,8 @@ k_deconv3d_tc(const __grid_constant__ DcMaps tm, const __grid_constant__ DcParam
                 const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
                 const size_t o = valid ? ((((size_t)b * Do + (2 * jz + pz)) * Ho + (2 * jy + py)) * Wo + (2 * jx + px)) * p.Cout : 0;
                 // the accumulator set is released after the LAST class has been read
-                epilogue_tile<NPAD>(taddr + (uint32_t)(cls * NPAD), cls == 7 ? &tempty[acc] : nullptr, lane, valid, out + o,
-                                    p.ncols, vec4, stats != nullptr, run);
+                epilogue_tile<NPAD>(taddr + (uint32_t)(cls * NPAD), cls == 7 ? &tempty[acc] : nullptr, lane, valid, out, o,
+                                    p.ncols, vec, p.raw16, stats != nullptr, run);
             }
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, 0, p.ncols);
@@ -287,7 +288,7 @@ int deconv_fused_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaSt
 }
 
 int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-                 double* stats, cudaStream_t st) {
+                 int raw16, double* stats, cudaStream_t st) {
     EncodeTiledFn encode = get_encode();
     if (!encode) {
         atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled entry point not available");
@@ -297,6 +298,7 @@ int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int 
     DcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.Dj = D; p.Hj = H; p.Wj = W; p.Cout = Cout; p.ncols = Cout;
+    p.raw16 = raw16;
     {
         static const int opts[][3] = {{2, 8, 8}, {1, 8, 16}, {4, 4, 8}, {2, 4, 16}, {1, 4, 32}, {4, 8, 4}, {8, 4, 4},
                                       {1, 16, 8}, {2, 16, 4}, {8, 8, 2}, {16, 4, 2}, {32, 2, 2}, {8, 16, 1}, {16, 8, 1},

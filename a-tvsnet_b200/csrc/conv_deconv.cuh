@@ -7,4 +7,4 @@ bool deconv_fused_applicable(int Cin, int Cout);
 size_t deconv_fused_weight_bytes(int Cin, int Cout);
 int deconv_fused_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
 int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-                 double* stats, cudaStream_t st);
+                 int raw16, double* stats, cudaStream_t st);

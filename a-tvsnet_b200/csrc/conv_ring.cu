@@ -61,6 +61,7 @@ constexpr int RG_MAXR = 16;      // ring slots (mbarrier pairs)
 struct RingParams {
     int B, D, H, W;
     int Cout, coff, ncols;
+    int raw16;          // raw output dtype: 0 fp32, 1 saturated fp16
     int nXT, nYT, nZS, ZS;
     int nring, pf;      // ring slots, planes of cp.async in flight per producer thread (pf <= nring - 1, <= 8)
     int wbytes;
@@ -357,6 +358,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
 #pragma unroll
         for (int k = 0; k < 2 * CP; ++k) run[k] = 0.f;
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
+        const int vec = raw_vec_mode(out, p.ncols, p.Cout, p.coff);
         uint32_t grp = 0, gphase = 0;
         TRACE_DECL
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
@@ -398,7 +400,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                 for (int mt = 0; mt < RG_MT; ++mt) {
                     const int xm = xq + 8 * mt;
                     if (xm >= p.W) continue;
-                    float* op = out + obase + (size_t)t * zstride + (size_t)xm * p.Cout;
+                    const size_t ooff = obase + (size_t)t * zstride + (size_t)xm * p.Cout;
                     if (bias != nullptr) {
                         // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
                         const float* brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xm) * p.Cout + p.coff;
@@ -415,16 +417,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                                 if (c < p.ncols) v[mt][c] += __ldg(brow + c);
                         }
                     }
-                    if (vec4) {
-#pragma unroll
-                        for (int c = 0; c < CP; c += 4)
-                            if (c < p.ncols)
-                                *reinterpret_cast<float4*>(op + c) = make_float4(v[mt][c], v[mt][c + 1], v[mt][c + 2], v[mt][c + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CP; ++c)
-                            if (c < p.ncols) op[c] = v[mt][c];
-                    }
+                    store_raw_row<CP>(out, ooff, v[mt], p.ncols, vec, p.raw16);
                     if (stats != nullptr) {
                         // per-THREAD running moments (rows = this thread's voxels): no cross-lane traffic per tile
 #pragma unroll
@@ -535,13 +528,14 @@ bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
 }
 
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              double* stats, const float* bias, cudaStream_t st) {
+              int raw16, double* stats, const float* bias, cudaStream_t st) {
     const int cp = ring_npad(Cin, Cout);
     const int nslabs = (Cout + cp - 1) / cp;
     const int sms = atvs_num_sms();
     RingParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
+    p.raw16 = raw16;
     p.nXT = (W + RG_TX - 1) / RG_TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
     p.wbytes = (int)ring_slab_bytes(Cin, cp);

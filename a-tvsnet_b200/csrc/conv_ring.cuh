@@ -18,7 +18,7 @@ size_t ring_weight_bytes(int Cin, int Cout);
 int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed);
 int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              double* stats, const float* bias, cudaStream_t st);
+              int raw16, double* stats, const float* bias, cudaStream_t st);
 
 // stride-2 variant (conv_ring_s2.cu)
 bool ring_s2_supported(int Cin, int Cout);
@@ -26,4 +26,4 @@ size_t ring_s2_weight_bytes(int Cin, int Cout);
 int ring_s2_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
 bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout);
 int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-                 double* stats, const float* bias, cudaStream_t st);
+                 int raw16, double* stats, const float* bias, cudaStream_t st);

@@ -34,6 +34,7 @@ struct S2Params {
     int B, D, H, W;             // input extents
     int Do, Ho, Wo;
     int Cout, coff, ncols;
+    int raw16;                  // raw output dtype: 0 fp32, 1 saturated fp16
     int nXT, nYT, nZS, ZS;
     int nring;
     int wbytes;
@@ -279,6 +280,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
 #pragma unroll
         for (int k = 0; k < 2 * CP; ++k) run[k] = 0.f;
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
+        const int vec = raw_vec_mode(out, p.ncols, p.Cout, p.coff);
         uint32_t grp = 0, gphase = 0;
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const S2Unit un = s2_decode(p, u);
@@ -303,7 +305,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
                 if (!valid) continue;
-                float* op = out + obase + (size_t)t * zstride;
+                const size_t ooff = obase + (size_t)t * zstride;
                 if (bias != nullptr) {
                     // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
                     const int z = un.z0 + t;
@@ -322,15 +324,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
                             if (c < p.ncols) v[c] += __ldg(brow + c);
                     }
                 }
-                if (vec4) {
-#pragma unroll
-                    for (int c = 0; c < CP; c += 4)
-                        if (c < p.ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CP; ++c)
-                        if (c < p.ncols) op[c] = v[c];
-                }
+                store_raw_row<CP>(out, ooff, v, p.ncols, vec, p.raw16);
                 if (stats != nullptr) {
 #pragma unroll
                     for (int c = 0; c < CP; ++c) {
@@ -430,13 +424,14 @@ bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout) {
 }
 
 int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-                 double* stats, const float* bias, cudaStream_t st) {
+                 int raw16, double* stats, const float* bias, cudaStream_t st) {
     const int cp = s2_cp(Cout);
     const int nslabs = (Cout + cp - 1) / cp;
     const int sms = atvs_num_sms();
     S2Params p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.D = D; p.H = H; p.W = W; p.Do = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Cout = Cout;
+    p.raw16 = raw16;
     p.nXT = (p.Wo + S2_TX - 1) / S2_TX;
     p.nYT = (p.Ho + S2_TY - 1) / S2_TY;
     p.wbytes = (int)s2_slab_bytes(Cin, cp);

@@ -44,6 +44,7 @@ struct TcParams {
     int ltd, lth, ltw;         // log2 of the brick dims (TD*TH*TW == 128)
     int nTD, nTH, nTW;
     int Cout, coff, ncols;     // real channel count, slab offset, real columns in this slab
+    int raw16;                 // raw output dtype: 0 fp32, 1 saturated fp16
     int nstages;
     long long ntiles;
 };
@@ -221,8 +222,8 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                 const int zc = (jz == 0) ? 0 : (jz == p.Do - 1 ? 2 : 1);
                 brow = bias + ((((size_t)b * 3 + zc) * p.Ho + jy) * p.Wo + jx) * p.Cout + p.coff;
             }
-            epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out + o, p.ncols,
-                                (p.ncols & 3) == 0 && (p.Cout & 3) == 0, stats != nullptr, run, brow);
+            epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out, o, p.ncols,
+                                raw_vec_mode(out, p.ncols, p.Cout, p.coff), p.raw16, stats != nullptr, run, brow);
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
     }
@@ -363,28 +364,33 @@ extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cou
 }
 
 static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
-                           int stride, int transposed, const float* plane_bias, float* raw_out, double* stats,
-                           atvs_stream_t stream);
+                           int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
+                           double* stats, atvs_stream_t stream);
 
 extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                                int Cout, int stride, int transposed, float* raw_out, double* stats,
+                                int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
                                 atvs_stream_t stream) {
-    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, transposed, nullptr, raw_out, stats, stream);
+    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, transposed, nullptr, raw_out, raw_dtype, stats,
+                            stream);
 }
 
 extern "C" int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                                     int Cout, int stride, const float* plane_bias, float* raw_out, double* stats,
-                                     atvs_stream_t stream) {
+                                     int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
+                                     double* stats, atvs_stream_t stream) {
     ATVS_CHECK_ARG(plane_bias, ATVS_E_NULL, "atvs_conv3d_bf16_bias: plane_bias is NULL");
     ATVS_CHECK_ARG(((uintptr_t)plane_bias & 15) == 0, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: plane_bias must be 16-byte aligned");
     ATVS_CHECK_ARG((D + stride - 1) / stride >= 2, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: needs at least 2 output planes");
-    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, stats, stream);
+    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, raw_dtype, stats, stream);
 }
 
 static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
-                           int stride, int transposed, const float* plane_bias, float* raw_out, double* stats,
-                           atvs_stream_t stream) {
+                           int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
+                           double* stats, atvs_stream_t stream) {
+    float* raw_out = (float*)raw_out_v;        // element offsets are dtype independent; kernels re-type the base
     ATVS_CHECK_ARG(x_bf16 && wpacked && raw_out, ATVS_E_NULL, "atvs_conv3d_bf16: NULL pointer");
+    ATVS_CHECK_ARG(raw_dtype == ATVS_F32 || raw_dtype == ATVS_F16, ATVS_E_DTYPE,
+                   "atvs_conv3d_bf16: raw_dtype %d (ATVS_F32 or ATVS_F16)", raw_dtype);
+    const int raw16 = raw_dtype == ATVS_F16;
     ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16: bad shape");
     ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
                    "atvs_conv3d_bf16: Cin=%d (8, 16, 32 or 64)", Cin);
@@ -403,13 +409,13 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
     cudaStream_t st = (cudaStream_t)stream;
     if (transposed && deconv_fused_applicable(Cin, Cout))
         return deconv_fused(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 1), B, D, H, W, Cin, Cout, raw_out,
-                            stats, st);
+                            raw16, stats, st);
     if (!transposed && stride == 2 && ring_s2_applicable(B, D, H, W, Cin, Cout))
         return ring_s2_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout), B, D, H,
-                            W, Cin, Cout, raw_out, stats, plane_bias, st);
+                            W, Cin, Cout, raw_out, raw16, stats, plane_bias, st);
     if (ring_applicable(B, D, H, W, stride, transposed))
         return ring_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
-                         stats, plane_bias, st);
+                         raw16, stats, plane_bias, st);
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     const int ncls = transposed ? 8 : 1;
     const int tps = (Cin == 8) ? 2 : 1;
@@ -430,6 +436,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
         p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
         p.os = g.os;
         p.Cout = Cout;
+        p.raw16 = raw16;
         p.ncls = c1 - c0;
         // brick shape: 128 voxels, minimise padded volume, prefer a wide x extent
         {

@@ -177,9 +177,34 @@ constexpr int BN_MAXC = 256;
 //   a layer whose only consumer is that add never has its normalised tensor written and re-read.
 // 8 elements per thread and iteration when C is a multiple of 8: two 16-byte raw loads, one 16-byte
 // bf16 store.
-template <typename T>
+// raw tensors are fp32 or fp16 (RawT): 8 / 4 / 1 consecutive values as fp32
+template <typename RawT> struct RawLd;
+template <> struct RawLd<float> {
+    static __device__ __forceinline__ void ld8(const float* p, float4& a, float4& b) {
+        // one 32-byte load when the row is 32-byte aligned is not guaranteed here (16-byte contract): two LDG.128
+        a = __ldcs(reinterpret_cast<const float4*>(p)); b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    }
+    static __device__ __forceinline__ float4 ld4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+};
+template <> struct RawLd<__half> {
+    static __device__ __forceinline__ float2 h2(unsigned u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+    static __device__ __forceinline__ void ld8(const __half* p, float4& a, float4& b) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+        const float2 x = h2(u.x), y = h2(u.y), z = h2(u.z), w = h2(u.w);
+        a = make_float4(x.x, x.y, y.x, y.y); b = make_float4(z.x, z.y, w.x, w.y);
+    }
+    static __device__ __forceinline__ float4 ld4(const __half* p) {
+        const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p));
+        const float2 x = h2(u.x), y = h2(u.y);
+        return make_float4(x.x, x.y, y.x, y.y);
+    }
+    static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+};
+
+template <typename T, typename RawT>
 __global__ void __launch_bounds__(256)
-k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, const float* __restrict__ raw2,
+k_bn_relu_add(const RawT* __restrict__ raw, const double* __restrict__ stats, const RawT* __restrict__ raw2,
               const double* __restrict__ stats2, long long count, int C, float eps, int relu,
               const T* __restrict__ s1, const T* __restrict__ s2, T* __restrict__ out_plain, T* __restrict__ out_sum) {
     __shared__ float sh_inv[BN_MAXC], sh_off[BN_MAXC], sh_inv2[BN_MAXC], sh_off2[BN_MAXC];
@@ -220,13 +245,16 @@ k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, c
              i += (long long)gridDim.x * blockDim.x) {
             const long long e = i << 3;
             const int c = pow2 ? (int)(e & (C - 1)) : (int)(e % C);
-            float4 ya = norm4(__ldcs(reinterpret_cast<const float4*>(raw + e)), sh_inv, sh_off, c);
-            float4 yb = norm4(__ldcs(reinterpret_cast<const float4*>(raw + e) + 1), sh_inv, sh_off, c + 4);
+            float4 ra, rb;
+            RawLd<RawT>::ld8(raw + e, ra, rb);
+            float4 ya = norm4(ra, sh_inv, sh_off, c);
+            float4 yb = norm4(rb, sh_inv, sh_off, c + 4);
             if (out_plain) Vec8<T>::st(out_plain + e, ya, yb);
             if (out_sum) {
                 if (raw2) {
-                    add4(ya, norm4(__ldcs(reinterpret_cast<const float4*>(raw2 + e)), sh_inv2, sh_off2, c));
-                    add4(yb, norm4(__ldcs(reinterpret_cast<const float4*>(raw2 + e) + 1), sh_inv2, sh_off2, c + 4));
+                    RawLd<RawT>::ld8(raw2 + e, ra, rb);
+                    add4(ya, norm4(ra, sh_inv2, sh_off2, c));
+                    add4(yb, norm4(rb, sh_inv2, sh_off2, c + 4));
                 }
                 if (s1) { float4 a, b; Vec8<T>::ld(s1 + e, a, b); add4(ya, a); add4(yb, b); }
                 if (s2) { float4 a, b; Vec8<T>::ld(s2 + e, a, b); add4(ya, a); add4(yb, b); }
@@ -238,10 +266,10 @@ k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, c
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
              i += (long long)gridDim.x * blockDim.x) {
             const int c = (int)((i << 2) % C);
-            float4 y = norm4(__ldcs(reinterpret_cast<const float4*>(raw) + i), sh_inv, sh_off, c);
+            float4 y = norm4(RawLd<RawT>::ld4(raw + (i << 2)), sh_inv, sh_off, c);
             if (out_plain) Vec4<T>::st(out_plain + (i << 2), y);
             if (out_sum) {
-                if (raw2) add4(y, norm4(__ldcs(reinterpret_cast<const float4*>(raw2) + i), sh_inv2, sh_off2, c));
+                if (raw2) add4(y, norm4(RawLd<RawT>::ld4(raw2 + (i << 2)), sh_inv2, sh_off2, c));
                 if (s1) add4(y, Vec4<T>::ld(s1 + (i << 2)));
                 if (s2) add4(y, Vec4<T>::ld(s2 + (i << 2)));
                 Vec4<T>::st(out_sum + (i << 2), y);
@@ -251,12 +279,12 @@ k_bn_relu_add(const float* __restrict__ raw, const double* __restrict__ stats, c
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
              i += (long long)gridDim.x * blockDim.x) {
             const int c = (int)(i % C);
-            float y = raw[i] * sh_inv[c] - sh_off[c];
+            float y = RawLd<RawT>::ld1(raw + i) * sh_inv[c] - sh_off[c];
             if (relu) y = fmaxf(y, 0.f);
             if (out_plain) Vec4<T>::st1(out_plain + i, y);
             if (out_sum) {
                 if (raw2) {
-                    float y2 = raw2[i] * sh_inv2[c] - sh_off2[c];
+                    float y2 = RawLd<RawT>::ld1(raw2 + i) * sh_inv2[c] - sh_off2[c];
                     if (relu) y2 = fmaxf(y2, 0.f);
                     y += y2;
                 }
@@ -492,22 +520,18 @@ extern "C" int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int 
     return 0;
 }
 
-static int bn_relu_add_impl(const float* raw, const double* stats, const float* raw2, const double* stats2, long long count,
-                            int C, float eps, int relu, const void* skip1, const void* skip2, void* out_plain,
-                            void* out_sum, int act_dtype, cudaStream_t st, const char* who) {
-    ATVS_CHECK_ARG(raw && (out_plain || out_sum), ATVS_E_NULL, "%s: NULL pointer", who);
-    ATVS_CHECK_ARG(count > 0 && C > 0 && C <= BN_MAXC, ATVS_E_SHAPE, "%s: count=%lld C=%d", who, count, C);
-    ATVS_CHECK_ARG((C & 3) != 0 || (((uintptr_t)raw | (uintptr_t)raw2 | (uintptr_t)skip1 | (uintptr_t)skip2 |
-                                      (uintptr_t)out_plain | (uintptr_t)out_sum) & 15) == 0,
-                   ATVS_E_SHAPE, "%s: buffers must be 16-byte aligned", who);
+template <typename RawT>
+static int bn_relu_add_launch(const RawT* raw, const double* stats, const RawT* raw2, const double* stats2, long long count,
+                              int C, float eps, int relu, const void* skip1, const void* skip2, void* out_plain,
+                              void* out_sum, int act_dtype, cudaStream_t st, const char* who) {
     const unsigned grid = grid_for(count * C / 8 + 1, 256, 8);
     if (act_dtype == ATVS_F32)
-        k_bn_relu_add<float><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu, (const float*)skip1,
-                                                   (const float*)skip2, (float*)out_plain, (float*)out_sum);
+        k_bn_relu_add<float, RawT><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu, (const float*)skip1,
+                                                         (const float*)skip2, (float*)out_plain, (float*)out_sum);
     else if (act_dtype == ATVS_BF16)
-        k_bn_relu_add<__nv_bfloat16><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu,
-                                                           (const __nv_bfloat16*)skip1, (const __nv_bfloat16*)skip2,
-                                                           (__nv_bfloat16*)out_plain, (__nv_bfloat16*)out_sum);
+        k_bn_relu_add<__nv_bfloat16, RawT><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu,
+                                                                 (const __nv_bfloat16*)skip1, (const __nv_bfloat16*)skip2,
+                                                                 (__nv_bfloat16*)out_plain, (__nv_bfloat16*)out_sum);
     else {
         atvs_set_error("%s: act_dtype %d", who, act_dtype);
         return ATVS_E_DTYPE;
@@ -516,19 +540,35 @@ static int bn_relu_add_impl(const float* raw, const double* stats, const float* 
     return 0;
 }
 
-extern "C" int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps, int relu,
-                                const void* skip1, const void* skip2, void* out_plain, void* out_sum, int act_dtype,
-                                atvs_stream_t stream) {
-    return bn_relu_add_impl(raw, stats, nullptr, nullptr, count, C, eps, relu, skip1, skip2, out_plain, out_sum, act_dtype,
-                            (cudaStream_t)stream, "atvs_bn_relu_add");
+static int bn_relu_add_impl(const void* raw, const double* stats, const void* raw2, const double* stats2, int raw_dtype,
+                            long long count, int C, float eps, int relu, const void* skip1, const void* skip2,
+                            void* out_plain, void* out_sum, int act_dtype, cudaStream_t st, const char* who) {
+    ATVS_CHECK_ARG(raw && (out_plain || out_sum), ATVS_E_NULL, "%s: NULL pointer", who);
+    ATVS_CHECK_ARG(count > 0 && C > 0 && C <= BN_MAXC, ATVS_E_SHAPE, "%s: count=%lld C=%d", who, count, C);
+    ATVS_CHECK_ARG(raw_dtype == ATVS_F32 || raw_dtype == ATVS_F16, ATVS_E_DTYPE, "%s: raw_dtype %d", who, raw_dtype);
+    ATVS_CHECK_ARG((C & 3) != 0 || (((uintptr_t)raw | (uintptr_t)raw2 | (uintptr_t)skip1 | (uintptr_t)skip2 |
+                                      (uintptr_t)out_plain | (uintptr_t)out_sum) & 15) == 0,
+                   ATVS_E_SHAPE, "%s: buffers must be 16-byte aligned", who);
+    if (raw_dtype == ATVS_F16)
+        return bn_relu_add_launch<__half>((const __half*)raw, stats, (const __half*)raw2, stats2, count, C, eps, relu, skip1,
+                                          skip2, out_plain, out_sum, act_dtype, st, who);
+    return bn_relu_add_launch<float>((const float*)raw, stats, (const float*)raw2, stats2, count, C, eps, relu, skip1, skip2,
+                                     out_plain, out_sum, act_dtype, st, who);
 }
 
-extern "C" int atvs_bn_relu_add_pair(const float* raw_a, const double* stats_a, const float* raw_b, const double* stats_b,
-                                     long long count, int C, float eps, int relu, const void* skip, void* out_plain_a,
-                                     void* out_sum, int act_dtype, atvs_stream_t stream) {
+extern "C" int atvs_bn_relu_add(const void* raw, int raw_dtype, const double* stats, long long count, int C, float eps,
+                                int relu, const void* skip1, const void* skip2, void* out_plain, void* out_sum,
+                                int act_dtype, atvs_stream_t stream) {
+    return bn_relu_add_impl(raw, stats, nullptr, nullptr, raw_dtype, count, C, eps, relu, skip1, skip2, out_plain, out_sum,
+                            act_dtype, (cudaStream_t)stream, "atvs_bn_relu_add");
+}
+
+extern "C" int atvs_bn_relu_add_pair(const void* raw_a, const double* stats_a, const void* raw_b, const double* stats_b,
+                                     int raw_dtype, long long count, int C, float eps, int relu, const void* skip,
+                                     void* out_plain_a, void* out_sum, int act_dtype, atvs_stream_t stream) {
     ATVS_CHECK_ARG(raw_b && out_sum, ATVS_E_NULL, "atvs_bn_relu_add_pair: NULL pointer");
-    return bn_relu_add_impl(raw_a, stats_a, raw_b, stats_b, count, C, eps, relu, skip, nullptr, out_plain_a, out_sum,
-                            act_dtype, (cudaStream_t)stream, "atvs_bn_relu_add_pair");
+    return bn_relu_add_impl(raw_a, stats_a, raw_b, stats_b, raw_dtype, count, C, eps, relu, skip, nullptr, out_plain_a,
+                            out_sum, act_dtype, (cudaStream_t)stream, "atvs_bn_relu_add_pair");
 }
 
 extern "C" int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, atvs_stream_t stream) {

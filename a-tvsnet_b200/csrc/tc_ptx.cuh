@@ -198,12 +198,81 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
         : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// raw convolution outputs: fp32 (parity path / layers without BN) or SATURATED fp16 (layers whose output only
+// feeds the batch-statistics BN pass: the moments still come from the fp32 accumulators, fp16 keeps 11
+// significant bits of the value that the BN pass immediately rounds to bf16 anyway, and halves the bytes
+// written here and read back there).  `off` is the ELEMENT offset of the row's first column.
+//   vec: 8 = rows of 8k columns, 32-byte aligned (one STG.256 / one 16-byte fp16 store per 8 columns)
+//        4 = rows of 4k columns, 16-byte aligned;  1 = scalar
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ int raw_vec_mode(const void* out, int ncols, int Cout, int coff) {
+    if (((ncols | Cout | coff) & 7) == 0 && (((uintptr_t)out) & 31) == 0) return 8;
+    if (((ncols | Cout | coff) & 3) == 0 && (((uintptr_t)out) & 15) == 0) return 4;
+    return 1;
+}
+template <int NC>
+__device__ __forceinline__ void store_raw_row(float* out, size_t off, const float* v, int ncols, int vec, int raw16) {
+    if (!raw16) {
+        float* op = out + off;
+        if (vec == 8) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 8)
+                if (c < ncols)
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + c), "f"(v[c]),
+                                 "f"(v[c + 1]), "f"(v[c + 2]), "f"(v[c + 3]), "f"(v[c + 4]), "f"(v[c + 5]), "f"(v[c + 6]),
+                                 "f"(v[c + 7])
+                                 : "memory");
+        } else if (vec == 4) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 4)
+                if (c < ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < ncols) op[c] = v[c];
+        }
+    } else {
+        __half* op = reinterpret_cast<__half*>(out) + off;
+        if (vec == 8) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 8)
+                if (c < ncols) {
+                    uint4 u;
+                    u.x = pack_f16x2_sat(v[c], v[c + 1]); u.y = pack_f16x2_sat(v[c + 2], v[c + 3]);
+                    u.z = pack_f16x2_sat(v[c + 4], v[c + 5]); u.w = pack_f16x2_sat(v[c + 6], v[c + 7]);
+                    *reinterpret_cast<uint4*>(op + c) = u;
+                }
+        } else if (vec == 4) {
+#pragma unroll
+            for (int c = 0; c < NC; c += 4)
+                if (c < ncols) {
+                    uint2 u;
+                    u.x = pack_f16x2_sat(v[c], v[c + 1]); u.y = pack_f16x2_sat(v[c + 2], v[c + 3]);
+                    *reinterpret_cast<uint2*>(op + c) = u;
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < ncols) {
+                    const uint32_t u = pack_f16x2_sat(v[c], 0.f);
+                    reinterpret_cast<unsigned short*>(op)[c] = (unsigned short)(u & 0xffffu);
+                }
+        }
+    }
+}
+
 // epilogue of one 128-row accumulator tile: TMEM -> registers, raw fp32 store of the real columns,
 // per-channel sum / sum of squares folded into per-lane running registers (batch-stat BN).
 template <int NPAD>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_bar, int lane, bool valid, float* op,
-                                              int ncols, bool vec4, bool want_stats, float* run,
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_bar, int lane, bool valid, float* out,
+                                              size_t off, int ncols, int vec, int raw16, bool want_stats, float* run,
                                               const float* bias_row = nullptr) {
+    const bool vec4 = vec >= 4;
     float v[NPAD];
 #pragma unroll
     for (int c = 0; c < NPAD; c += 16) tc_ld16(taddr + c, v + c);
@@ -226,17 +295,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_b
                 if (c < ncols) v[c] += __ldg(bias_row + c);
         }
     }
-    if (valid) {
-        if (vec4) {
-#pragma unroll
-            for (int c = 0; c < NPAD; c += 4)
-                if (c < ncols) *reinterpret_cast<float4*>(op + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < NPAD; ++c)
-                if (c < ncols) op[c] = v[c];
-        }
-    }
+    if (valid) store_raw_row<NPAD>(out, off, v, ncols, vec, raw16);
     if (want_stats && valid) {
         // per-THREAD running moments (row = this thread's voxel): no cross-lane traffic per tile
 #pragma unroll

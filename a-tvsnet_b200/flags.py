@@ -14,6 +14,8 @@ class _Flags(object):
         self.gpu_id = 0
         # 'fp32' = CUDA-core parity path, 'bf16' = tcgen05 tensor-core path for the 3-D CNN
         self.precision = 'bf16'
+        # tensor-core path: dtype of the raw (pre-BN) convolution outputs, 'f16' (saturated) or 'f32'
+        self.raw_dtype = 'f16'
 
 
 FLAGS = _Flags()

@@ -96,18 +96,35 @@ def conv3d_split(cv, wkey, w, cout, stride, stats_buf):
     bias, _ = conv3d_raw(cv.ref_tiled(planes), wkey + '/ref', w_ref, cout, stride, False, False)
     if stride == 2:                      # planes (interior, last) -> classes (first == interior, interior, last)
         bias = torch.cat([bias[:, :1], bias[:, :1], bias[:, 1:2]], dim=1).contiguous()
-    return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias)
+    return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias,
+                      raw_dtype=raw_dtype_for_bn(cv.warped))
 
 
-def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None, bias=None, out=None):
-    """x (B,D,H,W,Cin) fp32|bf16 -> raw fp32 (B,Do,Ho,Wo,Cout) [+ fp64 moments (2*Cout)].
+def raw_dtype_for_bn(x):
+    """dtype of a raw convolution output that only feeds the BN pass: fp16 on the tensor-core path
+    (FLAGS.raw_dtype = 'f16': saturated, moments still from the fp32 accumulators), fp32 otherwise."""
+    if x.dtype == torch.bfloat16 and getattr(FLAGS, 'raw_dtype', 'f16') == 'f16':
+        return torch.float16
+    return torch.float32
+
+
+def _raw_code(t):
+    return L.F16 if t.dtype == torch.float16 else L.F32
+
+
+def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None, bias=None, out=None,
+               raw_dtype=torch.float32):
+    """x (B,D,H,W,Cin) fp32|bf16 -> raw (B,Do,Ho,Wo,Cout) fp32 (or fp16 on request, bf16 inputs only)
+    [+ fp64 moments (2*Cout)].
     ``stats_buf``: pre-zeroed fp64 buffer of >= 2*Cout elements to accumulate the moments into."""
     B, D, H, W, cin = x.shape
     if transposed:
         od, oh, ow = 2 * D, 2 * H, 2 * W
     else:
         od, oh, ow = -(-D // stride), -(-H // stride), -(-W // stride)
-    raw = out if out is not None else torch.empty((B, od, oh, ow, cout), dtype=torch.float32, device=x.device)
+    if x.dtype == torch.float32:
+        raw_dtype = torch.float32
+    raw = out if out is not None else torch.empty((B, od, oh, ow, cout), dtype=raw_dtype, device=x.device)
     if not want_stats:
         stats = None
     elif stats_buf is not None:
@@ -125,10 +142,10 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None,
         pk = _packed_weight(wkey, w, cin, cout, int(transposed))
         if bias is not None:
             L.call("atvs_conv3d_bf16_bias", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, L.ptr(bias),
-                   L.ptr(raw), L.ptr(stats), L.stream())
+                   L.ptr(raw), _raw_code(raw), L.ptr(stats), L.stream())
         else:
             L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
-                   L.ptr(raw), L.ptr(stats), L.stream())
+                   L.ptr(raw), _raw_code(raw), L.ptr(stats), L.stream())
     if prof:
         e1.record()
         PROFILE[1].append((wkey, e0, e1, raw.numel() // cout, cin, cout))
@@ -141,7 +158,7 @@ def bn_relu_add(raw, stats, relu, skips, want_plain, want_sum, dtype):
     summ = torch.empty(raw.shape, dtype=dtype, device=raw.device) if want_sum else None
     s1 = skips[0] if len(skips) > 0 else None
     s2 = skips[1] if len(skips) > 1 else None
-    L.call("atvs_bn_relu_add", L.ptr(raw), L.ptr(stats), count, raw.shape[-1], BN_EPS, int(relu), L.ptr(s1),
+    L.call("atvs_bn_relu_add", L.ptr(raw), _raw_code(raw), L.ptr(stats), count, raw.shape[-1], BN_EPS, int(relu), L.ptr(s1),
            L.ptr(s2), L.ptr(plain), L.ptr(summ), L.F32 if dtype == torch.float32 else L.BF16, L.stream())
     return plain, summ
 
@@ -159,7 +176,9 @@ def bn_relu_add_pair(raw_a, stats_a, pend, relu, skip, want_plain, dtype):
     count = raw_a.numel() // raw_a.shape[-1]
     plain = torch.empty(raw_a.shape, dtype=dtype, device=raw_a.device) if want_plain else None
     summ = torch.empty(raw_a.shape, dtype=dtype, device=raw_a.device)
-    L.call("atvs_bn_relu_add_pair", L.ptr(raw_a), L.ptr(stats_a), L.ptr(pend.raw), L.ptr(pend.stats), count,
+    if pend.raw.dtype != raw_a.dtype:
+        raise RuntimeError("bn_relu_add_pair: raw dtypes differ")
+    L.call("atvs_bn_relu_add_pair", L.ptr(raw_a), L.ptr(stats_a), L.ptr(pend.raw), L.ptr(pend.stats), _raw_code(raw_a), count,
            raw_a.shape[-1], BN_EPS, int(relu), L.ptr(skip), L.ptr(plain), L.ptr(summ),
            L.F32 if dtype == torch.float32 else L.BF16, L.stream())
     return plain, summ
@@ -315,7 +334,8 @@ class Network(object):
                                               node.params['stride'], arena[arena_slot[name]])
                 else:
                     raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
-                                            node.params['stride'], transposed, True, arena[arena_slot[name]])
+                                            node.params['stride'], transposed, True, arena[arena_slot[name]],
+                                            raw_dtype=raw_dtype_for_bn(x))
                 # a layer that only feeds an `add` led by a LATER conv layer is normalised inside that
                 # layer's fused pass: keep its raw output and moments until then
                 cons = consumers[name]
@@ -421,7 +441,7 @@ def attention_activations(views, scope):
     raw = attention_activations_raw(views, scope)
     dt = views[0].dtype
     act = torch.empty(raw.shape, dtype=dt, device=raw.device)
-    L.call("atvs_bn_relu_add", L.ptr(raw), None, raw.shape[0] * raw.shape[1], raw.shape[2], BN_EPS, 1, None, None,
+    L.call("atvs_bn_relu_add", L.ptr(raw), _raw_code(raw), None, raw.shape[0] * raw.shape[1], raw.shape[2], BN_EPS, 1, None, None,
            L.ptr(act), None, L.F32 if dt == torch.float32 else L.BF16, L.stream())
     return act
 

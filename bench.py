@@ -151,6 +151,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     lib = A._lib.load()
     A.FLAGS.precision = args.precision
+    A.FLAGS.raw_dtype = args.raw_dtype
     workload = args.workload or 'cfg2'
     sharded = workload == 'cfg3' and world > 1
     group = dist.group.WORLD if sharded else None
@@ -419,6 +420,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=None, choices=[None] + list(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--raw-dtype', default='f16', choices=['f16', 'f32'],
+                    help='storage of the raw (pre-BN) convolution outputs on the bf16 path')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

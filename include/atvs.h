@@ -15,7 +15,7 @@
  *   - return value: 0 = ok, >0 = cudaError_t / CUresult of the failing call,
  *     <0 = argument error (ATVS_E_*); atvs_last_error() returns a thread-local message;
  *   - activations are channels-last (B,D,H,W,C), exactly the reference's NDHWC layout;
- *   - dtype codes: ATVS_F32 = 0, ATVS_BF16 = 1.
+ *   - dtype codes: ATVS_F32 = 0, ATVS_BF16 = 1, ATVS_F16 = 2 (raw convolution outputs only).
  */
 #ifndef ATVS_H_
 #define ATVS_H_
@@ -29,6 +29,7 @@ extern "C" {
 
 #define ATVS_F32  0
 #define ATVS_BF16 1
+#define ATVS_F16  2
 
 #define ATVS_E_SHAPE  (-1)   /* bad shape / alignment                     */
 #define ATVS_E_DTYPE  (-2)   /* unsupported dtype code                    */
@@ -84,7 +85,10 @@ int atvs_build_cost_volume(const float* ref_feature, const float* view_feature,
  * the PRE-batch-norm result.  stats (2*Cout doubles: sum, sum of squares; caller zeroes it)
  * receives the per-channel moments of raw_out when not NULL (batch-statistics BN, F4).
  * atvs_conv3d_fp32: CUDA-core fp32 parity path.  atvs_conv3d_bf16: tcgen05/TMEM implicit GEMM,
- * bf16 operands, fp32 accumulation; `wpacked` comes from atvs_pack_conv_weights_bf16.         */
+ * bf16 operands, fp32 accumulation; `wpacked` comes from atvs_pack_conv_weights_bf16.  The tensor
+ * path writes raw_out as raw_dtype = ATVS_F32 or ATVS_F16 (saturated; for layers whose raw output only
+ * feeds atvs_bn_relu_add*: the moments still come from the fp32 accumulators, the BN pass rounds to bf16
+ * right after, and the bytes written here and read there are halved).                              */
 int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int D, int H, int W, int Cin,
                      int Cout, int stride, int transposed, float* raw_out, double* stats,
                      atvs_stream_t stream);
@@ -93,7 +97,7 @@ size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed);
 int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed,
                                 void* wpacked, atvs_stream_t stream);
 int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                     int Cout, int stride, int transposed, float* raw_out, double* stats,
+                     int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
                      atvs_stream_t stream);
 /* same convolution plus a depth-invariant term: raw_out[b,z,y,x,:] += plane_bias[b,c(z),y,x,:] with
  * c(z) = 0 for the first output plane, 2 for the last, 1 otherwise; plane_bias (B,3,Ho,Wo,Cout) f32.
@@ -101,14 +105,15 @@ int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int 
  * reference half of the convolution is a 2-D result shared by all interior planes (computed once by
  * running this same primitive on a 3-plane (4 for stride 2) tile of the reference feature).         */
 int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                          int Cout, int stride, const float* plane_bias, float* raw_out, double* stats,
-                          atvs_stream_t stream);
+                          int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
+                          double* stats, atvs_stream_t stream);
 
 /* ---- batch-norm (batch statistics) + ReLU + skip adds ------ network.py:206-215, 541-550, 696
  * y = relu((raw - mean) * rsqrt(var + eps)) with mean/var from `stats` over `count` voxels
  * (biased variance); out_plain = y (may be NULL); out_sum = y + skip1 + skip2 (NULL skips are
- * omitted; may be NULL).  act_dtype is the dtype of skips and outputs.  n = count * C.          */
-int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int C, float eps,
+ * omitted; may be NULL).  act_dtype is the dtype of skips and outputs, raw_dtype (ATVS_F32 | ATVS_F16)
+ * that of the raw tensor(s).  n = count * C.                                                     */
+int atvs_bn_relu_add(const void* raw, int raw_dtype, const double* stats, long long count, int C, float eps,
                      int relu, const void* skip1, const void* skip2, void* out_plain,
                      void* out_sum, int act_dtype, atvs_stream_t stream);
 
@@ -116,8 +121,8 @@ int atvs_bn_relu_add(const float* raw, const double* stats, long long count, int
  * conv_b1_0_0 = add(conv_b0_6_0, conv_b0_0_1), cnn_wrapper/atvsnet.py:128-131):
  * out_sum = relu(bn(raw_a)) + relu(bn(raw_b)) + skip, each raw tensor with its own batch statistics;
  * out_plain_a = relu(bn(raw_a)) (may be NULL).  Saves writing and re-reading the normalised raw_b.  */
-int atvs_bn_relu_add_pair(const float* raw_a, const double* stats_a, const float* raw_b,
-                          const double* stats_b, long long count, int C, float eps, int relu,
+int atvs_bn_relu_add_pair(const void* raw_a, const double* stats_a, const void* raw_b,
+                          const double* stats_b, int raw_dtype, long long count, int C, float eps, int relu,
                           const void* skip, void* out_plain_a, void* out_sum, int act_dtype,
                           atvs_stream_t stream);
 

@@ -42,8 +42,9 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_prob2depth(p, 1, 8, 4, 4, p, p, 3, p, None, None) == -5          # up must be 1 or 4
     assert lib.atvs_build_cost_volume(p, p, p, None, 1, 8, 4, 4, 6, 0, 0, p, None) == -1  # F % 4
     assert lib.atvs_conv3d_fp32(p, p, 1, 2, 2, 2, 8, 5, 1, 0, p, None, None) == -5       # Cout
-    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, None, None) == -5      # Cin
-    assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, None, None) == -3      # odd D, stride 2
+    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, 0, None, None) == -5      # Cin
+    assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, 0, None, None) == -3      # odd D, stride 2
+    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 16, 8, 1, 0, p, 1, None, None) == -2   # raw dtype must be f32 | f16
     # per-tap TMA image + halo-ring images (stride 1, and stride 2 for Cin <= 32)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 36 * 2 * 96 * 16
     assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16 + 5 * 2 * 48 * 16

@@ -251,6 +251,50 @@ def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
+RAW16_CASES = [(8, 8, 1, 0, (1, 16, 64, 80)), (32, 8, 1, 0, (1, 16, 64, 80)), (8, 16, 1, 0, (1, 16, 64, 80)),
+               (16, 16, 1, 0, (1, 12, 24, 40)), (8, 16, 2, 0, (1, 64, 128, 160)), (32, 16, 2, 0, (1, 16, 64, 80)),
+               (16, 8, 2, 1, (1, 8, 32, 40)), (64, 32, 2, 1, (1, 4, 8, 12)), (64, 64, 1, 0, (1, 4, 8, 12)),
+               (8, 1, 1, 0, (1, 16, 64, 80))]
+
+
+@pytest.mark.parametrize('cin,cout,stride,transposed,shape', RAW16_CASES)
+def test_conv3d_bf16_raw_fp16(A, cin, cout, stride, transposed, shape):
+    """raw outputs stored as saturated fp16 (layers that only feed the BN pass): every tensor kernel (ring, stride-2
+    ring, per-tap TMA, fused deconv) against its own fp32 raw output; moments unchanged (fp32 accumulators); the BN
+    pass on the fp16 tensor equals the BN pass on the fp32 one to bf16 output rounding."""
+    from atvsnet_b200.network import conv3d_raw, bn_relu_add
+    x, w = _conv_case(cin, cout, stride, transposed, 11, shape=shape)
+    xb = torch.from_numpy(x).to(torch.bfloat16).cuda()
+    wb = torch.from_numpy(w).to(torch.bfloat16).float().cuda()
+    A.variables.packed_cache().clear()
+    r32, s32 = conv3d_raw(xb, 'r16_%d_%d' % (cin, cout), wb, cout, stride, bool(transposed), True)
+    r16, s16 = conv3d_raw(xb, 'r16_%d_%d' % (cin, cout), wb, cout, stride, bool(transposed), True, raw_dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert r16.dtype == torch.float16 and r16.shape == r32.shape
+    a, b = r32.cpu().numpy(), r16.float().cpu().numpy()
+    assert np.abs(a - b).max() <= 2.0 ** -11 * np.abs(a).max() + 1e-7         # one fp16 rounding
+    assert np.array_equal(a.astype(np.float16), r16.cpu().numpy())            # exactly round-to-nearest of the fp32 result
+    assert np.allclose(s32.cpu().numpy(), s16.cpu().numpy(), rtol=1e-6, atol=1e-3)
+    if cout % 4 == 0:
+        p32, _ = bn_relu_add(r32, s32, True, [], True, False, torch.bfloat16)
+        p16, _ = bn_relu_add(r16, s16, True, [], True, False, torch.bfloat16)
+        d = (p32.float() - p16.float()).abs()
+        assert float(d.max()) <= 2.0 ** -7 * max(1.0, float(p32.float().abs().max()))
+        assert float((d > 0).float().mean()) < 0.25
+
+
+def test_raw_fp16_saturates(A):
+    """values beyond the fp16 range are clamped to +-65504 (never inf), NaN stays NaN."""
+    from atvsnet_b200.network import conv3d_raw
+    x = torch.full((1, 8, 16, 16, 8), 300.0).to(torch.bfloat16).cuda()
+    w = torch.full((3, 3, 3, 8, 8), 2.0).cuda()
+    w[..., 1] = -2.0
+    A.variables.packed_cache().clear()
+    r16, _ = conv3d_raw(x, 'sat16', w, 8, 1, False, True, raw_dtype=torch.float16)
+    v = r16.float()
+    assert bool(torch.isfinite(v).all()) and float(v.max()) == 65504.0 and float(v.min()) == -65504.0
+
+
 S2_RING_CASES = [(8, 16, (1, 32, 128, 160)), (32, 16, (1, 16, 128, 192)), (16, 32, (2, 20, 144, 112)), (8, 8, (1, 12, 260, 196)),
                  (32, 64, (1, 8, 256, 160)), (16, 16, (1, 68, 132, 68))]
 
@@ -295,7 +339,15 @@ def test_conv3d_split_cost_volume(A, stride, shape):
     w = w.to(torch.bfloat16).float()
     A.variables.packed_cache().clear()
     stats = torch.zeros(128, dtype=torch.float64, device='cuda')
-    raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
+    A.FLAGS.raw_dtype = 'f32'
+    try:
+        raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
+    finally:
+        A.FLAGS.raw_dtype = 'f16'
+    # default storage of a raw output that feeds the BN pass: saturated fp16 = one rounding of the fp32 result
+    raw16, _ = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride,
+                            torch.zeros(128, dtype=torch.float64, device='cuda'))
+    assert raw16.dtype == torch.float16 and np.array_equal(npy(raw).astype(np.float16), raw16.cpu().numpy())
     full = np.concatenate([np.tile(ref.float().numpy()[:, None], (1, D, 1, 1, 1)), warped.float().numpy()], axis=-1)
     refo = onet.conv3d(full, w.numpy(), stride)
     assert raw.shape == refo.shape

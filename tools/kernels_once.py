@@ -33,7 +33,7 @@ def run():
     A.build_cost_volume(feats[:, 0], feats[:, 1], cams, D, ds, di, 0, 1, mode='concat', out_dtype=torch.float32)
     raws = []
     for i, (x, wt, cout, stride, tr) in enumerate(cs):
-        raws.append(conv3d_raw(x, 'once%d' % i, wt, cout, stride, tr, True))
+        raws.append(conv3d_raw(x, 'once%d' % i, wt, cout, stride, tr, True, raw_dtype=N.raw_dtype_for_bn(x)))
     raw, st = raws[1]
     N.bn_relu_add(raw, st, True, [], True, False, torch.bfloat16)
     N.bn_relu_add_pair(raw, st, N._PendingRaw(raws[0][0], raws[0][1], True), True, None, False, torch.bfloat16)
