@@ -30,7 +30,7 @@ _SIGS = {
     "atvs_attention_local_max": [_p, _i, _ll, _i, _i, _p, _p],
     "atvs_attention_partial": [_p, _p, _i, _ll, _i, _i, _p, _p, _p],
     "atvs_attention_finish": [_p, _ll, _i, _p, _p],
-    "atvs_attention_raw": [_p, _p, _i, _ll, _i, _i, _i, _p, _p, _p],
+    "atvs_attention_raw": [_p, _i, _p, _i, _ll, _i, _i, _i, _p, _p, _p],
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",

@@ -383,9 +383,9 @@ k_attention(const T* __restrict__ act, const T* __restrict__ x, int N, long long
 // 8->16 convolution per view ([W_unique | W_shared], network.py:313-344); the ReLU is applied while
 // loading, so the activations are never written back and re-read, and one thread owns 8 channels of a
 // voxel (16/32-byte loads).  Same three modes as k_attention.
-template <typename T, int MODE>
+template <typename T, typename ActT, int MODE>
 __global__ void __launch_bounds__(256)
-k_attention_raw(const float* __restrict__ act, const T* __restrict__ x, int N, long long V, int C,
+k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, long long V, int C,
                 const float* __restrict__ gmax, float* __restrict__ out) {
     const int G = C >> 3;
     const long long total = V * G;
@@ -400,10 +400,10 @@ k_attention_raw(const float* __restrict__ act, const T* __restrict__ x, int N, l
 #pragma unroll
         for (int n = 0; n < ATT_MAXN; ++n) {
             if (n < N) {
-                const float* ar = act + ((size_t)n * V + v) * (2 * C);
+                const ActT* ar = act + ((size_t)n * V + v) * (2 * C);
                 float4 u0, u1, s0, s1;
-                Vec8<float>::ld(ar + c0, u0, u1);
-                Vec8<float>::ld(ar + C + c0, s0, s1);
+                RawLd<ActT>::ld8(ar + c0, u0, u1);
+                RawLd<ActT>::ld8(ar + C + c0, s0, s1);
                 const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                 const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
@@ -645,8 +645,9 @@ extern "C" int atvs_attention_partial(const void* act, const void* x, int N, lon
     return launch_att<2>(act, x, N, V, C, dtype, gmax, num_den, (cudaStream_t)stream, "atvs_attention_partial");
 }
 
-extern "C" int atvs_attention_raw(const float* act_raw, const void* x, int N, long long V, int C, int x_dtype, int mode,
-                                  const float* gmax, float* out, atvs_stream_t stream) {
+extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void* x, int N, long long V, int C, int x_dtype,
+                                  int mode, const float* gmax, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(act_dtype == ATVS_F32 || act_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_attention_raw: act_dtype %d", act_dtype);
     ATVS_CHECK_ARG(act_raw && out && (mode == 1 || x) && (mode != 2 || gmax), ATVS_E_NULL, "atvs_attention_raw: NULL pointer");
     ATVS_CHECK_ARG(N > 0 && N <= ATT_MAXN && V > 0 && C > 0 && C % 8 == 0, ATVS_E_SHAPE, "atvs_attention_raw: N=%d V=%lld C=%d",
                    N, V, C);
@@ -655,7 +656,13 @@ extern "C" int atvs_attention_raw(const float* act_raw, const void* x, int N, lo
                    "atvs_attention_raw: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = grid_for(V * (C / 8), 256, 8);
-#define ATT_RAW(T, M) k_attention_raw<T, M><<<grid, 256, 0, st>>>(act_raw, (const T*)x, N, V, C, gmax, out)
+#define ATT_RAW(T, M)                                                                                         \
+    do {                                                                                                      \
+        if (act_dtype == ATVS_F16)                                                                            \
+            k_attention_raw<T, __half, M><<<grid, 256, 0, st>>>((const __half*)act_raw, (const T*)x, N, V, C, gmax, out); \
+        else                                                                                                  \
+            k_attention_raw<T, float, M><<<grid, 256, 0, st>>>((const float*)act_raw, (const T*)x, N, V, C, gmax, out);  \
+    } while (0)
     if (x_dtype == ATVS_F32 || mode == 1) {
         if (mode == 0) ATT_RAW(float, 0); else if (mode == 1) ATT_RAW(float, 1); else ATT_RAW(float, 2);
     } else if (x_dtype == ATVS_BF16) {

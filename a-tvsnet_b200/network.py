@@ -425,12 +425,13 @@ def _attention_weights(scope):
 
 def attention_activations_raw(views, scope):
     """network.py:282-351: per view the pair [conv(x,W_unique) | conv(x,W_shared)] as one 8->16
-    convolution, NOT yet activated: raw fp32 (N,V,16).  The ReLU is applied by the combine kernel."""
+    convolution, NOT yet activated: raw (N,V,16), fp16 on the tensor path (raw_dtype_for_bn) else fp32.
+    The ReLU is applied by the combine kernel."""
     key, w = _attention_weights(scope)
     c2 = w.shape[-1]
     B, D, H, W_, _ = views[0].shape
     nvox = views[0].numel() // views[0].shape[-1]
-    raw = torch.empty((len(views), nvox, c2), dtype=torch.float32, device=views[0].device)
+    raw = torch.empty((len(views), nvox, c2), dtype=raw_dtype_for_bn(views[0]), device=views[0].device)
     for n, x in enumerate(views):
         conv3d_raw(x, key + '/packed', w, c2, 1, False, False, out=raw[n].view(B, D, H, W_, c2))
     return raw
@@ -462,7 +463,7 @@ def attention_aggregation(cost_volumes, scope):
     out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
     if c % 8 == 0:
         raw = attention_activations_raw(views, scope)
-        L.call("atvs_attention_raw", L.ptr(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 0, None, L.ptr(out),
+        L.call("atvs_attention_raw", L.ptr(raw), _raw_code(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 0, None, L.ptr(out),
                L.stream())
     else:
         act = attention_activations(views, scope)

@@ -73,10 +73,10 @@ def aggregate(filtered_views, scope='attention_aggregate', group=None):
     raw = N.attention_activations_raw(views, scope)
     x = N.stack_views(views)
     lmax = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_raw", L.ptr(raw), None, len(views), nvox, c, L.dtype_code(x), 1, None, L.ptr(lmax), L.stream())
+    L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), None, len(views), nvox, c, L.dtype_code(x), 1, None, L.ptr(lmax), L.stream())
     dist.all_reduce(lmax, op=dist.ReduceOp.MAX, group=group)
     nd = torch.empty((nvox, 2 * c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_raw", L.ptr(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
+    L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
            L.stream())
     dist.all_reduce(nd, op=dist.ReduceOp.SUM, group=group)
     out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
