@@ -22,6 +22,9 @@ _SIGS = {
     "atvs_pack_conv_weights_bf16": [_p, _i, _i, _i, _p, _p],
     "atvs_conv3d_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "atvs_conv3d_bf16_bias": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
+    "atvs_conv3d_bf16_dual": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p],
+    "atvs_conv3d_bf16_dual_supported": [_i, _i, _i, _i, _i],
+    "atvs_pack_conv_weights_dual": [_p, _i, _p, _p],
     "atvs_bn_relu_add": [_p, _i, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
     "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
@@ -34,7 +37,7 @@ _SIGS = {
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
-                                "atvs_packed_weight_bytes", "atvs_launch_count"])
+                                "atvs_packed_weight_bytes", "atvs_dual_weight_bytes", "atvs_launch_count"])
 
 
 def lib_path():
@@ -59,6 +62,8 @@ def load():
         lib.atvs_packed_weight_bytes.argtypes = [_i, _i, _i]
         lib.atvs_packed_weight_bytes.restype = C.c_size_t
         lib.atvs_launch_count.restype = C.c_longlong
+        lib.atvs_dual_weight_bytes.argtypes = [_i]
+        lib.atvs_dual_weight_bytes.restype = C.c_size_t
         _lib = lib
     return _lib
 

@@ -383,6 +383,36 @@ extern "C" int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, in
     return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, raw_dtype, stats, stream);
 }
 
+extern "C" int atvs_conv3d_bf16_dual_supported(int B, int D, int H, int W, int Cin) {
+    return (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && ((D | H | W) & 1) == 0 && ring_applicable(B, D, H, W, 1, 0) ? 1 : 0;
+}
+
+extern "C" size_t atvs_dual_weight_bytes(int Cin) { return ring_dual_weight_bytes(Cin); }
+
+extern "C" int atvs_pack_conv_weights_dual(const float* kernel32, int Cin, void* wpacked, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(kernel32 && wpacked, ATVS_E_NULL, "atvs_pack_conv_weights_dual: NULL pointer");
+    ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP, "atvs_pack_conv_weights_dual: Cin=%d", Cin);
+    return ring_dual_pack(kernel32, Cin, wpacked, (cudaStream_t)stream);
+}
+
+extern "C" int atvs_conv3d_bf16_dual(const void* x_bf16, const void* wpacked32, int B, int D, int H, int W, int Cin,
+                                     const float* plane_bias1, const float* plane_bias2, void* raw_out1, void* raw_out2,
+                                     int raw_dtype, double* stats1, double* stats2, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x_bf16 && wpacked32 && raw_out1 && raw_out2, ATVS_E_NULL, "atvs_conv3d_bf16_dual: NULL pointer");
+    ATVS_CHECK_ARG(raw_dtype == ATVS_F32 || raw_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_conv3d_bf16_dual: raw_dtype %d", raw_dtype);
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16_dual: bad shape");
+    ATVS_CHECK_ARG(atvs_conv3d_bf16_dual_supported(B, D, H, W, Cin), ATVS_E_UNSUP,
+                   "atvs_conv3d_bf16_dual: needs Cin in {8,16,32,64}, even D,H,W and a ring-sized volume (got Cin=%d %dx%dx%d)",
+                   Cin, D, H, W);
+    ATVS_CHECK_ARG((((uintptr_t)x_bf16 | (uintptr_t)wpacked32 | (uintptr_t)plane_bias1 | (uintptr_t)plane_bias2) & 15) == 0 &&
+                       (((uintptr_t)raw_out1 | (uintptr_t)raw_out2) & 31) == 0,
+                   ATVS_E_SHAPE, "atvs_conv3d_bf16_dual: inputs must be 16-byte, outputs 32-byte aligned");
+    RingDual d;
+    d.out2 = raw_out2; d.stats2 = stats2; d.bias2 = plane_bias2;
+    return ring_conv(x_bf16, wpacked32, B, D, H, W, Cin, 8, (float*)raw_out1,
+                     raw_dtype == ATVS_F16, stats1, plane_bias1, (cudaStream_t)stream, &d);
+}
+
 static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
                            int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
                            double* stats, atvs_stream_t stream) {

@@ -92,12 +92,75 @@ def conv3d_split(cv, wkey, w, cout, stride, stats_buf):
     warped half.  Returns (raw fp32 (B,Do,ho,wo,Cout), moments)."""
     F = cv.ref.shape[-1]
     w_ref, w_warp = _split_weights(wkey, w, F)
+    bias = _split_bias(cv, wkey, w_ref, cout, stride)
+    return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias,
+                      raw_dtype=raw_dtype_for_bn(cv.warped))
+
+
+# fuse the two convolutions that open every U-Net block (8 ch stride 1 + 16 ch stride 2 on the same tensor) into
+# one pass over the input (atvs_conv3d_bf16_dual).  Correct (tests/test_gpu_parity.py::test_conv3d_dual_head) but
+# NOT faster on B200 as built: at cfg2 the fused launch takes 101 us (Cin 8) / 175 us (Cin 32) against 45 + 47 /
+# 97 + 85 us for the two separate kernels - the accumulator ring that fits two CTAs per SM is only 5 planes deep
+# and the 4 epilogue warps become the critical path (profiles/r01_dual_head_probe.txt).  Opt-in: ATVS_DUAL=1.
+DUAL_HEAD = __import__('os').environ.get('ATVS_DUAL') is not None
+
+
+def _split_bias(cv, wkey, w_ref, cout, stride):
+    """depth-invariant part of a first-layer convolution (the tiled reference half): 3 plane classes."""
     planes = 3 if stride == 1 else 4
     bias, _ = conv3d_raw(cv.ref_tiled(planes), wkey + '/ref', w_ref, cout, stride, False, False)
     if stride == 2:                      # planes (interior, last) -> classes (first == interior, interior, last)
         bias = torch.cat([bias[:, :1], bias[:, :1], bias[:, 1:2]], dim=1).contiguous()
-    return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias,
-                      raw_dtype=raw_dtype_for_bn(cv.warped))
+    return bias
+
+
+def dual_supported(x):
+    xin = x.warped if isinstance(x, SplitCostVolume) else x
+    if xin.dtype != torch.bfloat16:
+        return False
+    B, D, H, W, cin = xin.shape
+    return bool(L.load().atvs_conv3d_bf16_dual_supported(B, D, H, W, cin))
+
+
+def conv3d_dual(x, wkey1, w1, wkey2, w2, stats1, stats2):
+    """conv(x, w1) with 8 channels, stride 1 and conv(x, w2) with 16 channels, stride 2 in ONE pass over x (tensor or
+    SplitCostVolume).  Returns (raw1, stats1), (raw2, stats2); raw dtype = raw_dtype_for_bn."""
+    if w1.shape[-1] != 8 or w2.shape[-1] != 16:
+        raise ValueError("conv3d_dual: heads must have 8 and 16 output channels")
+    bias1 = bias2 = None
+    if isinstance(x, SplitCostVolume):
+        F = x.ref.shape[-1]
+        w1r, w1w = _split_weights(wkey1, w1, F)
+        w2r, w2w = _split_weights(wkey2, w2, F)
+        bias1 = _split_bias(x, wkey1, w1r, 8, 1)
+        bias2 = _split_bias(x, wkey2, w2r, 16, 2)
+        xin, wa, wb = x.warped, w1w, w2w
+    else:
+        xin, wa, wb = x, w1, w2
+    B, D, H, W, cin = xin.shape
+    cache = V.packed_cache()
+    ck = wkey1 + '|' + wkey2 + '/dual'
+    if ck not in cache:
+        cache[ck] = torch.cat([wa, wb, torch.zeros(wa.shape[:-1] + (8,), dtype=wa.dtype, device=wa.device)], dim=-1).contiguous()
+    if ck + '/packed' not in cache:
+        buf = torch.empty(L.load().atvs_dual_weight_bytes(cin), dtype=torch.uint8, device=xin.device)
+        L.call("atvs_pack_conv_weights_dual", L.ptr(cache[ck]), cin, L.ptr(buf), L.stream())
+        cache[ck + '/packed'] = buf
+    pk = cache[ck + '/packed']
+    rd = raw_dtype_for_bn(xin)
+    raw1 = torch.empty((B, D, H, W, 8), dtype=rd, device=xin.device)
+    raw2 = torch.empty((B, D // 2, H // 2, W // 2, 16), dtype=rd, device=xin.device)
+    s1, s2 = stats1[:16], stats2[:32]
+    prof = PROFILE is not None and PROFILE[0](wkey1)
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("atvs_conv3d_bf16_dual", L.ptr(xin), L.ptr(pk), B, D, H, W, cin, L.ptr(bias1), L.ptr(bias2), L.ptr(raw1),
+           L.ptr(raw2), _raw_code(raw1), L.ptr(s1), L.ptr(s2), L.stream())
+    if prof:
+        e1.record()
+        PROFILE[1].append((wkey1 + '+' + wkey2, e0, e1, raw1.numel() // 8, cin, 24))
+    return (raw1, s1), (raw2, s2)
 
 
 def raw_dtype_for_bn(x):
@@ -321,6 +384,7 @@ class Network(object):
                 nodes[name].value = v      # cast once
             return v
 
+        precomputed = {}     # conv_bn node -> (raw, stats) already produced by its partner's dual-head launch
         for name in order:
             node = nodes[name]
             if name in done:
@@ -329,7 +393,29 @@ class Network(object):
                 x = act_in(node.inputs[0])
                 transposed = node.kind == 'deconv_bn'
                 wname = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
-                if isinstance(x, SplitCostVolume):
+                partner = None
+                if DUAL_HEAD and not transposed and name not in precomputed and dual_supported(x):
+                    # the other convolution that opens this block: same input, (8 ch, stride 1) <-> (16 ch, stride 2)
+                    want = (8, 1) if (node.params['filters'], node.params['stride']) == (16, 2) else \
+                        ((16, 2) if (node.params['filters'], node.params['stride']) == (8, 1) else None)
+                    if want is not None:
+                        for other in consumers[node.inputs[0]]:
+                            on = nodes[other]
+                            if (other != name and other not in done and other not in precomputed and on.kind == 'conv_bn'
+                                    and on.inputs[0] == node.inputs[0]
+                                    and (on.params['filters'], on.params['stride']) == want):
+                                partner = other
+                                break
+                if name in precomputed:
+                    raw, stats = precomputed.pop(name)
+                elif partner is not None:
+                    n1, n2 = (name, partner) if node.params['stride'] == 1 else (partner, name)
+                    k1, k2 = n1 + '/conv3d/kernel', n2 + '/conv3d/kernel'
+                    r1, r2 = conv3d_dual(x, k1, V.get_variable(k1), k2, V.get_variable(k2), arena[arena_slot[n1]],
+                                         arena[arena_slot[n2]])
+                    raw, stats = r1 if n1 == name else r2
+                    precomputed[partner] = r2 if n1 == name else r1
+                elif isinstance(x, SplitCostVolume):
                     raw, stats = conv3d_split(x, wname, V.get_variable(wname), node.params['filters'],
                                               node.params['stride'], arena[arena_slot[name]])
                 else:

@@ -108,6 +108,21 @@ int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D,
                           int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
                           double* stats, atvs_stream_t stream);
 
+/* TWO convolutions of the same input in one pass over it (cnn_wrapper/atvsnet.py:104-114: every U-Net block starts
+ * with conv_b*_0_1 = 8 channels, stride 1 and conv_b*_1_0 = 16 channels, stride 2 on the same tensor).  The
+ * stride-2 head is evaluated densely next to the stride-1 head (its 16 columns ride in the same MMAs, whose cost
+ * is the fetch of the voxel tile, not N) and only the odd positions are kept: TF SAME on even extents pads
+ * (0,1), so out2[z',y',x'] is the dense result at (2z'+1, 2y'+1, 2x'+1).  wpacked32 = atvs_pack_conv_weights_dual
+ * (atvs_dual_weight_bytes(Cin) bytes) of the kernel [3,3,3,Cin,32] = [head-1 (8) | head-2 (16) | zeros (8)].  raw_out1 (B,D,H,W,8), raw_out2
+ * (B,D/2,H/2,W/2,16), both raw_dtype; stats1 (16 doubles) / stats2 (32 doubles) and the plane biases
+ * (B,3,H,W,8) / (B,3,H/2,W/2,16) f32 as for atvs_conv3d_bf16(_bias) or NULL.                      */
+size_t atvs_dual_weight_bytes(int Cin);
+int atvs_pack_conv_weights_dual(const float* kernel32, int Cin, void* wpacked, atvs_stream_t stream);
+int atvs_conv3d_bf16_dual_supported(int B, int D, int H, int W, int Cin);
+int atvs_conv3d_bf16_dual(const void* x_bf16, const void* wpacked32, int B, int D, int H, int W, int Cin,
+                          const float* plane_bias1, const float* plane_bias2, void* raw_out1, void* raw_out2,
+                          int raw_dtype, double* stats1, double* stats2, atvs_stream_t stream);
+
 /* ---- batch-norm (batch statistics) + ReLU + skip adds ------ network.py:206-215, 541-550, 696
  * y = relu((raw - mean) * rsqrt(var + eps)) with mean/var from `stats` over `count` voxels
  * (biased variance); out_plain = y (may be NULL); out_sum = y + skip1 + skip2 (NULL skips are

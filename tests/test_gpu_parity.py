@@ -359,6 +359,50 @@ def test_conv3d_split_cost_volume(A, stride, shape):
     assert rel_err(npy(raw), npy(raw2)) < 1e-5
 
 
+@pytest.mark.parametrize('cin,shape,split', [(8, (1, 16, 64, 80), False), (32, (1, 16, 64, 80), False), (16, (2, 12, 96, 64), False),
+                                             (32, (1, 18, 70, 90), True), (8, (1, 128, 128, 160), False)])
+def test_conv3d_dual_head(A, cin, shape, split):
+    """the two convolutions that open a U-Net block (8 ch stride 1 + 16 ch stride 2, same input) in one launch ==
+    the two separate launches: same fp32 accumulators up to summation order, same moments; also with the split
+    cost volume (plane-class biases on both heads)."""
+    from atvsnet_b200.network import SplitCostVolume, conv3d_split, conv3d_raw, conv3d_dual, dual_supported
+    rng = np.random.default_rng(21)
+    B, D, H, W = shape
+    ctot = 2 * cin if split else cin
+    x = torch.from_numpy(rng.standard_normal((B, D, H, W, cin)).astype(np.float32)).to(torch.bfloat16).cuda()
+    w1 = torch.from_numpy((rng.standard_normal((3, 3, 3, ctot, 8)) / np.sqrt(27 * ctot)).astype(np.float32)).to(torch.bfloat16).float().cuda()
+    w2 = torch.from_numpy((rng.standard_normal((3, 3, 3, ctot, 16)) / np.sqrt(27 * ctot)).astype(np.float32)).to(torch.bfloat16).float().cuda()
+    A.variables.packed_cache().clear()
+    A.FLAGS.raw_dtype = 'f32'
+    try:
+        if split:
+            ref = torch.from_numpy(rng.standard_normal((B, H, W, cin)).astype(np.float32)).cuda()
+            xin = SplitCostVolume(ref, x)
+        else:
+            xin = x
+        assert dual_supported(xin)
+        st = torch.zeros((4, 128), dtype=torch.float64, device='cuda')
+        (r1, s1), (r2, s2) = conv3d_dual(xin, 'dh1', w1, 'dh2', w2, st[0], st[1])
+        if split:
+            q1, t1 = conv3d_split(xin, 'dh1', w1, 8, 1, st[2])
+            q2, t2 = conv3d_split(xin, 'dh2', w2, 16, 2, st[3])
+        else:
+            q1, t1 = conv3d_raw(x, 'dh1', w1, 8, 1, False, True, st[2])
+            q2, t2 = conv3d_raw(x, 'dh2', w2, 16, 2, False, True, st[3])
+        torch.cuda.synchronize()
+    finally:
+        A.FLAGS.raw_dtype = 'f16'
+    assert r1.shape == q1.shape and r2.shape == q2.shape
+    assert rel_err(npy(r1), npy(q1)) < 2e-6 and rel_err(npy(r2), npy(q2)) < 2e-6
+    assert np.allclose(s1.cpu().numpy()[:16], t1.cpu().numpy()[:16], rtol=1e-5, atol=1e-2)
+    assert np.allclose(s2.cpu().numpy()[:32], t2.cpu().numpy()[:32], rtol=1e-5, atol=1e-2)
+    # default (fp16 raw) storage: exactly the rounding of the fp32 result
+    (h1, _), (h2, _) = conv3d_dual(xin, 'dh1', w1, 'dh2', w2, torch.zeros(128, dtype=torch.float64, device='cuda'),
+                                   torch.zeros(128, dtype=torch.float64, device='cuda'))
+    assert h1.dtype == torch.float16
+    assert np.array_equal(npy(r1).astype(np.float16), h1.cpu().numpy()) and np.array_equal(npy(r2).astype(np.float16), h2.cpu().numpy())
+
+
 def test_bn_relu_add_pair(A):
     """add of two freshly convolved layers, each with its own batch statistics, in one pass."""
     from oracle import network as onet
