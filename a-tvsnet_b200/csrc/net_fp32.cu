@@ -383,7 +383,7 @@ k_attention(const T* __restrict__ act, const T* __restrict__ x, int N, long long
 // 8->16 convolution per view ([W_unique | W_shared], network.py:313-344); the ReLU is applied while
 // loading, so the activations are never written back and re-read, and one thread owns 8 channels of a
 // voxel (16/32-byte loads).  Same three modes as k_attention.
-template <typename T, typename ActT, int MODE>
+template <typename T, typename ActT, int MODE, int NMAX>
 __global__ void __launch_bounds__(256)
 k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, long long V, int C,
                 const float* __restrict__ gmax, float* __restrict__ out) {
@@ -393,12 +393,12 @@ k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, lo
          idx += (long long)gridDim.x * blockDim.x) {
         const long long v = idx / G;
         const int c0 = (int)(idx % G) << 3;
-        float a[ATT_MAXN][8];
+        float a[NMAX][8];
         float S[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] = 0.f;
 #pragma unroll
-        for (int n = 0; n < ATT_MAXN; ++n) {
+        for (int n = 0; n < NMAX; ++n) {
             if (n < N) {
                 const ActT* ar = act + ((size_t)n * V + v) * (2 * C);
                 float4 u0, u1, s0, s1;
@@ -419,7 +419,7 @@ k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, lo
         for (int q = 0; q < 8; ++q) {
             float mm = -INFINITY;
 #pragma unroll
-            for (int n = 0; n < ATT_MAXN; ++n)
+            for (int n = 0; n < NMAX; ++n)
                 if (n < N) {
                     a[n][q] += S[q];
                     mm = fmaxf(mm, a[n][q]);
@@ -439,22 +439,30 @@ k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, lo
 #pragma unroll
         for (int q = 0; q < 8; ++q) { den[q] = 0.f; res[q] = 0.f; }
 #pragma unroll
-        for (int n = 0; n < ATT_MAXN; ++n)
+        for (int n = 0; n < NMAX; ++n)
             if (n < N) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    a[n][q] = expf(a[n][q] - m[q]);
+                    // bf16 activations: SFU exponential (the weights are rounded to 8 bits downstream anyway)
+                    a[n][q] = (sizeof(T) == 4) ? expf(a[n][q] - m[q]) : exp2f((a[n][q] - m[q]) * 1.4426950408889634f);
                     den[q] += a[n][q];
                 }
             }
+        float inv[8];
 #pragma unroll
-        for (int n = 0; n < ATT_MAXN; ++n)
+        for (int q = 0; q < 8; ++q) inv[q] = 1.0f / den[q];
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
             if (n < N) {
                 float4 x0, x1;
                 Vec8<T>::ld(x + ((size_t)n * V + v) * C + c0, x0, x1);
                 const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) res[q] += (MODE == 0 ? a[n][q] / den[q] : a[n][q]) * xx[q];
+                for (int q = 0; q < 8; ++q) {
+                    // fp32 path: the reference's e / sum, then * x (network.py:402-406); bf16 path: one reciprocal per channel
+                    const float sc = (MODE != 0) ? a[n][q] : ((sizeof(T) == 4) ? a[n][q] / den[q] : a[n][q] * inv[q]);
+                    res[q] += sc * xx[q];
+                }
             }
         if (MODE == 2) {
             Vec8<float>::st(out + v * (2 * C) + c0, make_float4(res[0], res[1], res[2], res[3]),
@@ -656,12 +664,18 @@ extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void
                    "atvs_attention_raw: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = grid_for(V * (C / 8), 256, 8);
-#define ATT_RAW(T, M)                                                                                         \
+#define ATT_RAW_N(T, M, NM)                                                                                   \
     do {                                                                                                      \
         if (act_dtype == ATVS_F16)                                                                            \
-            k_attention_raw<T, __half, M><<<grid, 256, 0, st>>>((const __half*)act_raw, (const T*)x, N, V, C, gmax, out); \
+            k_attention_raw<T, __half, M, NM><<<grid, 256, 0, st>>>((const __half*)act_raw, (const T*)x, N, V, C, gmax, out); \
         else                                                                                                  \
-            k_attention_raw<T, float, M><<<grid, 256, 0, st>>>((const float*)act_raw, (const T*)x, N, V, C, gmax, out);  \
+            k_attention_raw<T, float, M, NM><<<grid, 256, 0, st>>>((const float*)act_raw, (const T*)x, N, V, C, gmax, out);  \
+    } while (0)
+    // the per-view logits live in registers: instantiate for the view count (4 sources at cfg2) so that the
+    // kernel keeps its occupancy
+#define ATT_RAW(T, M)                                                                                         \
+    do {                                                                                                      \
+        if (N <= 2) ATT_RAW_N(T, M, 2); else if (N <= 4) ATT_RAW_N(T, M, 4); else ATT_RAW_N(T, M, ATT_MAXN);  \
     } while (0)
     if (x_dtype == ATVS_F32 || mode == 1) {
         if (mode == 0) ATT_RAW(float, 0); else if (mode == 1) ATT_RAW(float, 1); else ATT_RAW(float, 2);
@@ -672,6 +686,7 @@ extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void
         return ATVS_E_DTYPE;
     }
 #undef ATT_RAW
+#undef ATT_RAW_N
     ATVS_LAUNCH_CHECK();
     return 0;
 }

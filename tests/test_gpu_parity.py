@@ -569,6 +569,49 @@ def test_prob2depth(A, golden):
         assert (np.abs(npy(pu) - rpu) > 1e-5).mean() < 2e-3
 
 
+def test_full_size_properties_cfg2(A):
+    """BASELINE.json configs[1] sizes (D=128, 128x160 features), where the CPU oracle is too slow: size-independent
+    properties.  (a) impulse response of the halo-ring convolution = the (bf16) kernel, zero elsewhere; (b) the
+    BN pass leaves zero mean / unit variance per channel; (c) soft-argmin is invariant to a logit offset, returns
+    the plane depth for a one-hot volume, and the x4 variant agrees with the plain one at the shared corner pixels."""
+    from atvsnet_b200.network import conv3d_raw, bn_relu_add
+    D, H, W = 128, 128, 160
+    rng = np.random.default_rng(3)
+    # (a)
+    w = torch.from_numpy((rng.standard_normal((3, 3, 3, 8, 8)) * 0.2).astype(np.float32)).to(torch.bfloat16).float().cuda()
+    x = torch.zeros((1, D, H, W, 8), dtype=torch.bfloat16, device='cuda')
+    pz, py, px, pc = 77, 63, 95, 5
+    x[0, pz, py, px, pc] = 1.0
+    A.variables.packed_cache().clear()
+    raw, st = conv3d_raw(x, 'impulse', w, 8, 1, False, True)
+    got = raw[0, pz - 1:pz + 2, py - 1:py + 2, px - 1:px + 2].cpu().numpy()            # out[p + 1 - k] = w[k]
+    want = w[:, :, :, pc, :].cpu().numpy()[::-1, ::-1, ::-1]
+    assert np.array_equal(got, want)
+    assert abs(float(raw.double().sum()) - float(w[:, :, :, pc, :].double().sum())) < 1e-5
+    assert int((raw != 0).sum()) <= 27 * 8
+    assert np.allclose(st.cpu().numpy()[:8], w[:, :, :, pc, :].double().sum(dim=(0, 1, 2)).cpu().numpy(), atol=1e-6)
+    # (b)
+    xr = torch.randn((1, D, H, W, 8), device='cuda').to(torch.bfloat16)
+    raw, st = conv3d_raw(xr, 'impulse', w, 8, 1, False, True, raw_dtype=torch.float16)
+    y, _ = bn_relu_add(raw, st, False, [], True, False, torch.float32)
+    m, v = y.double().mean(dim=(0, 1, 2, 3)), y.double().var(dim=(0, 1, 2, 3), unbiased=False)
+    assert float(m.abs().max()) < 2e-3 and float((v - 1).abs().max()) < 5e-3
+    # (c)
+    vol = (torch.randn((1, D, H, W), device='cuda') * 3).contiguous()
+    ds, di = torch.tensor([0.05], device='cuda'), torch.tensor([0.0033], device='cuda')
+    e0, u0 = A.prob2depth_upsample(vol, D, ds, di)
+    e1, u1 = A.prob2depth_upsample(vol + 7.5, D, ds, di)
+    assert float((e0 - e1).abs().max()) < 1e-6 and float((u0 - u1).abs().max()) < 1e-6
+    assert float(e0.min()) >= 0.05 and float(e0.max()) <= 0.05 + 127 * 0.0033 + 1e-6
+    # align_corners x4: output corner pixels sit exactly on source corner pixels
+    assert abs(float(u0[0, 0, 0, 0]) - float(e0[0, 0, 0, 0])) < 2e-6
+    assert abs(float(u0[0, -1, -1, 0]) - float(e0[0, -1, -1, 0])) < 2e-5
+    hot = torch.full((1, D, H, W), 40.0, device='cuda')
+    hot[0, 31] = -40.0
+    eh, uh = A.prob2depth_upsample(hot, D, ds, di)
+    assert np.allclose(npy(eh), 0.05 + 31 * 0.0033, rtol=1e-6) and np.allclose(npy(uh), 0.05 + 31 * 0.0033, rtol=1e-6)
+
+
 # ------------------------------------------------------------------ end to end (stage I + II)
 def _e2e_inputs(A, D=16, h=16, w=24, nv=3, seed=3):
     cams = A.synthetic.orbit_cams(nv, h, w, D)[None]

@@ -26,6 +26,8 @@ def convs():
 
 
 cs = convs()
+A.variables.load_weights(A.variables.synthetic_weights())
+views4 = [torch.randn(1, D, h, w, 8, device='cuda').to(torch.bfloat16) for _ in range(4)]
 
 
 def run():
@@ -39,6 +41,7 @@ def run():
     N.bn_relu_add_pair(raw, st, N._PendingRaw(raws[0][0], raws[0][1], True), True, None, False, torch.bfloat16)
     A.prob2depth(vol, D, ds, di)
     A.prob2depth_upsample(vol, D, ds, di)
+    A.cost_volume_aggregation(views4, keepchannel=True)
 
 
 run()
