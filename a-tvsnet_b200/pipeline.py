@@ -59,10 +59,36 @@ def _side_streams(device, n):
     return _STREAMS[key]
 
 
-def aggregate(filtered_views, scope='attention_aggregate', group=None):
-    """AAM (network.py:379-408) over this rank's views; with ``group`` the softmax over views
-    is completed across ranks: all-reduce(max) of the local logit max, then all-reduce(sum) of
-    [numerator || denominator] (V,16) fp32."""
+def reduce_partials(nd, world, rank, group, finish, gather_dtype):
+    """Complete the view softmax across ranks from the local partials ``nd`` (V,2C) fp32 = [sum_n e^{l_n-m} x_n | sum_n
+    e^{l_n-m}]: reduce-scatter(SUM) so that every rank owns V/world voxels of the summed partials, ``finish`` (slab
+    (v,2C) -> (v,C) = num / den) on the owned slab, all-gather of the RESULT in ``gather_dtype``.  Against one
+    all-reduce of the partials this moves (2C*4 + C*s) instead of 2*2C*4 bytes per voxel over the links (40 vs 128 for
+    C = 8, bf16) and divides the finish work by ``world``.  Backends without reduce-scatter (gloo, CPU tests) take the
+    equivalent all-reduce + slice."""
+    import torch.distributed as dist
+    V, c2 = nd.shape
+    per = -(-V // world)
+    if per * world != V:                                   # pad to a multiple of world (tail rows are dropped again)
+        pad = torch.zeros((per * world, c2), dtype=nd.dtype, device=nd.device)
+        pad[:V] = nd
+        nd = pad
+    if dist.get_backend(group) == 'nccl':
+        slab = torch.empty((per, c2), dtype=nd.dtype, device=nd.device)
+        dist.reduce_scatter_tensor(slab, nd, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(nd, op=dist.ReduceOp.SUM, group=group)
+        slab = nd[rank * per:(rank + 1) * per].contiguous()
+    mine = finish(slab).to(gather_dtype).contiguous()
+    full = torch.empty((per * world, mine.shape[1]), dtype=gather_dtype, device=nd.device)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:V]
+
+
+def aggregate(filtered_views, scope='attention_aggregate', group=None, rank=0, world=1):
+    """AAM (network.py:379-408) over this rank's views; with ``group`` the softmax over views is completed across
+    ranks: all-reduce(MAX) of the local logit max (as bf16: any shift that is the same on every rank is exact for the
+    softmax), then reduce_partials() of [numerator || denominator] (V,16) fp32.  Sharded result: activation dtype."""
     if group is None:
         return N.attention_aggregation(filtered_views, scope)
     import torch.distributed as dist
@@ -74,13 +100,21 @@ def aggregate(filtered_views, scope='attention_aggregate', group=None):
     x = N.stack_views(views)
     lmax = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
     L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), None, len(views), nvox, c, L.dtype_code(x), 1, None, L.ptr(lmax), L.stream())
-    dist.all_reduce(lmax, op=dist.ReduceOp.MAX, group=group)
+    lmax16 = lmax.to(torch.bfloat16)
+    dist.all_reduce(lmax16, op=dist.ReduceOp.MAX, group=group)
+    lmax.copy_(lmax16)
+    del lmax16
     nd = torch.empty((nvox, 2 * c), dtype=torch.float32, device=x.device)
     L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
            L.stream())
-    dist.all_reduce(nd, op=dist.ReduceOp.SUM, group=group)
-    out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_finish", L.ptr(nd), nvox, c, L.ptr(out), L.stream())
+    del raw, lmax
+
+    def finish(slab):
+        out = torch.empty((slab.shape[0], c), dtype=torch.float32, device=slab.device)
+        L.call("atvs_attention_finish", L.ptr(slab), slab.shape[0], c, L.ptr(out), L.stream())
+        return out
+
+    out = reduce_partials(nd, world, rank, group, finish, x.dtype)
     return out.reshape(shape)
 
 
@@ -128,7 +162,7 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
             main.wait_stream(st)
     filtered = [results[(v, 'f')][0] for v in mine]
     depth_views = [results[(v, 'r')] for v in mine] if siamese else [None for _ in mine]
-    cost_agg = aggregate(filtered, 'attention_aggregate', group)
+    cost_agg = aggregate(filtered, 'attention_aggregate', group, rank, world)
     prob_agg = OutputConv({'data': cost_agg}).get_output().squeeze(-1)
     depth, _ = _prob2depth(prob_agg, ds, di, 1, False)
     out = dict(depth=depth, prob_volume_agg=prob_agg, cost_volume_agg=cost_agg, depth_views=depth_views)

@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II "
                                "+ x4 soft-argmin; FEM and refinement not included" % (workload, nv - 1, W, H, h, w, D),
                    "frames_per_step": maps_per_step,
-                   "parallelism": ("source views sharded over %d ranks, NCCL max+sum all-reduce" % world) if sharded
+                   "parallelism": ("source views sharded over %d ranks; NCCL all-reduce(max, bf16) + reduce-scatter(sum, fp32) + all-gather(result)" % world) if sharded
                    else ("dp%d: independent frames per rank, no collective" % world),
                    "l2": "no explicit flush: every step streams > 3 GB of intermediate volumes (L2 = 126 MB)",
                    "cuda_graph": graph is not None,
@@ -442,6 +442,8 @@ def main():
         import torch
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         os.environ.setdefault('MASTER_PORT', '29511')
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))

@@ -96,8 +96,20 @@ def _gloo_worker(rank, world, port, q):
     num = sum(ei * torch.from_numpy(xs[..., n]) for ei, n in zip(e, mine))
     den = sum(e)
     nd = torch.cat([num, den], dim=-1)
-    dist.all_reduce(nd, op=dist.ReduceOp.SUM)
-    out = (nd[..., :8] / nd[..., 8:]).numpy()
+    # the product's exchange step (pipeline.reduce_partials): reduce-scatter (all-reduce + slice on gloo), finish on the
+    # owned slab, all-gather of the result; 4*6*6 = 144 voxels and a ragged 143-voxel case (padding path)
+    flat = nd.reshape(-1, 16)
+    fin = lambda s_: s_[:, :8] / s_[:, 8:]
+    out = A.pipeline.reduce_partials(flat.clone(), world, rank, None, fin, torch.float32).reshape(1, 4, 6, 6, 8).numpy()
+    ragged = A.pipeline.reduce_partials(flat[:143].clone(), world, rank, None, fin, torch.float32).numpy()
+    assert np.array_equal(ragged, out.reshape(-1, 8)[:143])
+    # a bf16-rounded shift that is the same on every rank is as good as the exact max
+    l16 = torch.stack(l).max(dim=0).values.to(torch.bfloat16)
+    dist.all_reduce(l16, op=dist.ReduceOp.MAX)
+    e2 = [torch.exp(v - l16.float()) for v in l]
+    nd2 = torch.cat([sum(ei * torch.from_numpy(xs[..., n]) for ei, n in zip(e2, mine)), sum(e2)], dim=-1).reshape(-1, 16)
+    out2 = A.pipeline.reduce_partials(nd2, world, rank, None, fin, torch.float32).reshape(1, 4, 6, 6, 8).numpy()
+    assert np.abs(out2 - out).max() < 1e-5 * np.abs(out).max()
     if rank == 0:
         ref = onet.AttAggregation_keepchannel({'data': xs}, w).get_output()
         q.put(float(np.abs(out - ref).max() / np.abs(ref).max()))
