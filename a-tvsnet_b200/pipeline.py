@@ -169,3 +169,89 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     if upsample:
         out['depth_up'], _ = _prob2depth(prob_agg, ds, di, 4, False)
     return out
+
+
+class FrameStream(object):
+    """Depth maps for a stream of frames that live in PINNED HOST memory (what a reader thread hands over): the step is
+    captured once as a CUDA graph over fixed device buffers, and the host->device copy of frame i+1 and the
+    device->host copy of depth map i-1 run on their own streams while frame i computes (double-buffered staging).
+
+        fs = FrameStream(feats_shape, cams_shape, depth_num, device)
+        for depth_h in fs.run(frames):      # frames: iterable of (feats_pinned, cams_pinned)
+            ...                              # depth_h: pinned (B,4h,4w,1) fp32, valid until two frames later
+    """
+
+    def __init__(self, feats_shape, cams_shape, depth_num, device, siamese=True):
+        self.device = torch.device(device)
+        self.depth_num = int(depth_num)
+        dev = self.device
+        self.feats = torch.zeros(feats_shape, dtype=torch.float32, device=dev)
+        self.cams = torch.zeros(cams_shape, dtype=torch.float32, device=dev)
+        self.stage_f = [torch.empty_like(self.feats) for _ in range(2)]
+        self.stage_c = [torch.empty_like(self.cams) for _ in range(2)]
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.siamese = siamese
+        self.graph = None
+        self.out = None
+
+    def _capture(self):
+        for _ in range(3):      # eager warm-up: packs the weights, sets kernel attributes, fills the allocator
+            run_multiview(self.feats, self.cams, self.depth_num, siamese=self.siamese)
+        torch.cuda.synchronize(self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=s):
+                self.out = run_multiview(self.feats, self.cams, self.depth_num, siamese=self.siamese)['depth_up']
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.stage_o = [torch.empty_like(self.out) for _ in range(2)]
+        self.host_o = [torch.empty(self.out.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def run(self, frames):
+        """generator over pinned host depth maps, one per frame, in order (each is yielded once its copy is complete)."""
+        main = torch.cuda.current_stream(self.device)
+        first = True
+        free = [None, None]          # staging slot reusable once the step that read it has copied it out
+        done = [None, None]          # D2H of slot complete
+        pending = []
+        for i, (fh, ch) in enumerate(frames):
+            k = i & 1
+            if first:
+                # the graph is captured on real data of the first frame (BN statistics of zeros would be degenerate)
+                self.feats.copy_(fh, non_blocking=True)
+                self.cams.copy_(ch, non_blocking=True)
+                if self.graph is None:
+                    self._capture()
+                first = False
+            with torch.cuda.stream(self.s_in):
+                if free[k] is not None:
+                    self.s_in.wait_event(free[k])
+                self.stage_f[k].copy_(fh, non_blocking=True)
+                self.stage_c[k].copy_(ch, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.s_in)
+            main.wait_event(ready)
+            self.feats.copy_(self.stage_f[k], non_blocking=True)
+            self.cams.copy_(self.stage_c[k], non_blocking=True)
+            free[k] = torch.cuda.Event()
+            free[k].record(main)
+            self.graph.replay()
+            if done[k] is not None:
+                main.wait_event(done[k])          # stage_o[k] / host_o[k] of frame i-2 have been drained
+            self.stage_o[k].copy_(self.out, non_blocking=True)
+            computed = torch.cuda.Event()
+            computed.record(main)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(computed)
+                self.host_o[k].copy_(self.stage_o[k], non_blocking=True)
+                done[k] = torch.cuda.Event()
+                done[k].record(self.s_out)
+            pending.append((done[k], self.host_o[k]))
+            if len(pending) > 1:
+                ev, buf = pending.pop(0)
+                ev.synchronize()
+                yield buf
+        for ev, buf in pending:
+            ev.synchronize()
+            yield buf

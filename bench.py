@@ -221,14 +221,25 @@ def run_ours(args, rank, world, local_rank):
     ms_total = e0.elapsed_time(e1)
 
     # ---------------- timed region 2: end to end from / to pinned host memory ----------------
+    # the public streaming call (pipeline.FrameStream): frames arrive in pinned host memory, every step copies its
+    # inputs H2D and its depth map D2H; the copies of neighbouring frames overlap the step on their own streams
+    fstream = None
+    if graph is not None:
+        fstream = A.pipeline.FrameStream(tuple(feats_h.shape), tuple(cams_h.shape), D, dev, siamese=True)
+        for dm in fstream.run([(feats_h, cams_h)] * 3):
+            pass
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        feats_d.copy_(feats_h, non_blocking=True)
-        cams_d.copy_(cams_h, non_blocking=True)
-        res = run_step()
-        depth_h.copy_(res, non_blocking=True)
+    if fstream is not None:
+        for dm in fstream.run((feats_h, cams_h) for _ in range(args.steps)):
+            depth_h = dm
+    else:
+        for _ in range(args.steps):
+            feats_d.copy_(feats_h, non_blocking=True)
+            cams_d.copy_(cams_h, non_blocking=True)
+            res = run_step()
+            depth_h.copy_(res, non_blocking=True)
     f1.record()
     barrier()
     clocks = sampler.stop()
@@ -299,7 +310,10 @@ def run_ours(args, rank, world, local_rank):
                    "tensor_flops_per_step": flops_step,
                    "tensor_tflops_whole_step": flops_step * maps_per_step * args.steps / (ms_total * 1e-3) / 1e12 / world},
         "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "pipeline.FrameStream.run (pinned host frames in, pinned host depth maps out; copies of "
+                       "neighbouring frames overlap the step)" if fstream is not None else
+                       "pipeline.run_multiview bracketed by the H2D / D2H copies on one stream"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
