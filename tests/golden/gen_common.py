@@ -39,3 +39,24 @@ def smooth(rng, shape, passes=2):
         for ax in range(1, len(shape) - 1):
             x = (np.roll(x, 1, ax) + x + np.roll(x, -1, ax)) / np.float32(3)
     return (x / x.std()).astype(np.float32)
+
+
+def fem_variable_shapes():
+    """name -> shape of every variable the reference's ResNetDS2SPP graph asks for (written by make_golden_fem.py
+    from the reference code itself)."""
+    import json
+    import os
+    return {k: tuple(v) for k, v in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                 'fem_variables.json'))).items()}
+
+
+def fem_weights(seed=7):
+    """seeded FEM weights under the checkpoint's names: He-normal kernels, small biases / betas."""
+    w = {}
+    for i, (name, shape) in enumerate(sorted(fem_variable_shapes().items())):
+        rng = np.random.default_rng([seed, i])
+        if len(shape) == 4:
+            w[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / np.prod(shape[:-1]))).astype(np.float32)
+        else:
+            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+    return w

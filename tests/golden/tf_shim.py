@@ -349,3 +349,141 @@ def install(flags=None):
     sys.modules['tensorflow'] = tf
     sys.modules['tensorflow.contrib'] = contrib
     return tf
+
+
+# ------------------------------------------------------------------ 2-D primitives (FEM ResNetDS2SPP: cnn_wrapper/atvsnet.py:254-292,
+# network.py:552-616, 650-671).  NumPy einsum / slicing, independent of the torch-CPU oracle.
+AUTO_VARS = None      # when a dict: variables the graph asks for and that were not provided are CREATED (seeded) and
+                      # recorded as name -> shape, so that the variable list itself comes from the reference's code
+
+
+def _var2(name, shape, kind):
+    full = '/'.join(_SCOPE + [name])
+    if full not in VARIABLES and AUTO_VARS is not None:
+        rng = np.random.default_rng(__import__("zlib").crc32(full.encode()))
+        shape = tuple(int(v) for v in shape)
+        if kind == 'kernel':
+            fan_in = int(np.prod(shape[:-1]))
+            VARIABLES[full] = (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(F32)
+        else:
+            VARIABLES[full] = (rng.standard_normal(shape) * 0.1).astype(F32)
+        AUTO_VARS[full] = shape
+    return _var(name, shape)
+
+
+def _conv2d(x, w, stride, rate, pads):
+    """x (B,H,W,Ci), w [kh,kw,Ci,Co], explicit pads ((top,bottom),(left,right)), dilation `rate`."""
+    x, w = np.asarray(x, F32), np.asarray(w, F32)
+    B, H, W, Ci = x.shape
+    kh, kw = w.shape[0], w.shape[1]
+    xp = np.pad(x, ((0, 0), pads[0], pads[1], (0, 0)))
+    Hp, Wp = xp.shape[1], xp.shape[2]
+    Ho = (Hp - (kh - 1) * rate - 1) // stride + 1
+    Wo = (Wp - (kw - 1) * rate - 1) // stride + 1
+    out = np.zeros((B, Ho, Wo, w.shape[-1]), F32)
+    for a in range(kh):
+        for b in range(kw):
+            sl = xp[:, a * rate:a * rate + (Ho - 1) * stride + 1:stride, b * rate:b * rate + (Wo - 1) * stride + 1:stride, :]
+            out += np.einsum('bhwi,io->bhwo', sl, w[a, b], optimize=False).astype(F32)
+    return _t(out)
+
+
+def _same_pads2d(H, W, kh, kw, stride, rate):
+    keh, kew = (kh - 1) * rate + 1, (kw - 1) * rate + 1
+    ph, pw = _same_pad(H, keh, stride), _same_pad(W, kew, stride)
+    return (ph[0], ph[1]), (pw[0], pw[1])
+
+
+def _pair(v):
+    return (int(v[0]), int(v[1])) if isinstance(v, (list, tuple)) else (int(v), int(v))
+
+
+def _layers_conv2d(inputs, filters, kernel_size, strides=1, activation=None, use_bias=False, padding='SAME',
+                   trainable=True, reuse=None, name=None, kernel_initializer=None, dilation_rate=1):
+    kh, kw = _pair(kernel_size)
+    s = _pair(strides)[0]
+    r = _pair(dilation_rate)[0]
+    with _Ctx(name or 'conv2d', push=True):
+        w = _var2('kernel', (kh, kw, inputs.shape[-1], filters), 'kernel')
+        b = _var2('bias', (filters,), 'bias') if use_bias else None
+    pads = _same_pads2d(inputs.shape[1], inputs.shape[2], kh, kw, s, r) if padding == 'SAME' else ((0, 0), (0, 0))
+    y = _conv2d(inputs, w, s, r, pads)
+    if b is not None:
+        y = _t(np.asarray(y) + np.asarray(b))
+    return activation(y) if activation else y
+
+
+def _slim_conv2d(inputs, num_outputs, kernel_size, stride=1, padding='SAME', rate=1, activation_fn='relu',
+                 normalizer_fn=None, reuse=None, trainable=True, weights_initializer=None, scope=None, **kw):
+    assert normalizer_fn is None
+    kh, kw_ = _pair(kernel_size)
+    with _Ctx(scope or 'Conv', push=True):
+        w = _var2('weights', (kh, kw_, inputs.shape[-1], num_outputs), 'kernel')
+        b = _var2('biases', (num_outputs,), 'bias')
+    pads = _same_pads2d(inputs.shape[1], inputs.shape[2], kh, kw_, stride, rate) if padding == 'SAME' else ((0, 0), (0, 0))
+    y = np.asarray(_conv2d(inputs, w, stride, rate, pads)) + np.asarray(b)
+    if activation_fn == 'relu':                       # slim.conv2d's default activation_fn is tf.nn.relu
+        y = np.maximum(y, F32(0))
+    elif activation_fn is not None:
+        y = np.asarray(activation_fn(_t(y)))
+    return _t(y.astype(F32))
+
+
+def _slim_batch_norm(inputs, activation_fn=None, scope=None, reuse=None, trainable=True, decay=0.999, center=True,
+                     scale=False, epsilon=0.001, is_training=True, **kw):
+    """slim.batch_norm defaults: center=True, scale=False, epsilon=1e-3, is_training=True (batch statistics)."""
+    assert is_training and center and not scale
+    x = np.asarray(inputs, F32)
+    axes = tuple(range(x.ndim - 1))
+    mean = x.mean(axis=axes, dtype=F32)
+    var = np.mean(np.square(x - mean), axis=axes, dtype=F32)
+    inv = (F32(1) / np.sqrt(var + F32(epsilon))).astype(F32)
+    with _Ctx(scope or 'BatchNorm', push=True):
+        beta = np.asarray(_var2('beta', (x.shape[-1],), 'bias'))
+    y = x * inv - mean * inv + beta
+    if activation_fn is not None:
+        y = np.asarray(activation_fn(_t(y)))
+    return _t(y.astype(F32))
+
+
+def _slim_max_pool2d(inputs, kernel_size, stride=2, padding='VALID', scope=None):
+    kh, kw = _pair(kernel_size)
+    assert (kh, kw) == (1, 1) and padding == 'VALID'          # the only use: shortcut subsampling (network.py:576)
+    return _t(np.asarray(inputs)[:, ::stride, ::stride, :])
+
+
+def _avg_pool2d_same(inputs, pool_size, strides, padding='SAME', name=None):
+    """tf.layers.average_pooling2d, SAME: windows are clipped to the image and averaged over the VALID elements."""
+    assert padding == 'SAME'
+    x = np.asarray(inputs, F32)
+    B, H, W, C = x.shape
+    k, s = _pair(pool_size)[0], _pair(strides)[0]
+    (pt, pb, Ho), (pl, pr, Wo) = _same_pad(H, k, s), _same_pad(W, k, s)
+    out = np.zeros((B, Ho, Wo, C), F32)
+    for i in range(Ho):
+        y0, y1 = max(i * s - pt, 0), min(i * s - pt + k, H)
+        for j in range(Wo):
+            x0, x1 = max(j * s - pl, 0), min(j * s - pl + k, W)
+            out[:, i, j, :] = x[:, y0:y1, x0:x1, :].sum(axis=(1, 2), dtype=F32) / F32((y1 - y0) * (x1 - x0))
+    return _t(out)
+
+
+def install_2d(tf):
+    """add the 2-D layer set to a module tree made by install()."""
+    tf.pad = lambda x, paddings, **k: _t(np.pad(np.asarray(x), [(int(a), int(b)) for a, b in paddings]))
+    tf.layers.conv2d = _layers_conv2d
+    tf.layers.average_pooling2d = _avg_pool2d_same
+    relu = tf.nn.relu
+    slim = tf.contrib.slim
+
+    def conv2d(*a, **k):
+        if 'activation_fn' not in k:
+            k['activation_fn'] = 'relu'
+        elif k['activation_fn'] is relu:
+            k['activation_fn'] = 'relu'
+        return _slim_conv2d(*a, **k)
+    slim.conv2d = conv2d
+    slim.batch_norm = _slim_batch_norm
+    slim.max_pool2d = _slim_max_pool2d
+    slim.utils = types.SimpleNamespace(last_dimension=lambda shape, min_rank=1: int(shape[-1]))
+    return tf
