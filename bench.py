@@ -412,13 +412,13 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
 
 def cpu_baseline(workload):
     """the oracle port timed on the host cores on a bounded sample: the whole stage I (siamese) + II schedule of the
-    workload (all source views, attention aggregation, output conv, soft-argmin) on the first D/4 depth planes."""
+    workload (all source views, attention aggregation, output conv, soft-argmin) on the first D/2 depth planes."""
     import torch
     import atvsnet_b200 as A
     from oracle import model as om
     feats, cams, D = make_inputs(workload, 0)
     nv = cams.shape[1]
-    Ds = max(8, D // 4)
+    Ds = max(8, D // 2)
     weights = A.variables.synthetic_weights()
     ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
     om.TVSNet_base(feats[:, :2, :16, :16], cams, 8, ds, di, 1, weights)          # touch the code paths
