@@ -106,7 +106,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
     const int R = p.nring;
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
-            mbar_init(&full[s], S2_PRODUCERS);
+            mbar_init(&full[s], S2_PRODUCERS / 32);      // one arrival per producer WARP (lane 0, after __syncwarp)
             mbar_init(&empty[s], 1);
         }
         for (int g = 0; g < G; ++g) {
@@ -154,8 +154,11 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
             else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // every lane's copies have landed and are visible to the async proxy; one release-arrive per warp
+            // (128 per-thread arrivals on one mbarrier cost more than the plane's cp.async issue)
+            __syncwarp();
             for (; pending > (uint32_t)keep; --pending) {
-                mbar_arrive(&full[pslot]);
+                if ((threadIdx.x & 31) == 0) mbar_arrive(&full[pslot]);
                 if (++pslot == (uint32_t)R) pslot = 0;
             }
         };
