@@ -383,9 +383,14 @@ k_attention(const T* __restrict__ act, const T* __restrict__ x, int N, long long
 // 8->16 convolution per view ([W_unique | W_shared], network.py:313-344); the ReLU is applied while
 // loading, so the activations are never written back and re-read, and one thread owns 8 channels of a
 // voxel (16/32-byte loads).  Same three modes as k_attention.
+// the N per-view cost volumes (V,C) by pointer: the views stay where stage I wrote them (no stacking copy)
+struct AttViews {
+    const void* p[ATT_MAXN];
+};
+
 template <typename T, typename ActT, int MODE, int NMAX>
 __global__ void __launch_bounds__(256)
-k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, long long V, int C,
+k_attention_raw(const ActT* __restrict__ act, const AttViews xs, int N, long long V, int C,
                 const float* __restrict__ gmax, float* __restrict__ out) {
     const int G = C >> 3;
     const long long total = V * G;
@@ -455,7 +460,7 @@ k_attention_raw(const ActT* __restrict__ act, const T* __restrict__ x, int N, lo
         for (int n = 0; n < NMAX; ++n)
             if (n < N) {
                 float4 x0, x1;
-                Vec8<T>::ld(x + ((size_t)n * V + v) * C + c0, x0, x1);
+                Vec8<T>::ld(reinterpret_cast<const T*>(xs.p[n]) + (size_t)v * C + c0, x0, x1);
                 const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -653,23 +658,31 @@ extern "C" int atvs_attention_partial(const void* act, const void* x, int N, lon
     return launch_att<2>(act, x, N, V, C, dtype, gmax, num_den, (cudaStream_t)stream, "atvs_attention_partial");
 }
 
-extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void* x, int N, long long V, int C, int x_dtype,
-                                  int mode, const float* gmax, float* out, atvs_stream_t stream) {
+extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void* const* x_views, int N, long long V, int C,
+                                  int x_dtype, int mode, const float* gmax, float* out, atvs_stream_t stream) {
     ATVS_CHECK_ARG(act_dtype == ATVS_F32 || act_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_attention_raw: act_dtype %d", act_dtype);
-    ATVS_CHECK_ARG(act_raw && out && (mode == 1 || x) && (mode != 2 || gmax), ATVS_E_NULL, "atvs_attention_raw: NULL pointer");
+    ATVS_CHECK_ARG(act_raw && out && (mode == 1 || x_views) && (mode != 2 || gmax), ATVS_E_NULL, "atvs_attention_raw: NULL pointer");
     ATVS_CHECK_ARG(N > 0 && N <= ATT_MAXN && V > 0 && C > 0 && C % 8 == 0, ATVS_E_SHAPE, "atvs_attention_raw: N=%d V=%lld C=%d",
                    N, V, C);
     ATVS_CHECK_ARG(mode >= 0 && mode <= 2, ATVS_E_UNSUP, "atvs_attention_raw: mode %d", mode);
-    ATVS_CHECK_ARG((((uintptr_t)act_raw | (uintptr_t)x | (uintptr_t)gmax | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+    ATVS_CHECK_ARG((((uintptr_t)act_raw | (uintptr_t)gmax | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
                    "atvs_attention_raw: buffers must be 16-byte aligned");
+    AttViews xs;
+    for (int n = 0; n < ATT_MAXN; ++n) xs.p[n] = nullptr;
+    if (mode != 1)
+        for (int n = 0; n < N; ++n) {
+            ATVS_CHECK_ARG(x_views[n] && ((uintptr_t)x_views[n] & 15) == 0, ATVS_E_NULL,
+                           "atvs_attention_raw: view %d is NULL or not 16-byte aligned", n);
+            xs.p[n] = x_views[n];
+        }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = grid_for(V * (C / 8), 256, 8);
 #define ATT_RAW_N(T, M, NM)                                                                                   \
     do {                                                                                                      \
         if (act_dtype == ATVS_F16)                                                                            \
-            k_attention_raw<T, __half, M, NM><<<grid, 256, 0, st>>>((const __half*)act_raw, (const T*)x, N, V, C, gmax, out); \
+            k_attention_raw<T, __half, M, NM><<<grid, 256, 0, st>>>((const __half*)act_raw, xs, N, V, C, gmax, out);       \
         else                                                                                                  \
-            k_attention_raw<T, float, M, NM><<<grid, 256, 0, st>>>((const float*)act_raw, (const T*)x, N, V, C, gmax, out);  \
+            k_attention_raw<T, float, M, NM><<<grid, 256, 0, st>>>((const float*)act_raw, xs, N, V, C, gmax, out);         \
     } while (0)
     // the per-view logits live in registers: instantiate for the view count (4 sources at cfg2) so that the
     // kernel keeps its occupancy

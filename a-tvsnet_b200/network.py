@@ -509,18 +509,39 @@ def _attention_weights(scope):
     return key, cache[key]
 
 
+def attention_raw_alloc(n_views, like, device=None):
+    """raw logits buffer (N,V,16) for n_views volumes shaped (and typed) like ``like`` (B,D,H,W,C)."""
+    c = like.shape[-1]
+    nvox = like.numel() // c
+    return torch.empty((n_views, nvox, 2 * c), dtype=raw_dtype_for_bn(like), device=device or like.device)
+
+
+def attention_raw_view(raw, n, x, scope):
+    """network.py:313-344 for ONE view: the pair [conv(x,W_unique) | conv(x,W_shared)] as one 8->16 convolution into
+    raw[n], NOT yet activated (the ReLU is applied by the combine kernel).  Independent per view, so the stage-I
+    stream of a view can run it right behind that view's regularisation pass."""
+    key, w = _attention_weights(scope)
+    B, D, H, W_, _ = x.shape
+    conv3d_raw(x, key + '/packed', w, w.shape[-1], 1, False, False, out=raw[n].view(B, D, H, W_, w.shape[-1]))
+
+
 def attention_activations_raw(views, scope):
     """network.py:282-351: per view the pair [conv(x,W_unique) | conv(x,W_shared)] as one 8->16
     convolution, NOT yet activated: raw (N,V,16), fp16 on the tensor path (raw_dtype_for_bn) else fp32.
     The ReLU is applied by the combine kernel."""
-    key, w = _attention_weights(scope)
-    c2 = w.shape[-1]
-    B, D, H, W_, _ = views[0].shape
-    nvox = views[0].numel() // views[0].shape[-1]
-    raw = torch.empty((len(views), nvox, c2), dtype=raw_dtype_for_bn(views[0]), device=views[0].device)
+    raw = attention_raw_alloc(len(views), views[0])
     for n, x in enumerate(views):
-        conv3d_raw(x, key + '/packed', w, c2, 1, False, False, out=raw[n].view(B, D, H, W_, c2))
+        attention_raw_view(raw, n, x, scope)
     return raw
+
+
+def view_pointers(views):
+    """HOST array of the N per-view device pointers (atvs_attention_raw reads the views where they are)."""
+    import ctypes
+    for v in views:
+        if not v.is_contiguous() or v.dtype != views[0].dtype:
+            raise RuntimeError("attention views must be contiguous and of one dtype")
+    return (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
 
 
 def attention_activations(views, scope):
@@ -539,19 +560,20 @@ def stack_views(views):
     return torch.stack([v.reshape(nvox, c) for v in views], dim=0) if len(views) > 1 else views[0].reshape(1, nvox, c)
 
 
-def attention_aggregation(cost_volumes, scope):
-    """network.py:379-408 -> (B,D,H,W,C) fp32."""
+def attention_aggregation(cost_volumes, scope, raw=None):
+    """network.py:379-408 -> (B,D,H,W,C) fp32.  ``raw``: logits already produced by attention_raw_view()."""
     views = split_views(cost_volumes)
     shape = views[0].shape
     c = shape[-1]
     nvox = views[0].numel() // c
-    x = stack_views(views)
-    out = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
+    out = torch.empty((nvox, c), dtype=torch.float32, device=views[0].device)
     if c % 8 == 0:
-        raw = attention_activations_raw(views, scope)
-        L.call("atvs_attention_raw", L.ptr(raw), _raw_code(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 0, None, L.ptr(out),
-               L.stream())
+        if raw is None:
+            raw = attention_activations_raw(views, scope)
+        L.call("atvs_attention_raw", L.ptr(raw), _raw_code(raw), view_pointers(views), len(views), nvox, c,
+               L.dtype_code(views[0]), 0, None, L.ptr(out), L.stream())
     else:
+        x = stack_views(views)
         act = attention_activations(views, scope)
         L.call("atvs_attention_combine", L.ptr(act), L.ptr(x), len(views), nvox, c, L.dtype_code(x), L.ptr(out),
                L.stream())

@@ -85,19 +85,21 @@ def reduce_partials(nd, world, rank, group, finish, gather_dtype):
     return full[:V]
 
 
-def aggregate(filtered_views, scope='attention_aggregate', group=None, rank=0, world=1):
+def aggregate(filtered_views, scope='attention_aggregate', group=None, rank=0, world=1, raw=None):
     """AAM (network.py:379-408) over this rank's views; with ``group`` the softmax over views is completed across
     ranks: all-reduce(MAX) of the local logit max (as bf16: any shift that is the same on every rank is exact for the
     softmax), then reduce_partials() of [numerator || denominator] (V,16) fp32.  Sharded result: activation dtype."""
     if group is None:
-        return N.attention_aggregation(filtered_views, scope)
+        return N.attention_aggregation(filtered_views, scope, raw=raw)
     import torch.distributed as dist
     views = N.split_views(filtered_views)
     shape = views[0].shape
     c = shape[-1]
     nvox = views[0].numel() // c
-    raw = N.attention_activations_raw(views, scope)
-    x = N.stack_views(views)
+    if raw is None:
+        raw = N.attention_activations_raw(views, scope)
+    x = views[0]
+    xp = N.view_pointers(views)
     lmax = torch.empty((nvox, c), dtype=torch.float32, device=x.device)
     L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), None, len(views), nvox, c, L.dtype_code(x), 1, None, L.ptr(lmax), L.stream())
     lmax16 = lmax.to(torch.bfloat16)
@@ -105,7 +107,7 @@ def aggregate(filtered_views, scope='attention_aggregate', group=None, rank=0, w
     lmax.copy_(lmax16)
     del lmax16
     nd = torch.empty((nvox, 2 * c), dtype=torch.float32, device=x.device)
-    L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), L.ptr(x), len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
+    L.call("atvs_attention_raw", L.ptr(raw), N._raw_code(raw), xp, len(views), nvox, c, L.dtype_code(x), 2, L.ptr(lmax), L.ptr(nd),
            L.stream())
     del raw, lmax
 
@@ -138,23 +140,34 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     nstreams = max(1, min(CONCURRENT_PASSES, len(tasks)))
     main = torch.cuda.current_stream()
     results = {}
+    # attention logits (N,V,16), allocated on the calling stream before the passes fan out: every view's 8->16
+    # attention convolution runs on that view's stream right behind its forward pass instead of in the serial tail
+    B_, _, h_, w_, _ = features.shape
+    att_raw = N.attention_raw_alloc(len(mine), torch.empty((B_, int(depth_num), h_, w_, 8), dtype=N.act_dtype(),
+                                                           device='meta'), device=features.device)
+
+    def run_task(v, kind):
+        if kind == 'r':
+            return stage1_reverse(features, cams, depth_num, ds, di, v)
+        out = stage1_forward(features, cams, depth_num, ds, di, v)
+        N.attention_raw_view(att_raw, mine.index(v), N.to_act(out[0]), 'attention_aggregate')
+        return out
+
     if nstreams == 1:
         for v, kind in tasks:
-            fn = stage1_forward if kind == 'f' else stage1_reverse
-            results[(v, kind)] = fn(features, cams, depth_num, ds, di, v)
+            results[(v, kind)] = run_task(v, kind)
     else:
         if not N.V.packed_cache():
             # first call after load_weights: run one pass on the main stream so that the packed bf16 weight
             # images exist before other streams read them
             v, kind = tasks.pop(0)
-            results[(v, kind)] = (stage1_forward if kind == 'f' else stage1_reverse)(features, cams, depth_num, ds, di, v)
+            results[(v, kind)] = run_task(v, kind)
         streams = _side_streams(features.device, nstreams)
         for st in streams:
             st.wait_stream(main)
         for i, (v, kind) in enumerate(tasks):
             with torch.cuda.stream(streams[i % nstreams]):
-                fn = stage1_forward if kind == 'f' else stage1_reverse
-                out = fn(features, cams, depth_num, ds, di, v)
+                out = run_task(v, kind)
                 for t in (out if isinstance(out, tuple) else (out,)):
                     t.record_stream(main)
                 results[(v, kind)] = out
@@ -162,7 +175,7 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
             main.wait_stream(st)
     filtered = [results[(v, 'f')][0] for v in mine]
     depth_views = [results[(v, 'r')] for v in mine] if siamese else [None for _ in mine]
-    cost_agg = aggregate(filtered, 'attention_aggregate', group, rank, world)
+    cost_agg = aggregate(filtered, 'attention_aggregate', group, rank, world, raw=att_raw)
     prob_agg = OutputConv({'data': cost_agg}).get_output().squeeze(-1)
     depth, _ = _prob2depth(prob_agg, ds, di, 1, False)
     out = dict(depth=depth, prob_volume_agg=prob_agg, cost_volume_agg=cost_agg, depth_views=depth_views)

@@ -165,7 +165,8 @@ int atvs_attention_finish(const float* num_den, long long V, int C, float* out,
 /* the same three operations (mode 0 = combine, 1 = local max, 2 = partial) on the RAW fp32 output
  * (N,V,2C) of the attention convolution: relu (network.py:323-344) is applied while loading, the
  * activations are never stored.  C % 8 == 0.                                                      */
-int atvs_attention_raw(const void* act_raw, int act_dtype /* ATVS_F32 | ATVS_F16 */, const void* x, int N,
+int atvs_attention_raw(const void* act_raw, int act_dtype /* ATVS_F32 | ATVS_F16 */,
+                       const void* const* x_views /* HOST array of N device pointers, each (V,C) x_dtype */, int N,
                        long long V, int C, int x_dtype, int mode, const float* gmax, float* out,
                        atvs_stream_t stream);
 
