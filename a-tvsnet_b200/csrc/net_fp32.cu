@@ -202,6 +202,35 @@ template <> struct RawLd<__half> {
     static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
 };
 
+// 8 consecutive elements as they sit in memory (16 bytes for bf16 / fp16, 32 for fp32): loads are issued in this form
+// and unpacked to fp32 only when used, so that several of them can be in flight per thread at 16 registers
+template <typename E> struct Pk8 { uint4 u; };
+template <> struct Pk8<float> { float4 a, b; };
+template <typename E>
+__device__ __forceinline__ Pk8<E> ldp8(const E* p) {
+    Pk8<E> r;
+    r.u = __ldcs(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ Pk8<float> ldp8<float>(const float* p) {
+    Pk8<float> r;
+    r.a = __ldcs(reinterpret_cast<const float4*>(p));
+    r.b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+}
+__device__ __forceinline__ void unpack8(const Pk8<float>& k, float4& a, float4& b) { a = k.a; b = k.b; }
+__device__ __forceinline__ void unpack8(const Pk8<__half>& k, float4& a, float4& b) {
+    const float2 x = RawLd<__half>::h2(k.u.x), y = RawLd<__half>::h2(k.u.y), z = RawLd<__half>::h2(k.u.z), w = RawLd<__half>::h2(k.u.w);
+    a = make_float4(x.x, x.y, y.x, y.y); b = make_float4(z.x, z.y, w.x, w.y);
+}
+__device__ __forceinline__ void unpack8(const Pk8<__nv_bfloat16>& k, float4& a, float4& b) {
+    a = make_float4(__uint_as_float(k.u.x << 16), __uint_as_float(k.u.x & 0xffff0000u), __uint_as_float(k.u.y << 16),
+                    __uint_as_float(k.u.y & 0xffff0000u));
+    b = make_float4(__uint_as_float(k.u.z << 16), __uint_as_float(k.u.z & 0xffff0000u), __uint_as_float(k.u.w << 16),
+                    __uint_as_float(k.u.w & 0xffff0000u));
+}
+
 template <typename T, typename RawT>
 __global__ void __launch_bounds__(256)
 k_bn_relu_add(const RawT* __restrict__ raw, const double* __restrict__ stats, const RawT* __restrict__ raw2,
@@ -241,24 +270,48 @@ k_bn_relu_add(const RawT* __restrict__ raw, const double* __restrict__ stats, co
     if ((C & 7) == 0) {
         const long long n8 = n >> 3;
         const bool pow2 = (C & (C - 1)) == 0;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long e = i << 3;
-            const int c = pow2 ? (int)(e & (C - 1)) : (int)(e % C);
-            float4 ra, rb;
-            RawLd<RawT>::ld8(raw + e, ra, rb);
-            float4 ya = norm4(ra, sh_inv, sh_off, c);
-            float4 yb = norm4(rb, sh_inv, sh_off, c + 4);
-            if (out_plain) Vec8<T>::st(out_plain + e, ya, yb);
-            if (out_sum) {
-                if (raw2) {
-                    RawLd<RawT>::ld8(raw2 + e, ra, rb);
-                    add4(ya, norm4(ra, sh_inv2, sh_off2, c));
-                    add4(yb, norm4(rb, sh_inv2, sh_off2, c + 4));
+        // two 8-element groups per thread and iteration, every load of both issued before the first use: with ~1500
+        // resident threads per SM one 16-byte load each is not enough bytes in flight to cover the HBM latency
+        constexpr int U = 2;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        const bool sum_in = out_sum != nullptr;
+        for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += U * stride) {
+            long long e[U];
+            bool ok[U];
+            Pk8<RawT> pr[U], pq[U];
+            Pk8<T> p1[U], p2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * stride;
+                ok[u] = i < n8;
+                e[u] = (ok[u] ? i : i0) << 3;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pr[u] = ldp8<RawT>(raw + e[u]);
+                if (sum_in && raw2) pq[u] = ldp8<RawT>(raw2 + e[u]);
+                if (sum_in && s1) p1[u] = ldp8<T>(s1 + e[u]);
+                if (sum_in && s2) p2[u] = ldp8<T>(s2 + e[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const int c = pow2 ? (int)(e[u] & (C - 1)) : (int)(e[u] % C);
+                float4 ta, tb;
+                unpack8(pr[u], ta, tb);
+                float4 ya = norm4(ta, sh_inv, sh_off, c);
+                float4 yb = norm4(tb, sh_inv, sh_off, c + 4);
+                if (out_plain) Vec8<T>::st(out_plain + e[u], ya, yb);
+                if (sum_in) {
+                    if (raw2) {
+                        unpack8(pq[u], ta, tb);
+                        add4(ya, norm4(ta, sh_inv2, sh_off2, c));
+                        add4(yb, norm4(tb, sh_inv2, sh_off2, c + 4));
+                    }
+                    if (s1) { unpack8(p1[u], ta, tb); add4(ya, ta); add4(yb, tb); }
+                    if (s2) { unpack8(p2[u], ta, tb); add4(ya, ta); add4(yb, tb); }
+                    Vec8<T>::st(out_sum + e[u], ya, yb);
                 }
-                if (s1) { float4 a, b; Vec8<T>::ld(s1 + e, a, b); add4(ya, a); add4(yb, b); }
-                if (s2) { float4 a, b; Vec8<T>::ld(s2 + e, a, b); add4(ya, a); add4(yb, b); }
-                Vec8<T>::st(out_sum + e, ya, yb);
             }
         }
     } else if ((C & 3) == 0) {
