@@ -1,0 +1,282 @@
+// fem2d.cu - first CUDA path of the 2-D feature extraction module (ResNetDS2SPP):
+//   atvs_conv2d_fp32            <- tf.layers.conv2d / slim.conv2d (network.py:142-215, 570-599): k = 1 | 3, stride, dilation,
+//                                  explicit top/left padding (covers TF 'SAME' and the bottleneck's pad + 'VALID'), bias, ReLU
+//   atvs_channel_moments        <- the batch statistics of tf.layers.batch_normalization / slim.batch_norm (training)
+//   atvs_bn2d_apply             <- (x - mean) * rsqrt(var + eps) [+ beta] [ReLU]
+//   atvs_avg_pool_same          <- tf.layers.average_pooling2d 'SAME' (mean over the valid elements)
+//   atvs_resize_bilinear_align  <- tf.image.resize_images(bilinear, align_corners=True) on NHWC
+// fp32 CUDA-core kernels (register-tiled direct convolution): the PARITY path of this row.  The tensor-core (tcgen05)
+// version - channel-chunked taps, dilation, bias/ReLU epilogue - is the next step; see DESIGN.md section 6.
+#include "common.cuh"
+
+namespace {
+
+struct Conv2dParams {
+    int B, H, W, Cin, Cout, Ho, Wo;
+    int stride, rate, pad_t, pad_l, relu;
+    int tiles_x, tiles_y;
+};
+
+constexpr int C2_TW = 32, C2_TH = 8, C2_CO = 32, C2_KC = 16;
+
+// block = 256 threads = 64 pixel quads (4 consecutive x) x 4 groups of 8 output channels; one 8 x 32 pixel tile and
+// 32 output channels per block.  Per (tap, 16-channel chunk) the weights [16][32] are staged in shared memory; a thread
+// does 128 FMAs per 4 input float4 loads and 8 weight LDS.128.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              const Conv2dParams p, float* __restrict__ out) {
+    __shared__ __align__(16) float ws[C2_KC][C2_CO];
+    const int t = threadIdx.x;
+    const int cg = t & 3, q = t >> 2;
+    const int qy = q >> 3, qx = q & 7;
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x;
+    tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y;
+    const int b = tile / p.tiles_y;
+    const int co0 = blockIdx.y * C2_CO;
+    const int oy = ty * C2_TH + qy;
+    const int ox0 = tx * C2_TW + qx * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+    const bool vec = (p.Cin & 3) == 0;
+    const float* xb = x + (size_t)b * p.H * p.W * p.Cin;
+    for (int tap = 0; tap < K * K; ++tap) {
+        const int ky = tap / K, kx = tap % K;
+        const int iy = oy * p.stride - p.pad_t + ky * p.rate;
+        const bool yok = oy < p.Ho && iy >= 0 && iy < p.H;
+        int ix[4];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ix[j] = (ox0 + j) * p.stride - p.pad_l + kx * p.rate;
+            ok[j] = yok && (ox0 + j) < p.Wo && ix[j] >= 0 && ix[j] < p.W;
+        }
+        for (int c0 = 0; c0 < p.Cin; c0 += C2_KC) {
+            __syncthreads();
+            for (int i = t; i < C2_KC * C2_CO; i += 256) {
+                const int ci = i / C2_CO, co = i % C2_CO;
+                float v = 0.f;
+                if (c0 + ci < p.Cin && co0 + co < p.Cout) v = __ldg(w + ((size_t)tap * p.Cin + c0 + ci) * p.Cout + co0 + co);
+                ws[ci][co] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c4 = 0; c4 < C2_KC; c4 += 4) {
+                if (c0 + c4 >= p.Cin) break;
+                float in[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!ok[j]) {
+                        in[j][0] = in[j][1] = in[j][2] = in[j][3] = 0.f;
+                    } else if (vec) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4));
+                        in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc)
+                            in[j][cc] = (c0 + c4 + cc < p.Cin) ? __ldg(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4 + cc) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8 + 4]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float a = in[j][cc];
+                        acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
+                        acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
+                        acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
+                        acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
+                    }
+                }
+            }
+        }
+    }
+    if (oy >= p.Ho) return;
+    const int co = co0 + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ox = ox0 + j;
+        if (ox >= p.Wo) continue;
+        float* o = out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + co;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (co + c >= p.Cout) break;
+            float v = acc[j][c] + (bias ? __ldg(bias + co + c) : 0.f);
+            if (p.relu) v = fmaxf(v, 0.f);
+            o[c] = v;
+        }
+    }
+}
+
+// per-channel sum and sum of squares of an (count, C) tensor; 256 % C == 0 keeps a thread on one channel
+__global__ void __launch_bounds__(256)
+k_channel_moments(const float* __restrict__ x, long long count, int C, double* __restrict__ stats) {
+    __shared__ double sh[2][256];
+    const long long n = count * C;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double s = 0.0, s2 = 0.0;
+    const bool fixed = (256 % C) == 0;
+    if (fixed) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double v = (double)x[i];
+            s += v;
+            s2 += v * v;
+        }
+        sh[0][threadIdx.x] = s;
+        sh[1][threadIdx.x] = s2;
+        __syncthreads();
+        if (threadIdx.x < C) {
+            double a = 0.0, a2 = 0.0;
+            for (int k = threadIdx.x; k < 256; k += C) { a += sh[0][k]; a2 += sh[1][k]; }
+            atomicAdd(&stats[threadIdx.x], a);
+            atomicAdd(&stats[C + threadIdx.x], a2);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double v = (double)x[i];
+            const int c = (int)(i % C);
+            atomicAdd(&stats[c], v);
+            atomicAdd(&stats[C + c], v * v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn2d_apply(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ beta, long long count,
+             int C, float eps, int relu, float* __restrict__ out) {
+    const long long n = count * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const double mean = stats[c] / (double)count;
+        double var = stats[C + c] / (double)count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float inv = (float)(1.0 / sqrt(var + (double)eps));
+        float y = x[i] * inv - (float)mean * inv;
+        if (beta) y += beta[c];
+        if (relu) y = fmaxf(y, 0.f);
+        out[i] = y;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_avg_pool_same(const float* __restrict__ x, int B, int H, int W, int C, int k, int s, int pad_t, int pad_l, int Ho, int Wo,
+                float* __restrict__ out) {
+    const long long n = (long long)B * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int y0 = max(oy * s - pad_t, 0), y1 = min(oy * s - pad_t + k, H);
+        const int x0 = max(ox * s - pad_l, 0), x1 = min(ox * s - pad_l + k, W);
+        float acc = 0.f;
+        for (int y = y0; y < y1; ++y)
+            for (int xx = x0; xx < x1; ++xx) acc += x[(((size_t)b * H + y) * W + xx) * C + c];
+        out[i] = acc / (float)((y1 - y0) * (x1 - x0));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_resize_bilinear_align(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ out) {
+    const long long n = (long long)B * Ho * Wo * C;
+    const float sy = Ho > 1 ? __fdiv_rn((float)(H - 1), (float)(Ho - 1)) : 0.f;
+    const float sx = Wo > 1 ? __fdiv_rn((float)(W - 1), (float)(Wo - 1)) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const float fy_ = __fmul_rn((float)oy, sy), fx_ = __fmul_rn((float)ox, sx);
+        const int y0 = (int)floorf(fy_), x0 = (int)floorf(fx_);
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float fy = fy_ - (float)y0, fx = fx_ - (float)x0;
+        const float* xb = x + (size_t)b * H * W * C + c;
+        const float tl = xb[((size_t)y0 * W + x0) * C], tr = xb[((size_t)y0 * W + x1) * C];
+        const float bl = xb[((size_t)y1 * W + x0) * C], br = xb[((size_t)y1 * W + x1) * C];
+        const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), fx));
+        const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), fx));
+        out[i] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), fy));
+    }
+}
+
+inline unsigned ew_grid(long long n) {
+    long long g = (n + 255) / 256;
+    const long long cap = (long long)atvs_num_sms() * 8;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int atvs_conv2d_fp32(const float* x, const float* kernel, const float* bias, int B, int H, int W, int Cin, int Cout,
+                                int ksize, int stride, int rate, int pad_top, int pad_left, int Ho, int Wo, int relu,
+                                float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && kernel && out, ATVS_E_NULL, "atvs_conv2d_fp32: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Ho > 0 && Wo > 0, ATVS_E_SHAPE, "atvs_conv2d_fp32: bad shape");
+    ATVS_CHECK_ARG(ksize == 1 || ksize == 3, ATVS_E_UNSUP, "atvs_conv2d_fp32: kernel size %d (1 or 3)", ksize);
+    ATVS_CHECK_ARG(stride >= 1 && rate >= 1 && pad_top >= 0 && pad_left >= 0, ATVS_E_UNSUP, "atvs_conv2d_fp32: stride/rate/pad");
+    ATVS_CHECK_ARG((Cin & 3) != 0 || ((uintptr_t)x & 15) == 0, ATVS_E_SHAPE, "atvs_conv2d_fp32: x must be 16-byte aligned");
+    Conv2dParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
+    p.stride = stride; p.rate = rate; p.pad_t = pad_top; p.pad_l = pad_left; p.relu = relu;
+    p.tiles_x = (Wo + C2_TW - 1) / C2_TW;
+    p.tiles_y = (Ho + C2_TH - 1) / C2_TH;
+    dim3 grid((unsigned)((long long)B * p.tiles_x * p.tiles_y), (unsigned)((Cout + C2_CO - 1) / C2_CO));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ksize == 1) k_conv2d_fp32<1><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else k_conv2d_fp32<3><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_channel_moments(const float* x, long long count, int C, double* stats, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && stats, ATVS_E_NULL, "atvs_channel_moments: NULL pointer");
+    ATVS_CHECK_ARG(count > 0 && C > 0, ATVS_E_SHAPE, "atvs_channel_moments: count=%lld C=%d", count, C);
+    unsigned g = ew_grid(count * C);
+    if (g > 592) g = 592;          // fp64 atomics per block: keep the tail short
+    k_channel_moments<<<g, 256, 0, (cudaStream_t)stream>>>(x, count, C, stats);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_bn2d_apply(const float* x, const double* stats, const float* beta, long long count, int C, float eps,
+                               int relu, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && stats && out, ATVS_E_NULL, "atvs_bn2d_apply: NULL pointer");
+    ATVS_CHECK_ARG(count > 0 && C > 0, ATVS_E_SHAPE, "atvs_bn2d_apply: count=%lld C=%d", count, C);
+    k_bn2d_apply<<<ew_grid(count * C), 256, 0, (cudaStream_t)stream>>>(x, stats, beta, count, C, eps, relu, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_avg_pool_same(const float* x, int B, int H, int W, int C, int ksize, int stride, float* out,
+                                  atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && out, ATVS_E_NULL, "atvs_avg_pool_same: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && ksize > 0 && stride > 0, ATVS_E_SHAPE, "atvs_avg_pool_same: bad shape");
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    int th = (Ho - 1) * stride + ksize - H, tw = (Wo - 1) * stride + ksize - W;
+    if (th < 0) th = 0;
+    if (tw < 0) tw = 0;
+    k_avg_pool_same<<<ew_grid((long long)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, ksize, stride, th / 2,
+                                                                                        tw / 2, Ho, Wo, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_resize_bilinear_align(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out,
+                                          atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && out, ATVS_E_NULL, "atvs_resize_bilinear_align: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, ATVS_E_SHAPE, "atvs_resize_bilinear_align: bad shape");
+    k_resize_bilinear_align<<<ew_grid((long long)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}

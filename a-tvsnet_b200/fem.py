@@ -1,0 +1,143 @@
+"""2-D feature extraction module ``ResNetDS2SPP`` (/root/reference/cnn_wrapper/atvsnet.py:254-292 on the layers of
+cnn_wrapper/network.py:142-215 conv / conv_bn, :552-616 bottleneck / res_block, :650-671 image_resize / avg_pool,
+:690-697 concat / add) on torch CUDA tensors, NHWC fp32, through the C ABI (csrc/fem2d.cu).
+
+First CUDA path of SURVEY.md 8(f) row N1: fp32 CUDA-core kernels, checked against oracle/fem.py and the reference-graph
+golden vectors.  Variables are looked up under the checkpoint names (tests/golden/fem_variables.json).  The tensor-core
+version is future work, so the hot-path entry points keep taking features; ``extract_features`` is the image-side
+entry that produces them (model.py:420-425 TVSNet_feature_extraction)."""
+import torch
+
+from . import _lib as L
+from . import variables as V
+
+BN_EPS = 1e-3
+
+
+def _same_pad(n, k_eff, s):
+    out = -(-n // s)
+    total = max((out - 1) * s + k_eff - n, 0)
+    return total // 2, out
+
+
+def conv2d(x, kernel, stride=1, rate=1, bias=None, relu=False, padding='SAME', explicit_pad=None):
+    """x (B,H,W,Cin) fp32 cuda, kernel [k,k,Cin,Cout].  padding 'SAME' (TF) or 'VALID' after ``explicit_pad`` =
+    (begin, end) zero rows/cols on both axes (the bottleneck's tf.pad + VALID, network.py:589-595)."""
+    L.require_cuda(x, kernel)
+    x = L.f32c(x)
+    B, H, W, cin = x.shape
+    k, cout = kernel.shape[0], kernel.shape[-1]
+    k_eff = (k - 1) * rate + 1
+    if explicit_pad is not None:
+        pb, pe = explicit_pad
+        pt = pl = pb
+        Ho = (H + pb + pe - k_eff) // stride + 1
+        Wo = (W + pb + pe - k_eff) // stride + 1
+    elif padding == 'SAME':
+        pt, Ho = _same_pad(H, k_eff, stride)
+        pl, Wo = _same_pad(W, k_eff, stride)
+    else:
+        pt = pl = 0
+        Ho, Wo = (H - k_eff) // stride + 1, (W - k_eff) // stride + 1
+    out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
+    L.call("atvs_conv2d_fp32", L.ptr(x), L.ptr(kernel), L.ptr(bias), B, H, W, cin, cout, k, stride, rate, pt, pl, Ho, Wo,
+           int(relu), L.ptr(out), L.stream())
+    return out
+
+
+def batch_norm(x, beta=None, relu=False):
+    """batch statistics over (B,H,W), biased variance, eps 1e-3, optional ``+ beta``, optional ReLU."""
+    C = x.shape[-1]
+    count = x.numel() // C
+    stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+    L.call("atvs_channel_moments", L.ptr(x), count, C, L.ptr(stats), L.stream())
+    out = torch.empty_like(x)
+    L.call("atvs_bn2d_apply", L.ptr(x), L.ptr(stats), L.ptr(beta), count, C, BN_EPS, int(relu), L.ptr(out), L.stream())
+    return out
+
+
+def conv_bn(x, name, stride=1, rate=1):
+    """network.py:173-215 on a 4-D tensor: name/conv2d/kernel, BN without affine, ReLU."""
+    return batch_norm(conv2d(x, V.get_variable(name + '/conv2d/kernel'), stride, rate), None, True)
+
+
+def add(a, b):
+    out = torch.empty_like(a)
+    L.call("atvs_add", L.ptr(a), L.ptr(b), L.ptr(out), L.F32, a.numel(), L.stream())
+    return out
+
+
+def bottleneck(x, scope, depth, stride=1, rate=1):
+    """network.py:552-603."""
+    g = V.get_variable
+    depth_in = x.shape[-1]
+    preact = batch_norm(x, g(scope + '/preact/beta'), True)
+    if depth == depth_in:
+        shortcut = x if stride == 1 else x[:, ::stride, ::stride, :].contiguous()
+    else:
+        shortcut = conv2d(preact, g(scope + '/shortcut/weights'), stride, 1, g(scope + '/shortcut/biases'))
+    r = conv2d(preact, g(scope + '/conv1/weights'), 1, 1, g(scope + '/conv1/biases'), relu=True)
+    if stride == 1:
+        r = conv2d(r, g(scope + '/conv2/weights'), 1, rate, g(scope + '/conv2/biases'), relu=True)
+    else:
+        k_eff = 3 + 2 * (rate - 1)
+        beg = (k_eff - 1) // 2
+        r = conv2d(r, g(scope + '/conv2/weights'), stride, rate, g(scope + '/conv2/biases'), relu=True,
+                   explicit_pad=(beg, k_eff - 1 - beg))
+    r = conv2d(r, g(scope + '/conv3/weights'), 1, 1, g(scope + '/conv3/biases'))
+    return add(shortcut, r)
+
+
+def res_block(x, name, depth, num_block, stride=1, rate=1):
+    """network.py:605-616."""
+    if num_block == 1:
+        return bottleneck(x, name, depth, stride, rate)
+    out = bottleneck(x, name + '_0', depth, stride, rate)
+    for i in range(1, num_block):
+        out = bottleneck(out, name + '_%d' % i if i != num_block - 1 else name, depth, 1, rate)
+    return out
+
+
+def avg_pool(x, k, s):
+    B, H, W, C = x.shape
+    out = torch.empty((B, -(-H // s), -(-W // s), C), dtype=torch.float32, device=x.device)
+    L.call("atvs_avg_pool_same", L.ptr(x), B, H, W, C, k, s, L.ptr(out), L.stream())
+    return out
+
+
+def image_resize(x, Ho, Wo):
+    B, H, W, C = x.shape
+    out = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
+    L.call("atvs_resize_bilinear_align", L.ptr(x), B, H, W, C, Ho, Wo, L.ptr(out), L.stream())
+    return out
+
+
+def ResNetDS2SPP(image, return_layers=False):
+    """cnn_wrapper/atvsnet.py:254-292: image (B,H,W,3) fp32 cuda -> feature (B,H/4,W/4,32) fp32."""
+    L.require_cuda(image)
+    layers = {}
+    x = conv_bn(L.f32c(image), 'conv0_0', stride=2)
+    x = conv_bn(x, 'conv0_1')
+    x = layers['conv0_2'] = conv_bn(x, 'conv0_2')
+    x = layers['conv0_x'] = res_block(x, 'conv0_x', 32, 3, 1, 1)
+    c1 = layers['conv1_x'] = res_block(x, 'conv1_x', 64, 8, 2, 1)
+    x = layers['conv2_x'] = res_block(c1, 'conv2_x', 128, 3, 1, 2)
+    c3 = layers['conv3_x'] = res_block(x, 'conv3_x', 128, 3, 1, 4)
+    h, w = c3.shape[1], c3.shape[2]
+    branches = []
+    for i, k in enumerate((64, 32, 16, 8)):
+        b = image_resize(conv_bn(avg_pool(c3, k, k), 'branch_%d_conv' % i), h, w)
+        layers['branch_%d' % i] = b
+        branches.append(b)
+    cat = torch.cat([c1, c3] + branches, dim=-1).contiguous()
+    f0 = layers['fusion0'] = conv_bn(cat, 'fusion0')
+    out = layers['fusion1'] = conv2d(f0, V.get_variable('fusion1/kernel'))
+    return (out, layers) if return_layers else out
+
+
+def extract_features(images):
+    """model.py:420-425 TVSNet_feature_extraction over all views: images (B,N,H,W,3) -> features (B,N,H/4,W/4,32).
+    Every view is a separate batch of ONE for the batch statistics, as in the reference's per-view towers."""
+    B, N = images.shape[0], images.shape[1]
+    feats = [torch.stack([ResNetDS2SPP(images[b:b + 1, n])[0] for n in range(N)], dim=0) for b in range(B)]
+    return torch.stack(feats, dim=0)

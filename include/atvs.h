@@ -170,6 +170,27 @@ int atvs_attention_raw(const void* act_raw, int act_dtype /* ATVS_F32 | ATVS_F16
                        long long V, int C, int x_dtype, int mode, const float* gmax, float* out,
                        atvs_stream_t stream);
 
+/* ---- 2-D feature extraction module (FEM, ResNetDS2SPP) --- cnn_wrapper/atvsnet.py:254-292, network.py:142-215, 552-671
+ * fp32 NHWC CUDA-core parity path of SURVEY.md 8(f) row N1 (the tensor-core version is not built yet).
+ * atvs_conv2d_fp32: kernel [k,k,Cin,Cout] (TF layout), k = 1 | 3, stride, dilation `rate`, explicit zero padding
+ *   pad_top / pad_left (bottom / right follow from Ho, Wo): TF 'SAME' and the bottleneck's pad + 'VALID'
+ *   (network.py:589-595) are both expressed this way; out (B,Ho,Wo,Cout) = [relu](conv + bias), bias may be NULL.
+ * atvs_channel_moments: stats[0..C) += sum, stats[C..2C) += sum of squares over `count` rows (caller zeroes stats).
+ * atvs_bn2d_apply: (x - mean) * rsqrt(var + eps) [+ beta[c]] [relu], batch statistics from stats / count
+ *   (tf.layers.batch_normalization(center=False) -> beta NULL; slim.batch_norm -> beta).
+ * atvs_avg_pool_same: tf.layers.average_pooling2d 'SAME', mean over the valid elements; out (B,ceil(H/s),ceil(W/s),C).
+ * atvs_resize_bilinear_align: tf.image.resize_images(bilinear, align_corners=True), TF's lerp order.            */
+int atvs_conv2d_fp32(const float* x, const float* kernel, const float* bias, int B, int H, int W, int Cin,
+                     int Cout, int ksize, int stride, int rate, int pad_top, int pad_left, int Ho, int Wo,
+                     int relu, float* out, atvs_stream_t stream);
+int atvs_channel_moments(const float* x, long long count, int C, double* stats, atvs_stream_t stream);
+int atvs_bn2d_apply(const float* x, const double* stats, const float* beta, long long count, int C, float eps,
+                    int relu, float* out, atvs_stream_t stream);
+int atvs_avg_pool_same(const float* x, int B, int H, int W, int C, int ksize, int stride, float* out,
+                       atvs_stream_t stream);
+int atvs_resize_bilinear_align(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out,
+                               atvs_stream_t stream);
+
 /* ---- prob2depth / get_propability_map / prob2depth_upsample -------- model.py:80-129, 13-76
  * prob_volume (B,D,H,W) f32 logits; softmax over D of -logit, expectation against
  * linspace(start, start+(D-1)*interval, D) -> depth (B,H*up,W*up) f32; prob_map (same shape,
