@@ -78,3 +78,42 @@ def synthetic_weights(seed=1234, logit_gain=4.0):
         w[scope + '/attention_activation/weight_shared'] = he((3, 3, 3, 8, 8), 27 * 8)
         w[outc + '/kernel'] = he((3, 3, 3, 8, 1), 27 * 8) * np.float32(logit_gain)
     return w
+
+
+def fem_variable_shapes():
+    """name -> shape of the FEM (ResNetDS2SPP) variables, cnn_wrapper/atvsnet.py:254-292 + network.py:552-616 naming
+    (SURVEY.md Appendix B); tests/test_host_logic.py holds it equal to the list recorded from the reference's own
+    graph code (tests/golden/fem_variables.json)."""
+    s = {'conv0_0/conv2d/kernel': (3, 3, 3, 32), 'conv0_1/conv2d/kernel': (3, 3, 32, 32),
+         'conv0_2/conv2d/kernel': (3, 3, 32, 32)}
+    cin = 32
+    for name, depth, nblock in (('conv0_x', 32, 3), ('conv1_x', 64, 8), ('conv2_x', 128, 3), ('conv3_x', 128, 3)):
+        for i in range(nblock):
+            scope = name + '_%d' % i if i != nblock - 1 else name
+            s[scope + '/preact/beta'] = (cin,)
+            if cin != depth:
+                s[scope + '/shortcut/weights'] = (1, 1, cin, depth)
+                s[scope + '/shortcut/biases'] = (depth,)
+            s[scope + '/conv1/weights'] = (1, 1, cin, depth)
+            s[scope + '/conv2/weights'] = (3, 3, depth, depth)
+            s[scope + '/conv3/weights'] = (1, 1, depth, depth)
+            for c in ('conv1', 'conv2', 'conv3'):
+                s[scope + '/' + c + '/biases'] = (depth,)
+            cin = depth
+    for i in range(4):
+        s['branch_%d_conv/conv2d/kernel' % i] = (3, 3, 128, 32)
+    s['fusion0/conv2d/kernel'] = (3, 3, 320, 128)
+    s['fusion1/kernel'] = (1, 1, 128, 32)
+    return s
+
+
+def synthetic_fem_weights(seed=4321):
+    """seeded FEM weights under the checkpoint names: He-normal kernels, small biases / betas."""
+    w = {}
+    for i, (name, shape) in enumerate(sorted(fem_variable_shapes().items())):
+        rng = np.random.default_rng([seed, i])
+        if len(shape) == 4:
+            w[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / np.prod(shape[:-1]))).astype(np.float32)
+        else:
+            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+    return w

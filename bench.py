@@ -155,11 +155,19 @@ def run_ours(args, rank, world, local_rank):
     workload = args.workload or 'cfg2'
     sharded = workload == 'cfg3' and world > 1
     group = dist.group.WORLD if sharded else None
-    A.variables.load_weights(A.variables.synthetic_weights(), device=dev)
+    allw = A.variables.synthetic_weights()
+    if args.from_images:
+        allw.update(A.variables.synthetic_fem_weights())
+    A.variables.load_weights(allw, device=dev)
     feats, cams, D = make_inputs(workload, frame_seed=rank if not sharded else 0)
     nv, H, W, _ = WORKLOADS[workload]
     h, w = H // 4, W // 4
     V = D * h * w
+    if args.from_images:
+        # images in (example.py:332-336 feeds raw 0..255 BGR): the step starts with the 2-D feature extraction module
+        # (fp32 CUDA-core first path, a-tvsnet_b200/fem.py); `feats` then stands for the (1,N,H,W,3) image tensor
+        rng = np.random.default_rng(1000 + (rank if not sharded else 0))
+        feats = (127.5 + 50.0 * rng.standard_normal((1, nv, H, W, 3))).clip(0, 255).astype(np.float32)
 
     # pinned host buffers (end-to-end path) and resident device inputs (kernel path)
     feats_h = torch.from_numpy(feats).pin_memory()
@@ -171,7 +179,8 @@ def run_ours(args, rank, world, local_rank):
     depth_h = torch.empty((1, H, W, 1), dtype=torch.float32).pin_memory()
 
     def step():
-        return A.pipeline.run_multiview(feats_d, cams_d, D, siamese=True, upsample=True, group=group, rank=rank,
+        f = A.fem.extract_features(feats_d) if args.from_images else feats_d
+        return A.pipeline.run_multiview(f, cams_d, D, siamese=True, upsample=True, group=group, rank=rank,
                                         world=world)['depth_up']
 
     # warm-up (eager): compiles nothing, but sets kernel attributes, packs weights, fills the allocator
@@ -224,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
     # the public streaming call (pipeline.FrameStream): frames arrive in pinned host memory, every step copies its
     # inputs H2D and its depth map D2H; the copies of neighbouring frames overlap the step on their own streams
     fstream = None
-    if graph is not None:
+    if graph is not None and not args.from_images:
         fstream = A.pipeline.FrameStream(tuple(feats_h.shape), tuple(cams_h.shape), D, dev, siamese=True)
         for dm in fstream.run([(feats_h, cams_h)] * 3):
             pass
@@ -277,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- the HBM-bound kernels of the path (K1, K4) on this workload's shapes ----------------
     kernels = None
-    if rank == 0 and args.precision == 'bf16':
+    if rank == 0 and args.precision == 'bf16' and not args.from_images:
         kernels = hbm_kernel_lines(A, feats_d, cams_d, D, h, w, res if res is not None else out)
         if roof is not None:
             roof["traffic"], roof["traffic_source"] = ncu_traffic("k_conv3d_ring<32, 8, 2>")
@@ -300,8 +309,11 @@ def run_ours(args, rank, world, local_rank):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == 'bf16' else "f32", "data": "synthetic",
-        "config": {"workload": "%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II "
-                               "+ x4 soft-argmin; FEM and refinement not included" % (workload, nv - 1, W, H, h, w, D),
+        "config": {"workload": ("%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II "
+                                "+ x4 soft-argmin; FEM and refinement not included" % (workload, nv - 1, W, H, h, w, D))
+                   if not args.from_images else
+                   ("%s: 1 ref + %d src, %dx%d IMAGES in, FEM (fp32 CUDA-core first path) -> %dx%dx32 features, D=%d, "
+                    "stages I (siamese) + II + x4 soft-argmin; refinement not included" % (workload, nv - 1, W, H, h, w, D)),
                    "frames_per_step": maps_per_step,
                    "parallelism": ("source views sharded over %d ranks; NCCL all-reduce(max, bf16) + reduce-scatter(sum, fp32) + all-gather(result)" % world) if sharded
                    else ("dp%d: independent frames per rank, no collective" % world),
@@ -443,6 +455,8 @@ def main():
     ap.add_argument('--raw-dtype', default='f16', choices=['f16', 'f32'],
                     help='storage of the raw (pre-BN) convolution outputs on the bf16 path')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--from-images', action='store_true',
+                    help='start from images: include the 2-D feature extraction module (fp32 first path) in the step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
 
