@@ -17,12 +17,13 @@ struct Conv2dParams {
     int tiles_x, tiles_y;
 };
 
-constexpr int C2_TW = 32, C2_TH = 8, C2_CO = 32, C2_KC = 16;
+constexpr int C2_TH = 8, C2_CO = 32, C2_KC = 16;      // tile: 8 rows x (8 * PX) pixels, 32 output channels
 
-// block = 256 threads = 64 pixel quads (4 consecutive x) x 4 groups of 8 output channels; one 8 x 32 pixel tile and
-// 32 output channels per block.  Per (tap, 16-channel chunk) the weights [16][32] are staged in shared memory; a thread
-// does 128 FMAs per 4 input float4 loads and 8 weight LDS.128.
-template <int K>
+// block = 256 threads = 64 pixel groups (PX consecutive x) x 4 groups of 8 output channels; one 8 x (8*PX) pixel tile
+// and 32 output channels per block.  Per (tap, 16-channel chunk) the weights [16][32] are staged in shared memory; a
+// thread does PX*32 FMAs per PX input float4 loads and 8 weight LDS.128.  PX = 4 for the large maps, PX = 2 when that
+// would leave the SMs with about one block each (the 1/4-resolution layers: occupancy 14 % with PX = 4).
+template <int K, int PX>
 __global__ void __launch_bounds__(256)
 k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               const Conv2dParams p, float* __restrict__ out) {
@@ -37,10 +38,10 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
     const int b = tile / p.tiles_y;
     const int co0 = blockIdx.y * C2_CO;
     const int oy = ty * C2_TH + qy;
-    const int ox0 = tx * C2_TW + qx * 4;
-    float acc[4][8];
+    const int ox0 = tx * (8 * PX) + qx * PX;
+    float acc[PX][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < PX; ++j)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
     const bool vec = (p.Cin & 3) == 0;
@@ -49,10 +50,10 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
         const int ky = tap / K, kx = tap % K;
         const int iy = oy * p.stride - p.pad_t + ky * p.rate;
         const bool yok = oy < p.Ho && iy >= 0 && iy < p.H;
-        int ix[4];
-        bool ok[4];
+        int ix[PX];
+        bool ok[PX];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < PX; ++j) {
             ix[j] = (ox0 + j) * p.stride - p.pad_l + kx * p.rate;
             ok[j] = yok && (ox0 + j) < p.Wo && ix[j] >= 0 && ix[j] < p.W;
         }
@@ -68,9 +69,9 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
 #pragma unroll
             for (int c4 = 0; c4 < C2_KC; c4 += 4) {
                 if (c0 + c4 >= p.Cin) break;
-                float in[4][4];
+                float in[PX][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < PX; ++j) {
                     if (!ok[j]) {
                         in[j][0] = in[j][1] = in[j][2] = in[j][3] = 0.f;
                     } else if (vec) {
@@ -87,7 +88,7 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
                     const float4 w0 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8]);
                     const float4 w1 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8 + 4]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < PX; ++j) {
                         const float a = in[j][cc];
                         acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
                         acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
@@ -101,7 +102,7 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
     if (oy >= p.Ho) return;
     const int co = co0 + cg * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PX; ++j) {
         const int ox = ox0 + j;
         if (ox >= p.Wo) continue;
         float* o = out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + co;
@@ -185,6 +186,38 @@ k_avg_pool_same(const float* __restrict__ x, int B, int H, int W, int C, int k, 
     }
 }
 
+// the SPP windows are up to 64 x 64 (the whole map) with a handful of outputs: gridDim.y blocks share one output pixel,
+// each block splits its part of the window over 256 / C thread groups (consecutive threads = consecutive channels:
+// coalesced rows), reduces through shared memory and adds its share to the (pre-zeroed) output
+__global__ void __launch_bounds__(256)
+k_avg_pool_same_block(const float* __restrict__ x, int H, int W, int C, int k, int s, int pad_t, int pad_l, int Ho, int Wo,
+                      float* __restrict__ out) {
+    __shared__ float sh[256];
+    int o = blockIdx.x;
+    const int ox = o % Wo;
+    o /= Wo;
+    const int oy = o % Ho;
+    const int b = o / Ho;
+    const int G = 256 / C;
+    const int c = threadIdx.x % C, g = threadIdx.x / C;
+    const int y0 = max(oy * s - pad_t, 0), y1 = min(oy * s - pad_t + k, H);
+    const int x0 = max(ox * s - pad_l, 0), x1 = min(ox * s - pad_l + k, W);
+    const int ww = x1 - x0, nwin = (y1 - y0) * ww;
+    float acc = 0.f;
+    if (g < G)
+        for (int i = blockIdx.y * G + g; i < nwin; i += G * gridDim.y) {
+            const int y = y0 + i / ww, xx = x0 + i % ww;
+            acc += x[(((size_t)b * H + y) * W + xx) * C + c];
+        }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float tot = 0.f;
+        for (int q = 0; q < G; ++q) tot += sh[q * C + threadIdx.x];
+        atomicAdd(&out[(((size_t)b * Ho + oy) * Wo + ox) * C + threadIdx.x], tot / (float)nwin);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_resize_bilinear_align(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ out) {
     const long long n = (long long)B * Ho * Wo * C;
@@ -229,12 +262,18 @@ extern "C" int atvs_conv2d_fp32(const float* x, const float* kernel, const float
     Conv2dParams p;
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
     p.stride = stride; p.rate = rate; p.pad_t = pad_top; p.pad_l = pad_left; p.relu = relu;
-    p.tiles_x = (Wo + C2_TW - 1) / C2_TW;
     p.tiles_y = (Ho + C2_TH - 1) / C2_TH;
-    dim3 grid((unsigned)((long long)B * p.tiles_x * p.tiles_y), (unsigned)((Cout + C2_CO - 1) / C2_CO));
+    const int slabs = (Cout + C2_CO - 1) / C2_CO;
+    // 4 pixels per thread unless that leaves fewer than ~4 blocks per SM
+    int px = 4;
+    if ((long long)B * ((Wo + 31) / 32) * p.tiles_y * slabs < 3LL * atvs_num_sms()) px = 2;
+    p.tiles_x = (Wo + 8 * px - 1) / (8 * px);
+    dim3 grid((unsigned)((long long)B * p.tiles_x * p.tiles_y), (unsigned)slabs);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ksize == 1) k_conv2d_fp32<1><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
-    else k_conv2d_fp32<3><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    if (ksize == 1 && px == 4) k_conv2d_fp32<1, 4><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else if (ksize == 1) k_conv2d_fp32<1, 2><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else if (px == 4) k_conv2d_fp32<3, 4><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else k_conv2d_fp32<3, 2><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -266,8 +305,17 @@ extern "C" int atvs_avg_pool_same(const float* x, int B, int H, int W, int C, in
     int th = (Ho - 1) * stride + ksize - H, tw = (Wo - 1) * stride + ksize - W;
     if (th < 0) th = 0;
     if (tw < 0) tw = 0;
-    k_avg_pool_same<<<ew_grid((long long)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, ksize, stride, th / 2,
-                                                                                        tw / 2, Ho, Wo, out);
+    if (C <= 256 && ksize * ksize >= 64) {
+        int splits = (ksize * ksize + 255) / 256;          // <= ~128 window pixels per thread group
+        if (splits > 64) splits = 64;
+        cudaStream_t st = (cudaStream_t)stream;
+        ATVS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * Ho * Wo * C, st));
+        k_avg_pool_same_block<<<dim3((unsigned)((long long)B * Ho * Wo), (unsigned)splits), 256, 0, st>>>(
+            x, H, W, C, ksize, stride, th / 2, tw / 2, Ho, Wo, out);
+    }
+    else
+        k_avg_pool_same<<<ew_grid((long long)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, ksize, stride,
+                                                                                            th / 2, tw / 2, Ho, Wo, out);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
