@@ -46,7 +46,22 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
         for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
     const bool vec = (p.Cin & 3) == 0;
     const float* xb = x + (size_t)b * p.H * p.W * p.Cin;
-    for (int tap = 0; tap < K * K; ++tap) {
+    // flattened (tap, 16-channel chunk) loop; the weights of step it+1 are fetched into registers while step it computes
+    const int nch = (p.Cin + C2_KC - 1) / C2_KC;
+    const int nit = K * K * nch;
+    float wnext[2];
+    auto fetch = [&](int it) {
+        const int tap = it / nch, c0 = (it - tap * nch) * C2_KC;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = t + r * 256;
+            const int ci = i / C2_CO, co = i % C2_CO;
+            wnext[r] = (c0 + ci < p.Cin && co0 + co < p.Cout) ? __ldg(w + ((size_t)tap * p.Cin + c0 + ci) * p.Cout + co0 + co) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int it = 0; it < nit; ++it) {
+        const int tap = it / nch, c0 = (it - tap * nch) * C2_KC;
         const int ky = tap / K, kx = tap % K;
         const int iy = oy * p.stride - p.pad_t + ky * p.rate;
         const bool yok = oy < p.Ho && iy >= 0 && iy < p.H;
@@ -57,44 +72,42 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
             ix[j] = (ox0 + j) * p.stride - p.pad_l + kx * p.rate;
             ok[j] = yok && (ox0 + j) < p.Wo && ix[j] >= 0 && ix[j] < p.W;
         }
-        for (int c0 = 0; c0 < p.Cin; c0 += C2_KC) {
-            __syncthreads();
-            for (int i = t; i < C2_KC * C2_CO; i += 256) {
-                const int ci = i / C2_CO, co = i % C2_CO;
-                float v = 0.f;
-                if (c0 + ci < p.Cin && co0 + co < p.Cout) v = __ldg(w + ((size_t)tap * p.Cin + c0 + ci) * p.Cout + co0 + co);
-                ws[ci][co] = v;
-            }
-            __syncthreads();
+        __syncthreads();
 #pragma unroll
-            for (int c4 = 0; c4 < C2_KC; c4 += 4) {
-                if (c0 + c4 >= p.Cin) break;
-                float in[PX][4];
+        for (int r = 0; r < 2; ++r) {
+            const int i = t + r * 256;
+            ws[i / C2_CO][i % C2_CO] = wnext[r];
+        }
+        __syncthreads();
+        if (it + 1 < nit) fetch(it + 1);
+#pragma unroll
+        for (int c4 = 0; c4 < C2_KC; c4 += 4) {
+            if (c0 + c4 >= p.Cin) break;
+            float in[PX][4];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                if (!ok[j]) {
+                    in[j][0] = in[j][1] = in[j][2] = in[j][3] = 0.f;
+                } else if (vec) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4));
+                    in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][3] = v.w;
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        in[j][cc] = (c0 + c4 + cc < p.Cin) ? __ldg(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4 + cc) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8 + 4]);
 #pragma unroll
                 for (int j = 0; j < PX; ++j) {
-                    if (!ok[j]) {
-                        in[j][0] = in[j][1] = in[j][2] = in[j][3] = 0.f;
-                    } else if (vec) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4));
-                        in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc)
-                            in[j][cc] = (c0 + c4 + cc < p.Cin) ? __ldg(xb + ((size_t)iy * p.W + ix[j]) * p.Cin + c0 + c4 + cc) : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8]);
-                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8 + 4]);
-#pragma unroll
-                    for (int j = 0; j < PX; ++j) {
-                        const float a = in[j][cc];
-                        acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
-                        acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
-                        acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
-                        acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
-                    }
+                    const float a = in[j][cc];
+                    acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
+                    acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
+                    acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
+                    acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
                 }
             }
         }
