@@ -45,6 +45,20 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, 0, None, None) == -5      # Cin
     assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, 0, None, None) == -3      # odd D, stride 2
     assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 16, 8, 1, 0, p, 1, None, None) == -2   # raw dtype must be f32 | f16
+    # entry points added in round 1: raw dtype / view table / dual head / FEM validation before any launch
+    assert lib.atvs_bn_relu_add(p, 7, p, 8, 8, 1e-3, 1, None, None, p, None, 0, None) == -2              # raw dtype
+    assert lib.atvs_attention_raw(p, 0, None, 2, 8, 8, 0, 0, None, p, None) == -4                        # views NULL
+    assert lib.atvs_attention_raw(p, 0, p, 9, 8, 8, 0, 0, None, p, None) == -1                           # N > 8
+    assert lib.atvs_conv3d_bf16_dual_supported(1, 16, 64, 80, 8) == 1
+    assert lib.atvs_conv3d_bf16_dual_supported(1, 15, 64, 80, 8) == 0                                    # odd D
+    assert lib.atvs_conv3d_bf16_dual_supported(1, 4, 8, 8, 8) == 0                                       # below ring size
+    assert lib.atvs_conv3d_bf16_dual(p, p, 1, 15, 64, 80, 8, None, None, p, p, 0, None, None, None) == -5
+    assert lib.atvs_dual_weight_bytes(8) == 5 * 2 * 144 * 16 and lib.atvs_dual_weight_bytes(32) == 18 * 2 * 96 * 16
+    assert lib.atvs_conv2d_fp32(p, p, None, 1, 8, 8, 4, 8, 5, 1, 1, 2, 2, 8, 8, 0, p, None) == -5        # kernel size 5
+    assert lib.atvs_conv2d_fp32(None, p, None, 1, 8, 8, 4, 8, 3, 1, 1, 1, 1, 8, 8, 0, p, None) == -4
+    assert lib.atvs_channel_moments(p, 0, 8, p, None) == -1 and lib.atvs_bn2d_apply(p, None, None, 4, 8, 1e-3, 0, p, None) == -4
+    assert lib.atvs_avg_pool_same(p, 1, 8, 8, 4, 0, 1, p, None) == -1
+    assert lib.atvs_resize_bilinear_align(p, 1, 8, 8, 4, 0, 4, p, None) == -1
     # per-tap TMA image + halo-ring images (stride 1, and stride 2 for Cin <= 32)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 36 * 2 * 96 * 16
     assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16 + 5 * 2 * 48 * 16
