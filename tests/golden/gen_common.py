@@ -60,3 +60,21 @@ def fem_weights(seed=7):
         else:
             w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
     return w
+
+
+def named_weights(json_name, seed):
+    """seeded weights for a recorded variable list (name -> shape JSON next to this file): He-normal kernels (4-D and
+    5-D; transposed-conv kernels [..,Cout,Cin] use fan-in of their LAST axis), small biases / betas."""
+    import json
+    import os
+    shapes = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), json_name)))
+    w = {}
+    for i, (name, shape) in enumerate(sorted(shapes.items())):
+        rng = np.random.default_rng([seed, i])
+        shape = tuple(shape)
+        if len(shape) >= 4:
+            fan_in = np.prod(shape[:-2]) * (shape[-1] if 'transpose' in name else shape[-2])
+            w[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        else:
+            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+    return w

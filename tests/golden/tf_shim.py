@@ -137,7 +137,7 @@ def _layers_conv3d(inputs, filters, kernel_size, strides=1, activation=None, use
                    trainable=True, reuse=None, name=None, kernel_initializer=None, dilation_rate=1):
     assert padding == 'SAME' and not use_bias and dilation_rate == 1
     with _Ctx(name or 'conv3d', push=True):
-        w = _var('kernel', (kernel_size,) * 3 + (inputs.shape[-1], filters))
+        w = _var2('kernel', (kernel_size,) * 3 + (inputs.shape[-1], filters), 'kernel')
     y = _conv3d(inputs, w, strides)
     return activation(y) if activation else y
 
@@ -146,7 +146,7 @@ def _layers_conv3d_transpose(inputs, filters, kernel_size, strides=1, activation
                              padding='SAME', trainable=True, reuse=None, name=None, kernel_initializer=None):
     assert padding == 'SAME' and not use_bias
     with _Ctx(name or 'conv3d_transpose', push=True):
-        w = _var('kernel', (kernel_size,) * 3 + (filters, inputs.shape[-1]))
+        w = _var2('kernel', (kernel_size,) * 3 + (filters, inputs.shape[-1]), 'kernel')
     y = _conv3d_transpose(inputs, w, strides)
     return activation(y) if activation else y
 
