@@ -39,6 +39,10 @@ _SIGS = {
     "atvs_bn2d_apply": [_p, _p, _p, _ll, _i, _f, _i, _p, _p],
     "atvs_avg_pool_same": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_resize_bilinear_align": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "atvs_transform_depth": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "atvs_refine_geo_group": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "atvs_refine_photo_group": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "atvs_visual_hull": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",

@@ -858,9 +858,179 @@ k_prob2depth_up_sliced(const float* __restrict__ vol, int B, int D, int H, int W
     }
 }
 
+// ------------------------------------------------------------------ refinement stage geometry
+// transform_depth, homography_warping.py:275-326: depth of the LEFT view re-expressed in the RIGHT camera, on the
+// left pixel grid.  mv = (mat (9), vec (3)) from k_bydepth_setup(left, right).  The reference's clip upper bounds
+// (tf.reduce_max of the clipped tensor itself) never bind.
+__global__ void k_transform_depth(const float* __restrict__ depth, const float* __restrict__ mv, int B, int H, int W,
+                                  int inverse_depth, float* __restrict__ out) {
+    const long long n = (long long)B * H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
+    const float* m = mv + (size_t)b * 12;
+    float d = depth[i];
+    const bool valid = d > 1e-10f;
+    if (inverse_depth) {
+        d = fmaxf(d, 1e-10f);
+        d = DIV(1.0f, d);
+        d = MUL(d, valid ? 1.0f : 0.0f);
+    }
+    const float px = MUL(ADD((float)x, 0.5f), d), py = MUL(ADD((float)y, 0.5f), d);
+    float z = ADD(ADD(ADD(MUL(m[6], px), MUL(m[7], py)), MUL(m[8], d)), m[11]);
+    if (inverse_depth) {
+        z = fmaxf(z, 1e-10f);
+        z = DIV(1.0f, z);
+        z = MUL(z, valid ? 1.0f : 0.0f);
+    }
+    out[i] = z;
+}
+
+// geo_group of model.py:286-326, 328-337 in one pass: (B,D,H,W,1+C+2) =
+//   [ |d_ref - v| / di / D | (|warp(d_view_t, H_d) - v| / di / D) * mask, repeated C times (the reference tiles the mask to
+//     the C feature channels) | |wg - d_ref| * wg_mask | d_ref ],   v = start + d * interval
+__global__ void __launch_bounds__(256)
+k_refine_geo_group(const float* __restrict__ d_ref, const float* __restrict__ d_view_t, const float* __restrict__ hv,
+                   const float* __restrict__ wg, const uint8_t* __restrict__ wg_mask, const float* __restrict__ dstart,
+                   const float* __restrict__ dint, int B, int D, int H, int W, int C, float* __restrict__ out) {
+    const long long n = (long long)B * D * H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int d = (int)((i / ((long long)W * H)) % D), b = (int)(i / ((long long)W * H * D));
+    const size_t pix = ((size_t)b * H + y) * W + x;
+    const float ds = dstart[b], di = dint[b];
+    const float val = ADD(ds, MUL((float)d, di));
+    const float dr = d_ref[pix];
+    const float g_ref = DIV(DIV(fabsf(SUB(dr, val)), di), (float)D);
+    float u, v;
+    homography_uv(hv + ((size_t)b * D + d) * 9, x, y, u, v);
+    const Sample sm = make_sample(u, v, H, W);
+    const float wd = sample1(sm, d_view_t + (size_t)b * H * W, W, 1, 0);
+    const float g_view = MUL(DIV(DIV(fabsf(SUB(wd, val)), di), (float)D), sm.valid ? 1.0f : 0.0f);
+    const float g_err = MUL(fabsf(SUB(wg[pix], dr)), wg_mask[pix] ? 1.0f : 0.0f);
+    float* o = out + (size_t)i * (C + 3);
+    o[0] = g_ref;
+    for (int c = 0; c < C; ++c) o[1 + c] = g_view;
+    o[C + 1] = g_err;
+    o[C + 2] = dr;
+}
+
+// photo_group of model.py:269-281, 309-312, 328-336: (B,D,H,W,3C) = [L1 cost volume | |wf - ref_f| * mask | ref_f]
+__global__ void __launch_bounds__(256)
+k_refine_photo_group(const float* __restrict__ cost_photo, const float* __restrict__ wf, const uint8_t* __restrict__ mask,
+                     const float* __restrict__ ref_f, long long nvox, long long plane, int C, float* __restrict__ out) {
+    const long long n = nvox * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long vox = i / C;
+        const int c = (int)(i % C);
+        const long long b = vox / plane;                       // plane = D*H*W, pixels per batch element = H*W
+        (void)b;
+        out[vox * 3 * C + c] = cost_photo[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_refine_photo_tail(const float* __restrict__ wf, const uint8_t* __restrict__ mask, const float* __restrict__ ref_f, int B,
+                    int D, long long hw, int C, float* __restrict__ out) {
+    const long long n = (long long)B * D * hw * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long vox = i / C;
+        const long long p = vox % hw;
+        const long long b = vox / (hw * D);
+        const size_t pix = (size_t)b * hw + p;
+        const float r = ref_f[pix * C + c];
+        out[vox * 3 * C + C + c] = MUL(fabsf(SUB(wf[pix * C + c], r)), mask[pix] ? 1.0f : 0.0f);
+        out[vox * 3 * C + 2 * C + c] = r;
+    }
+}
+
+// get_visual_hull, homography_warping.py:329-387, for view_num = 2 (the only use: model.py:321-323 with num_depths = 2):
+// (B,D,H,W,1) = ([ref > 0][ref beyond plane] + [w > 0][w beyond plane]) / 2, w = nearest warp of the transformed depth
+__global__ void __launch_bounds__(256)
+k_visual_hull2(const float* __restrict__ ref_depth, const float* __restrict__ trans, const float* __restrict__ hv,
+               const float* __restrict__ dstart, const float* __restrict__ dint, int B, int D, int H, int W, int inverse_depth,
+               float* __restrict__ out) {
+    const long long n = (long long)B * D * H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int d = (int)((i / ((long long)W * H)) % D), b = (int)(i / ((long long)W * H * D));
+    const float val = ADD(dstart[b], MUL(dint[b], (float)d));
+    const float r = ref_depth[((size_t)b * H + y) * W + x];
+    float hull = (r > 0.0f && (inverse_depth ? r > val : val > r)) ? 1.0f : 0.0f;
+    float u, v;
+    homography_uv(hv + ((size_t)b * D + d) * 9, x, y, u, v);
+    int x0, y0;
+    bool valid;
+    nearest_cell(u, v, H, W, x0, y0, valid);
+    const float wd = trans[((size_t)b * H + y0) * W + x0];
+    hull += (wd > 0.0f && (inverse_depth ? wd > val : val > wd)) ? 1.0f : 0.0f;
+    out[i] = DIV(hull, 2.0f);
+}
+
 }  // namespace
 
 // =========================================================================== C ABI
+extern "C" int atvs_transform_depth(const float* depth, const float* left_cam, const float* right_cam, int B, int H, int W,
+                                    int inverse_depth, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(depth && left_cam && right_cam && out, ATVS_E_NULL, "atvs_transform_depth: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_transform_depth: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* mv = nullptr;
+    ATVS_CUDA(cudaMallocAsync(&mv, sizeof(float) * 12 * B, st));
+    k_bydepth_setup<<<(B + 63) / 64, 64, 0, st>>>(left_cam, right_cam, B, mv);
+    const long long n = (long long)B * H * W;
+    k_transform_depth<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(depth, mv, B, H, W, inverse_depth, out);
+    ATVS_CUDA(cudaFreeAsync(mv, st));
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_refine_geo_group(const float* d_ref, const float* d_view_trans, const float* homographies, const float* wg,
+                                     const uint8_t* wg_mask, const float* depth_start, const float* depth_interval, int B,
+                                     int D, int H, int W, int C, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(d_ref && d_view_trans && homographies && wg && wg_mask && depth_start && depth_interval && out, ATVS_E_NULL,
+                   "atvs_refine_geo_group: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 1 && W > 1 && C > 0, ATVS_E_SHAPE, "atvs_refine_geo_group: bad shape");
+    const long long n = (long long)B * D * H * W;
+    k_refine_geo_group<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_ref, d_view_trans, homographies, wg, wg_mask,
+                                                                                   depth_start, depth_interval, B, D, H, W, C, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_refine_photo_group(const float* cost_photo, const float* warped_feature, const uint8_t* mask,
+                                       const float* ref_feature, int B, int D, int H, int W, int C, float* out,
+                                       atvs_stream_t stream) {
+    ATVS_CHECK_ARG(cost_photo && warped_feature && mask && ref_feature && out, ATVS_E_NULL, "atvs_refine_photo_group: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0, ATVS_E_SHAPE, "atvs_refine_photo_group: bad shape");
+    const long long nvox = (long long)B * D * H * W;
+    long long g = (nvox * C + 255) / 256;
+    const long long cap = (long long)atvs_num_sms() * 8;
+    if (g > cap) g = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_refine_photo_group<<<(unsigned)g, 256, 0, st>>>(cost_photo, warped_feature, mask, ref_feature, nvox, (long long)D * H * W, C, out);
+    k_refine_photo_tail<<<(unsigned)g, 256, 0, st>>>(warped_feature, mask, ref_feature, B, D, (long long)H * W, C, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_visual_hull(const float* ref_depth, const float* trans_depth, const float* homographies,
+                                const float* depth_start, const float* depth_interval, int B, int D, int H, int W,
+                                int view_num, int inverse_depth, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(ref_depth && trans_depth && homographies && depth_start && depth_interval && out, ATVS_E_NULL,
+                   "atvs_visual_hull: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 1 && W > 1, ATVS_E_SHAPE, "atvs_visual_hull: bad shape");
+    ATVS_CHECK_ARG(view_num == 2, ATVS_E_UNSUP, "atvs_visual_hull: view_num=%d (the refinement stage uses 2)", view_num);
+    const long long n = (long long)B * D * H * W;
+    k_visual_hull2<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref_depth, trans_depth, homographies, depth_start,
+                                                                               depth_interval, B, D, H, W, inverse_depth, out);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int atvs_get_homographies(const float* left_cam, const float* right_cam, int B, int D,
                                      const float* depth_start, const float* depth_interval, int inverse_depth,
                                      float* out, atvs_stream_t stream) {

@@ -191,6 +191,28 @@ int atvs_avg_pool_same(const float* x, int B, int H, int W, int C, int ksize, in
 int atvs_resize_bilinear_align(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out,
                                atvs_stream_t stream);
 
+/* ---- refinement-stage geometry (stage III) ----- homography_warping.py:275-387, model.py:269-337
+ * fp32 first path.  atvs_transform_depth: depth (B,H,W) of the left view re-expressed in the right camera, on the left
+ *   pixel grid (inverse depth in and out when inverse_depth).
+ * atvs_refine_geo_group: (B,D,H,W,C+3) = [ |d_ref - v|/di/D | (|bilinear warp(d_view_trans, H_d) - v|/di/D)*mask x C |
+ *   |wg - d_ref|*wg_mask | d_ref ], v = start + d*interval; wg / wg_mask = nearest by-depth warp of d_view_trans
+ *   (atvs_homography_warping_by_depth); the C-fold repetition is the reference's tiled mask (C = 16 -> 19 channels).
+ * atvs_refine_photo_group: (B,D,H,W,3C) = [cost_photo (B,D,H,W,C) from atvs_build_cost_volume(L1_MASKED) |
+ *   |warped_feature - ref_feature|*mask tiled over D | ref_feature tiled over D].
+ * atvs_visual_hull: (B,D,H,W) for view_num = 2: ([ref>0][ref beyond plane] + [w>0][w beyond plane]) / 2 with w the
+ *   nearest homography warp of trans_depth by H_d.                                                            */
+int atvs_transform_depth(const float* depth, const float* left_cam, const float* right_cam, int B, int H, int W,
+                         int inverse_depth, float* out, atvs_stream_t stream);
+int atvs_refine_geo_group(const float* d_ref, const float* d_view_trans, const float* homographies, const float* wg,
+                          const uint8_t* wg_mask, const float* depth_start, const float* depth_interval, int B, int D,
+                          int H, int W, int C, float* out, atvs_stream_t stream);
+int atvs_refine_photo_group(const float* cost_photo, const float* warped_feature, const uint8_t* mask,
+                            const float* ref_feature, int B, int D, int H, int W, int C, float* out,
+                            atvs_stream_t stream);
+int atvs_visual_hull(const float* ref_depth, const float* trans_depth, const float* homographies,
+                     const float* depth_start, const float* depth_interval, int B, int D, int H, int W, int view_num,
+                     int inverse_depth, float* out, atvs_stream_t stream);
+
 /* ---- prob2depth / get_propability_map / prob2depth_upsample -------- model.py:80-129, 13-76
  * prob_volume (B,D,H,W) f32 logits; softmax over D of -logit, expectation against
  * linspace(start, start+(D-1)*interval, D) -> depth (B,H*up,W*up) f32; prob_map (same shape,
