@@ -184,6 +184,36 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     return out
 
 
+def run_example_schedule(images, cams, depth_num, features=None):
+    """The whole four-stage schedule of example.py:144-181 on the device, images in:
+      I   per source view: FEM features -> TVSNet_base_siamese -> (filtered cost, prob volume, depth_view)
+      II  AAM1 (keepchannel) -> output_conv -> prob2depth                              (run_multiview)
+      III per source view: TVSNet_refine(depth_agg_init, depth_view_n, prob_agg, cost_agg, images, cams)   (refine.py, fp32)
+      IV  AAM2 (keepchannel) -> output_conv_refine -> prob2depth_upsample -> final x4 inverse-depth map
+    images (B,N,H,W,3) fp32 0..255, cams (B,N,2,4,4) at feature resolution.  ``features`` (B,N,h,w,32) skips the FEM."""
+    from . import fem, refine
+    from .atvsnet import OutputConv_refine
+    L.require_cuda(images, cams)
+    cams = L.f32c(cams)
+    feats = features if features is not None else fem.extract_features(images)
+    out = run_multiview(feats, cams, depth_num, siamese=True, upsample=False)
+    ds = cams[:, 0, 1, 3, 0].contiguous()
+    di = cams[:, 0, 1, 3, 1].contiguous()
+    n_views = cams.shape[1]
+    refined_costs, refined_probs = [], []
+    for n, v in enumerate(range(1, n_views)):
+        rp, rc = refine.TVSNet_refine(out['depth'], out['depth_views'][n], out['prob_volume_agg'], out['cost_volume_agg'],
+                                      images, cams, depth_num, ds, di, v)
+        refined_probs.append(rp)
+        refined_costs.append(rc)
+    cost_ref = N.attention_aggregation(refined_costs, 'attention_aggregate_refine')
+    prob_ref = OutputConv_refine({'data': cost_ref}).get_output().squeeze(-1)
+    out['depth_refined'], _ = _prob2depth(prob_ref, ds, di, 1, False)
+    out['depth_refined_up'], _ = _prob2depth(prob_ref, ds, di, 4, False)
+    out.update(refined_cost_volume_agg=cost_ref, refined_prob_volume_agg=prob_ref, refined_prob_volumes=refined_probs)
+    return out
+
+
 class FrameStream(object):
     """Depth maps for a stream of frames that live in PINNED HOST memory (what a reader thread hands over): the step is
     captured once as a CUDA graph over fixed device buffers, and the host->device copy of frame i+1 and the

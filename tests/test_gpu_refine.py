@@ -65,3 +65,44 @@ def test_refinement_matches_reference_functions(A, g):
     assert rel(rp.cpu().numpy() - g['prob'], g['refined_prob'] - g['prob']) < 2e-4
     assert rel(rc.cpu().numpy() - g['cost'], g['refined_cost'] - g['cost']) < 2e-4
     assert grp['geo_group'].shape[-1] == 19 and grp['photo_group'].shape[-1] == 48
+
+
+def test_four_stage_schedule_fp32_against_oracle(A):
+    """example.py:144-181 end to end, images in: FEM -> stage I/II -> TVSNet_refine per source -> AAM2 -> x4 soft-argmin,
+    fp32 CUDA path against the same schedule composed from the CPU oracles."""
+    from gen_common import fem_weights, named_weights
+    from oracle import fem as ofem
+    from oracle import model as om
+    from oracle import refine as oref
+    rng = np.random.default_rng(17)
+    nv, H, W, D = 3, 32, 64, 8
+    h, w = H // 4, W // 4
+    imgs = (127.5 + 50 * rng.standard_normal((1, nv, H, W, 3))).clip(0, 255).astype(np.float32)
+    cams = A.synthetic.orbit_cams(nv, h, w, D)[None]
+    ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
+    allw = A.variables.synthetic_weights(seed=11, logit_gain=2.0)
+    allw.update(fem_weights(7))
+    allw.update(named_weights('refine_variables.json', 5))
+    # ---- oracle schedule
+    feats = np.stack([ofem.ResNetDS2SPP(imgs[:, n], allw)[0] for n in range(nv)])[None]
+    s12 = om.run_multiview_stage12(feats, cams, D, allw, siamese=True)
+    rcs = []
+    for n, v in enumerate(range(1, nv)):
+        rp, rc = oref.TVSNet_refine(s12['depth_agg_init'], s12['depth_views'][n], s12['prob_volume_agg'],
+                                    s12['cost_volume_agg'], imgs, cams, D, ds, di, v, allw)
+        rcs.append(rc)
+    cref = om.cost_volume_aggregation_refine(np.stack(rcs, axis=-1), allw, keepchannel=True)
+    pref = om.output_conv_refine(cref, allw)
+    _, est_up = om.prob2depth_upsample(pref, D, ds, di)
+    # ---- CUDA schedule
+    A.variables.load_weights(allw)
+    A.FLAGS.precision = 'fp32'
+    try:
+        out = A.pipeline.run_example_schedule(cu(imgs), cu(cams), D)
+        torch.cuda.synchronize()
+    finally:
+        A.FLAGS.precision = 'bf16'
+    rng_ = float((D - 1) * di[0])
+    assert tuple(out['depth_refined_up'].shape) == est_up.shape
+    assert float(np.abs(out['depth'].cpu().numpy() - s12['depth_agg_init']).mean()) / rng_ < 1e-3
+    assert float(np.abs(out['depth_refined_up'].cpu().numpy() - est_up).mean()) / rng_ < 2e-3
