@@ -59,6 +59,10 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_channel_moments(p, 0, 8, p, None) == -1 and lib.atvs_bn2d_apply(p, None, None, 4, 8, 1e-3, 0, p, None) == -4
     assert lib.atvs_avg_pool_same(p, 1, 8, 8, 4, 0, 1, p, None) == -1
     assert lib.atvs_resize_bilinear_align(p, 1, 8, 8, 4, 0, 4, p, None) == -1
+    assert lib.atvs_transform_depth(p, p, None, 1, 4, 4, 1, p, None) == -4
+    assert lib.atvs_visual_hull(p, p, p, p, p, 1, 4, 4, 4, 3, 1, p, None) == -5                        # view_num must be 2
+    assert lib.atvs_refine_geo_group(p, p, p, p, p, p, p, 1, 4, 1, 4, 16, p, None) == -1               # H > 1
+    assert lib.atvs_refine_photo_group(p, p, None, p, 1, 4, 4, 4, 16, p, None) == -4
     # per-tap TMA image + halo-ring images (stride 1, and stride 2 for Cin <= 32)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 36 * 2 * 96 * 16
     assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16 + 5 * 2 * 48 * 16
