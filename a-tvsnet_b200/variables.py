@@ -117,3 +117,46 @@ def synthetic_fem_weights(seed=4321):
         else:
             w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
     return w
+
+
+def refine_variable_shapes():
+    """name -> shape of the refinement-stage variables (shallow feature net model.py:143-154 / atvsnet.py:245-251 and
+    CostVolRefineNet atvsnet.py:295-336); tests/test_host_logic.py holds it equal to the list recorded from the
+    reference's own code (tests/golden/refine_variables.json)."""
+    s = {}
+    cin = 3
+    for i in range(3):
+        scope = 'global_refine_conv0_x' + ('_%d' % i if i != 2 else '')
+        s[scope + '/preact/beta'] = (cin,)
+        if cin != 16:
+            s[scope + '/shortcut/weights'] = (1, 1, cin, 16)
+            s[scope + '/shortcut/biases'] = (16,)
+        s[scope + '/conv1/weights'] = (1, 1, cin, 16)
+        s[scope + '/conv2/weights'] = (3, 3, 16, 16)
+        s[scope + '/conv3/weights'] = (1, 1, 16, 16)
+        for c in ('conv1', 'conv2', 'conv3'):
+            s[scope + '/' + c + '/biases'] = (16,)
+        cin = 16
+    s['global_refine_shallow_feature/kernel'] = (1, 1, 16, 16)
+    p = 'global_refine_'
+    for name, ci, co in (('photo_3dconv', 48, 8), ('geo_3dconv', 19, 8), ('prob_3dconv', 1, 8), ('vishull_3dconv', 1, 8),
+                         ('3dconv1_0', 32, 16), ('3dconv2_0', 16, 32), ('3dconv3_0', 32, 64), ('3dconv0_1', 32, 8),
+                         ('3dconv1_1', 16, 16), ('3dconv2_1', 32, 32), ('3dconv3_1', 64, 64)):
+        s[p + name + '/conv3d/kernel'] = (3, 3, 3, ci, co)
+    for name, ci, co in (('3dconv4_0', 64, 32), ('3dconv5_0', 32, 16), ('3dconv6_0', 16, 8)):
+        s[p + name + '/conv3d_transpose/kernel'] = (3, 3, 3, co, ci)
+    s['global_refined_cost_vol/kernel'] = (3, 3, 3, 8, 1)
+    return s
+
+
+def synthetic_refine_weights(seed=2468):
+    """seeded refinement-stage weights under the checkpoint names."""
+    w = {}
+    for i, (name, shape) in enumerate(sorted(refine_variable_shapes().items())):
+        rng = np.random.default_rng([seed, i])
+        if len(shape) >= 4:
+            fan_in = np.prod(shape[:-2]) * (shape[-1] if 'transpose' in name else shape[-2])
+            w[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        else:
+            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+    return w

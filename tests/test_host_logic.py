@@ -36,6 +36,14 @@ def test_fem_variable_names_equal_the_reference_graph_list():
     assert set(w) == set(rec) and all(w[k].shape == rec[k] and w[k].dtype == np.float32 for k in rec)
 
 
+def test_refine_variable_names_equal_the_reference_code_list():
+    import json
+    rec = {k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, 'tests', 'golden', 'refine_variables.json'))).items()}
+    assert A.variables.refine_variable_shapes() == rec
+    w = A.variables.synthetic_refine_weights()
+    assert set(w) == set(rec) and all(w[k].shape == rec[k] for k in rec)
+
+
 def test_flags_defaults_follow_reference():
     assert A.FLAGS.max_d == 128 and A.FLAGS.view_num == 5 and A.FLAGS.batch_size == 1
     assert A.FLAGS.inverse_depth is True and A.FLAGS.sample_scale == 0.25

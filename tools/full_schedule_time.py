@@ -1,16 +1,14 @@
 """time the whole four-stage example.py schedule (images in: FEM, stages I-IV) at cfg2, eager launches, per stage"""
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden'))
 import numpy as np
 import torch
 import atvsnet_b200 as A
-from gen_common import named_weights
 
 nv, H, W, D = 5, 512, 640, 128
 w = A.variables.synthetic_weights()
 w.update(A.variables.synthetic_fem_weights())
-w.update(named_weights('refine_variables.json', 5))
+w.update(A.variables.synthetic_refine_weights())
 A.variables.load_weights(w)
 rng = np.random.default_rng(0)
 imgs = torch.from_numpy((127.5 + 50 * rng.standard_normal((1, nv, H, W, 3))).clip(0, 255).astype(np.float32)).cuda()
