@@ -292,7 +292,10 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
     __stcs(reinterpret_cast<uint2*>(p), pk);
 }
 
-constexpr int K1_DCHUNK = 8;
+#ifndef ATVS_K1_DCHUNK
+#define ATVS_K1_DCHUNK 8      // depth planes per block of K1 (measured: 4 / 8 / 16)
+#endif
+constexpr int K1_DCHUNK = ATVS_K1_DCHUNK;
 
 // grid: x = pixel*channel-group tiles, y = depth chunks, z = batch.
 // one thread = one pixel x 4 channels, looping over K1_DCHUNK planes with the reference
