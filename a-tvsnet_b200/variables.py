@@ -160,3 +160,15 @@ def synthetic_refine_weights(seed=2468):
         else:
             w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
     return w
+
+
+def load_checkpoint(prefix, device='cuda'):
+    """restore every variable of a TensorFlow V2 checkpoint (``prefix.index`` / ``prefix.data-*``, example.py:121-125)
+    by name, without TensorFlow (ckpt.read_checkpoint): optimizer slots and non-float entries are ignored."""
+    from . import ckpt
+    w = {k: v for k, v in ckpt.read_checkpoint(prefix).items()
+         if v.dtype == np.float32 and not k.endswith(('/Adam', '/Adam_1', '/Momentum', '/RMSProp', '/RMSProp_1'))}
+    if not w:
+        raise RuntimeError("no float variables found in checkpoint %r" % prefix)
+    load_weights(w, device=device)
+    return sorted(w)
