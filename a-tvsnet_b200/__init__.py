@@ -5,9 +5,9 @@ libatvs.so; there is no CPU fallback."""
 from . import _lib, variables  # noqa: F401
 from .flags import FLAGS  # noqa: F401
 from .homography_warping import get_homographies, homography_warping, homography_warping_by_depth  # noqa: F401
-from .model import (TVSNet_base, TVSNet_base_siamese, build_cost_volume, cost_volume_aggregation,  # noqa: F401
-                    cost_volume_aggregation_refine, cost_volume_reasoning, output_conv, output_conv_refine,
-                    prob2depth, prob2depth_upsample)
+from .model import (TVSNet, TVSNet_base, TVSNet_base_siamese, TVSNet_feature_extraction, TVSNet_refine,  # noqa: F401
+                    build_cost_volume, cost_volume_aggregation, cost_volume_aggregation_refine, cost_volume_reasoning,
+                    output_conv, output_conv_refine, prob2depth, prob2depth_upsample)
 from .atvsnet import (AttAggregation, AttAggregation_keepchannel, AttAggregation_refine,  # noqa: F401
                       AttAggregation_refine_keepchannel, OutputConv, OutputConv_refine, StackedUNet,
                       StackedUNet_prob)

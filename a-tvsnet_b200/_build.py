@@ -22,6 +22,7 @@ SOURCES = {
     "conv_ring.cu": [],
     "conv_ring_s2.cu": [],
     "conv_deconv.cu": [],
+    "conv_deconv_ring.cu": [],
     "fem2d.cu": [],
 }
 

@@ -19,12 +19,9 @@ _SIGS = {
     "atvs_homography_warping_by_depth": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_build_cost_volume": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_conv3d_fp32": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
-    "atvs_pack_conv_weights_bf16": [_p, _i, _i, _i, _p, _p],
-    "atvs_conv3d_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
-    "atvs_conv3d_bf16_bias": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
-    "atvs_conv3d_bf16_dual": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p],
-    "atvs_conv3d_bf16_dual_supported": [_i, _i, _i, _i, _i],
-    "atvs_pack_conv_weights_dual": [_p, _i, _p, _p],
+    "atvs_pack_conv_weights_tc": [_p, _i, _i, _i, _i, _p, _p],
+    "atvs_conv3d_tc": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "atvs_conv3d_tc_bias": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
     "atvs_bn_relu_add": [_p, _i, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
     "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
@@ -46,7 +43,7 @@ _SIGS = {
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
-                                "atvs_packed_weight_bytes", "atvs_dual_weight_bytes", "atvs_launch_count"])
+                                "atvs_packed_weight_bytes", "atvs_launch_count"])
 
 
 def lib_path():
@@ -71,8 +68,6 @@ def load():
         lib.atvs_packed_weight_bytes.argtypes = [_i, _i, _i]
         lib.atvs_packed_weight_bytes.restype = C.c_size_t
         lib.atvs_launch_count.restype = C.c_longlong
-        lib.atvs_dual_weight_bytes.argtypes = [_i]
-        lib.atvs_dual_weight_bytes.restype = C.c_size_t
         _lib = lib
     return _lib
 
@@ -103,6 +98,8 @@ def dtype_code(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise RuntimeError("unsupported dtype %s" % t.dtype)
 
 

@@ -41,6 +41,11 @@ class StackedUNet_prob(Network):
         self.feed(p + '_6_0', p + '_0_1').add(name=joined)
 
     def setup(self):
+        shp = tuple(self.inputs['data'].shape)
+        if len(shp) != 5 or any(int(n) % 8 for n in shp[1:4]):
+            # three stride-2 convolutions, then three stride-2 transposed convolutions joined by `add`
+            # (atvsnet.py:104-128): TF raises a shape error at the first join otherwise
+            raise ValueError("StackedUNet: input must be (B,D,h,w,C) with D, h, w multiples of 8, got %s" % (shp,))
         for b in range(3):
             self._block(b)
         if self.with_prob:

@@ -24,6 +24,7 @@ struct DcParams {
     int ltd, lth, ltw, nTD, nTH, nTW;
     int Cout, ncols;
     int raw16;                     // raw output dtype: 0 fp32, 1 saturated fp16
+    uint32_t fmt;                  // operand format bits of the instruction descriptor (tc_fmt_bits)
     int nstages;
     int sh_off[8][3];              // shift s reads input voxel j + sh_off[s]
     int sh_first[9];               // pairs of shift s are [sh_first[s], sh_first[s+1])
@@ -60,7 +61,7 @@ k_deconv3d_tc(const __grid_constant__ DcMaps tm, const __grid_constant__ DcParam
     constexpr int WPAIR_BYTES = NPAD * CIN * 2;
     constexpr uint32_t ACC_COLS = 8 * NPAD;                 // one accumulator set (8 classes)
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;            // double buffered: 256 (N=16) or 512 (N=32)
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t IDESC = (1u << 4) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24) | p.fmt;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -246,14 +247,14 @@ __host__ __device__ inline PairTable make_pair_table() {
 }
 
 // weight image: [27 pairs, shift-major][NPAD rows (co)][Cin (k)] bf16 from the TF kernel [3,3,3,Cout,Cin]
-__global__ void k_pack_deconv(const float* __restrict__ w, int Cin, int Cout, int npad, __nv_bfloat16* __restrict__ out) {
+__global__ void k_pack_deconv(const float* __restrict__ w, int Cin, int Cout, int npad, int f16, unsigned short* __restrict__ out) {
     const PairTable t = make_pair_table();
     const int pr = blockIdx.x;
     const int kidx = t.pair_kidx[pr];
-    __nv_bfloat16* o = out + (size_t)pr * npad * Cin;
+    unsigned short* o = out + (size_t)pr * npad * Cin;
     for (int i = threadIdx.x; i < npad * Cin; i += blockDim.x) {
         const int n = i / Cin, k = i % Cin;
-        o[i] = __float2bfloat16_rn(n < Cout ? w[((size_t)kidx * Cout + n) * Cin + k] : 0.f);
+        o[i] = tc_cvt16(n < Cout ? w[((size_t)kidx * Cout + n) * Cin + k] : 0.f, f16);
     }
 }
 
@@ -281,13 +282,13 @@ bool deconv_fused_applicable(int Cin, int Cout) {
 
 size_t deconv_fused_weight_bytes(int Cin, int Cout) { return (size_t)27 * deconv_npad(Cout) * Cin * 2; }
 
-int deconv_fused_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st) {
-    k_pack_deconv<<<27, 128, 0, st>>>(kernel, Cin, Cout, deconv_npad(Cout), (__nv_bfloat16*)wimg);
+int deconv_fused_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cudaStream_t st) {
+    k_pack_deconv<<<27, 128, 0, st>>>(kernel, Cin, Cout, deconv_npad(Cout), dtype == ATVS_F16, (unsigned short*)wimg);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
 
-int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+int deconv_fused(const void* x_bf16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
                  int raw16, double* stats, cudaStream_t st) {
     EncodeTiledFn encode = get_encode();
     if (!encode) {
@@ -299,6 +300,7 @@ int deconv_fused(const void* x_bf16, const void* wimg, int B, int D, int H, int 
     memset(&p, 0, sizeof(p));
     p.B = B; p.Dj = D; p.Hj = H; p.Wj = W; p.Cout = Cout; p.ncols = Cout;
     p.raw16 = raw16;
+    p.fmt = tc_fmt_bits(dtype);
     {
         static const int opts[][3] = {{2, 8, 8}, {1, 8, 16}, {4, 4, 8}, {2, 4, 16}, {1, 4, 32}, {4, 8, 4}, {8, 4, 4},
                                       {1, 16, 8}, {2, 16, 4}, {8, 8, 2}, {16, 4, 2}, {32, 2, 2}, {8, 16, 1}, {16, 8, 1},

@@ -62,13 +62,7 @@ struct RingParams {
     int B, D, H, W;
     int Cout, coff, ncols;
     int raw16;          // raw output dtype: 0 fp32, 1 saturated fp16
-    // dual-head mode (CP = 32 only): columns [0,8) = the stride-1 head (out / stats / bias as usual), columns
-    // [8,24) = a STRIDE-2 16-channel convolution of the same input evaluated densely and kept at the odd
-    // positions only: out2[z',y',x'] = dense[2z'+1, 2y'+1, 2x'+1] (TF SAME on even extents = padding (0,1))
-    int dual;
-    void* out2;
-    double* stats2;
-    const float* bias2;
+    uint32_t fmt;       // operand format bits of the instruction descriptor (tc_fmt_bits)
     int nXT, nYT, nZS, ZS;
     int nring, pf;      // ring slots, planes of cp.async in flight per producer thread (pf <= nring - 1, <= 8)
     int wbytes;
@@ -81,12 +75,11 @@ struct RingCfg {
     static constexpr int NKC = CIN / 8;
     static constexpr int SLOT_BYTES = (NKC * RG_KCH_PAD + 127) / 128 * 128;
     static constexpr int NSTEPS = (CIN >= 16) ? 9 * (CIN / 16) : 5;     // K=16 MMA steps per input plane
-    // CP = 24 is the dual-head layout [8 stride-1 | 16 stride-2 columns] at two CTAs per SM (256 TMEM columns each)
-    static constexpr bool PAD = (CP == 8 || CP == 24);                  // runs are padded to N % 16 == 0 with zero weights
-    static constexpr int G = (CP == 8) ? 15 : (CP == 24 ? 5 : 8);       // accumulator groups in the ring
-    static constexpr int NROWS = (CP == 8) ? 64 : (CP == 24 ? 144 : 3 * CP);   // rows of one weight step image
+    static constexpr bool PAD = (CP == 8);                              // runs are padded to N % 16 == 0 with zero weights
+    static constexpr int G = (CP == 8) ? 15 : 8;                        // accumulator groups in the ring
+    static constexpr int NROWS = (CP == 8) ? 64 : 3 * CP;               // rows of one weight step image
     static constexpr int STEP_BYTES = 2 * NROWS * 16;
-    static constexpr uint32_t TILE_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy; CP=24: 5 groups + 8 dummy columns
+    static constexpr uint32_t TILE_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy
     static constexpr uint32_t TMEM_COLS = RG_MT * TILE_COLS;
 };
 
@@ -117,17 +110,9 @@ __device__ __forceinline__ int unit_iend(const RingParams& p, const Unit& u) {
 // weight-image window (in rows of 8) and MMA N for a run of `len` output planes whose first plane meets
 // the z tap `f` (2, 1 or 0; the following planes meet f-1, ...).
 //   CP = 8 image groups : [w2 0 w1 0 w2 w1 w0 0]      CP = 16, 32 : [w2 w1 w0]
-//   CP = 24 image rows  : [w2 w1 w0 0(8) | w2 0(8) | w1 0(8)]  (144 rows)
 template <int CP>
 __device__ __forceinline__ void ring_window(int f, int len, uint32_t& row_off_bytes, uint32_t& idesc) {
-    if (CP == 24) {
-        int row;
-        if (len == 3) row = 0;
-        else if (len == 2) row = (f == 2) ? 0 : 24;
-        else row = (f == 0) ? 48 : (f == 2 ? 80 : 112);
-        row_off_bytes = (uint32_t)row * 16u;
-        idesc = ring_idesc(len == 3 ? 80 : (len == 2 ? 48 : 32));
-    } else if (CP == 8) {
+    if (CP == 8) {
         int grp;
         if (len == 1) grp = (f == 2) ? 0 : (f == 1 ? 2 : 6);
         else if (len == 2) grp = (f == 2) ? 4 : 5;
@@ -142,7 +127,7 @@ __device__ __forceinline__ void ring_window(int f, int len, uint32_t& row_off_by
 
 template <int CIN, int CP, int MINB>
 __global__ void __launch_bounds__(RG_THREADS, MINB)
-k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingParams p,
+k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
               const float* __restrict__ bias) {
     using Cfg = RingCfg<CIN, CP>;
@@ -244,7 +229,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                 const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
                 goff[k] = (j >= Cfg::NKC * RG_NVOX) ? -2 : (ok ? (gy * p.W + gx) * CIN + c * 8 : -1);
             }
-            const __nv_bfloat16* zbase = x + ((size_t)un.b * p.D + (un.z0 - 1 + ibeg)) * zstride_in;
+            const uint16_t* zbase = x + ((size_t)un.b * p.D + (un.z0 - 1 + ibeg)) * zstride_in;
             for (int i = ibeg; i <= iend; ++i, zbase += zstride_in) {
                 mbar_wait(&empty[slot], sphase ^ 1);
                 TRACE(0);
@@ -255,7 +240,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                         const int j = ptid + k * RG_PRODUCERS;
                         const uint32_t soff = (uint32_t)((j % Cfg::NKC) * RG_KCH_PAD + (j / Cfg::NKC) * 16);
                         const bool ok = goff[k] >= 0;
-                        const __nv_bfloat16* src = ok ? zbase + goff[k] : x;
+                        const uint16_t* src = ok ? zbase + goff[k] : x;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + soff), "l"(src),
                                      "r"(ok ? 16 : 0)
                                      : "memory");
@@ -283,7 +268,7 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
         constexpr uint32_t B_HI = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = next 8 rows
         constexpr uint32_t A_LBO = (CIN >= 16) ? ((uint32_t)(RG_KCH_PAD >> 4) << 16) : 0u;
         constexpr uint32_t FAST_BOFF = (CP == 8) ? 4u * 128u : 0u;                      // window [w2 w1 w0 (0)]
-        constexpr uint32_t FAST_IDESC = ring_idesc(CP == 8 ? 32 : (CP == 24 ? 80 : 3 * CP));
+        const uint32_t FAST_IDESC = ring_idesc(CP == 8 ? 32 : 3 * CP) | p.fmt;
         const uint32_t a_lo_ring = (smem_u32(ring) >> 4) | A_LBO;
         const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | ((uint32_t)((Cfg::NROWS * 16) >> 4) << 16);
         auto issue_plane = [&](uint32_t dcol, uint32_t a_lo0, uint32_t b_lo, uint32_t idesc) {
@@ -341,10 +326,10 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                     const int len1 = min(len, G - (int)glo), len2 = len - len1;
                     uint32_t boff, idesc;
                     ring_window<CP>(f, len1, boff, idesc);
-                    issue_plane(tmem_base + glo * (uint32_t)CP, a_lo0, b_lo0 + (boff >> 4), idesc);
+                    issue_plane(tmem_base + glo * (uint32_t)CP, a_lo0, b_lo0 + (boff >> 4), idesc | p.fmt);
                     if (len2 > 0) {
                         ring_window<CP>(f - len1, len2, boff, idesc);
-                        issue_plane(tmem_base, a_lo0, b_lo0 + (boff >> 4), idesc);
+                        issue_plane(tmem_base, a_lo0, b_lo0 + (boff >> 4), idesc | p.fmt);
                     }
                 }
                 tc_commit(&empty[slot]);
@@ -438,44 +423,12 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                         }
                     }
                     store_raw_row<CP>(out, ooff, v[mt], p.ncols, vec, p.raw16);
-                    bool head2 = false;
-                    if constexpr (CP == 32 || CP == 24) if (p.dual) {
-                        head2 = (z & 1) && (y & 1) && (xm & 1);
-                        if (head2) {
-                            const int Do2 = p.D >> 1, Ho2 = p.H >> 1, Wo2 = p.W >> 1;
-                            const int z2 = z >> 1, y2 = y >> 1, x2 = xm >> 1;
-                            if (p.bias2 != nullptr) {
-                                const int zc2 = (z2 == 0) ? 0 : (z2 == Do2 - 1 ? 2 : 1);
-                                const float* b2 = p.bias2 + ((((size_t)un.b * 3 + zc2) * Ho2 + y2) * Wo2 + x2) * 16;
-#pragma unroll
-                                for (int c = 0; c < 16; c += 4) {
-                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(b2 + c));
-                                    v[mt][8 + c] += bv.x; v[mt][9 + c] += bv.y; v[mt][10 + c] += bv.z; v[mt][11 + c] += bv.w;
-                                }
-                            }
-                            const size_t off2 = ((((size_t)un.b * Do2 + z2) * Ho2 + y2) * Wo2 + x2) * 16;
-                            store_raw_row<16>(reinterpret_cast<float*>(p.out2), off2, v[mt] + 8, 16, 8, p.raw16);
-                        }
-                    }
                     if (stats != nullptr) {
                         // per-THREAD running moments (rows = this thread's voxels): no cross-lane traffic per tile
-                        bool done_stats = false;
-                        if constexpr (CP == 32 || CP == 24) if (p.dual) {
-                            // columns [0,8): every voxel; [8,24): the kept (odd) positions of the stride-2 head
 #pragma unroll
-                            for (int c = 0; c < 24; ++c) {
-                                const float q = (c < 8 || head2) ? v[mt][c] : 0.f;
-                                run[c] += q;
-                                run[CP + c] = fmaf(q, q, run[CP + c]);
-                            }
-                            done_stats = true;
-                        }
-                        if (!done_stats) {
-#pragma unroll
-                            for (int c = 0; c < CP; ++c) {
-                                run[c] += v[mt][c];
-                                run[CP + c] = fmaf(v[mt][c], v[mt][c], run[CP + c]);
-                            }
+                        for (int c = 0; c < CP; ++c) {
+                            run[c] += v[mt][c];
+                            run[CP + c] = fmaf(v[mt][c], v[mt][c], run[CP + c]);
                         }
                     }
                 }
@@ -491,8 +444,6 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
                 for (int off = 16; off >= 1; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
                 const int c = k % CP;
                 if (lane == 0 && c < p.ncols) atomicAdd(&stats[(k < CP ? 0 : p.Cout) + p.coff + c], (double)tot);
-                if ((CP == 32 || CP == 24) && p.dual && lane == 0 && c >= 8 && c < 24 && p.stats2 != nullptr)
-                    atomicAdd(&p.stats2[(k < CP ? 0 : 16) + c - 8], (double)tot);
             }
         }
     }
@@ -505,28 +456,19 @@ k_conv3d_ring(const __nv_bfloat16* __restrict__ x, const __grid_constant__ RingP
     }
 }
 
-// weight image of one Cout slab: [step][2 chunks][NROWS rows][8 channels] bf16; the rows are groups of
+// weight image of one Cout slab: [step][2 chunks][NROWS rows][8 channels] 16-bit; the rows are groups of
 // CP output channels, each group holding one z tap (or zeros), see ring_window()
-__global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int cp, int nslabs,
-                            __nv_bfloat16* __restrict__ out) {
+__global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int cp, int nslabs, int f16,
+                            unsigned short* __restrict__ out) {
     const int nsteps = ring_nsteps(Cin);
-    const int nrows = (cp == 8) ? 64 : (cp == 24 ? 144 : 3 * cp);
+    const int nrows = (cp == 8) ? 64 : 3 * cp;
     const int slab = blockIdx.x / nsteps, step = blockIdx.x % nsteps;
-    __nv_bfloat16* o = out + ((size_t)slab * nsteps + step) * 2 * nrows * 8;
+    unsigned short* o = out + ((size_t)slab * nsteps + step) * 2 * nrows * 8;
     for (int i = threadIdx.x; i < 2 * nrows * 8; i += blockDim.x) {
         const int chunk = i / (nrows * 8), r = (i / 8) % nrows, e = i % 8;
-        int grp = r / cp, n = r % cp;
+        const int grp = r / cp, n = r % cp;
         int dz;
-        if (cp == 24) {
-            // rows [w2 w1 w0 0(8) | w2 0(8) | w1 0(8)] of the dual-head image (columns 0..23 of a 32-column kernel)
-            if (r < 72) { dz = 2 - r / 24; n = r % 24; }
-            else if (r < 80) { dz = -1; n = 0; }
-            else if (r < 104) { dz = 2; n = r - 80; }
-            else if (r < 112) { dz = -1; n = 0; }
-            else if (r < 136) { dz = 1; n = r - 112; }
-            else { dz = -1; n = 0; }
-            grp = 0;
-        } else if (cp == 8) {
+        if (cp == 8) {
             const int map[8] = {2, -1, 1, -1, 2, 1, 0, -1};
             dz = map[grp];
         } else {
@@ -544,12 +486,12 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
         const int co = slab * cp + n;
         float val = 0.f;
         if (dz >= 0 && tap2d >= 0 && co < Cout) val = w[((size_t)(dz * 9 + tap2d) * Cin + k) * Cout + co];
-        o[i] = __float2bfloat16_rn(val);
+        o[i] = tc_cvt16(val, f16);
     }
 }
 
 template <int CIN, int CP, int MINB>
-int launch_ring(const __nv_bfloat16* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
+int launch_ring(const uint16_t* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
                 const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -562,24 +504,10 @@ int launch_ring(const __nv_bfloat16* x, const RingParams& p, const uint8_t* wimg
 }
 
 size_t ring_slab_bytes(int Cin, int cp) {
-    return (size_t)ring_nsteps(Cin) * 2 * ((cp == 8) ? 64 : (cp == 24 ? 144 : 3 * cp)) * 16;
+    return (size_t)ring_nsteps(Cin) * 2 * ((cp == 8) ? 64 : 3 * cp) * 16;
 }
 
 }  // namespace
-
-// dual-head launches: 24 columns per plane (two CTAs per SM) when the padded-window weight image fits next to a
-// few ring planes, else the plain 32-column layout (one CTA per SM)
-int ring_dual_cp(int Cin) {
-    if (const char* e = getenv("ATVS_DUAL_CP")) return atoi(e) == 24 ? 24 : 32;
-    return Cin <= 16 ? 24 : 32;
-}
-size_t ring_dual_weight_bytes(int Cin) { return ring_slab_bytes(Cin, ring_dual_cp(Cin)); }
-int ring_dual_pack(const float* kernel32, int Cin, void* wimg, cudaStream_t st) {
-    const int cp = ring_dual_cp(Cin);
-    k_pack_ring<<<ring_nsteps(Cin), 128, 0, st>>>(kernel32, Cin, 32, cp, 1, (__nv_bfloat16*)wimg);
-    ATVS_LAUNCH_CHECK();
-    return 0;
-}
 
 // columns per output plane: the smallest of {8, 16, 32} covering Cout (more output channels: slabs of 32)
 int ring_npad(int Cin, int Cout) {
@@ -593,10 +521,11 @@ size_t ring_weight_bytes(int Cin, int Cout) {
     return (size_t)nslabs * ring_slab_bytes(Cin, cp);
 }
 
-int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st) {
+int ring_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cudaStream_t st) {
     const int cp = ring_npad(Cin, Cout);
     const int nslabs = (Cout + cp - 1) / cp;
-    k_pack_ring<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, cp, nslabs, (__nv_bfloat16*)wimg);
+    k_pack_ring<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, cp, nslabs, dtype == ATVS_F16,
+                                                           (unsigned short*)wimg);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -606,20 +535,16 @@ bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
     return !transposed && stride == 1 && (long long)D * H * W >= minvox && H >= 8 && W >= 8;
 }
 
-int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              int raw16, double* stats, const float* bias, cudaStream_t st, const RingDual* dual) {
-    // dual-head launch: the weight image has 32 columns [8 stride-1 | 16 stride-2 | 8 zero], Cout = 8 is head 1
-    const int cp = dual ? ring_dual_cp(Cin) : ring_npad(Cin, Cout);
-    const int nslabs = dual ? 1 : (Cout + cp - 1) / cp;
+int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+              int raw16, double* stats, const float* bias, cudaStream_t st) {
+    const int cp = ring_npad(Cin, Cout);
+    const int nslabs = (Cout + cp - 1) / cp;
     const int sms = atvs_num_sms();
     RingParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
     p.raw16 = raw16;
-    if (dual) {
-        p.dual = 1;
-        p.out2 = dual->out2; p.stats2 = dual->stats2; p.bias2 = dual->bias2;
-    }
+    p.fmt = tc_fmt_bits(dtype);
     p.nXT = (W + RG_TX - 1) / RG_TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
     p.wbytes = (int)ring_slab_bytes(Cin, cp);
@@ -678,10 +603,9 @@ int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, 
         int rc = 0;
 #define RG_CASE(CI, CPV)                                                                                              \
     if (Cin == CI && cp == CPV) {                                                                                     \
-        rc = (minb == 2) ? launch_ring<CI, CPV, 2>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st) \
-                         : launch_ring<CI, CPV, 1>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st); \
+        rc = (minb == 2) ? launch_ring<CI, CPV, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st) \
+                         : launch_ring<CI, CPV, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st); \
     } else
-        RG_CASE(8, 24) RG_CASE(16, 24)
         RG_CASE(8, 8) RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(16, 8) RG_CASE(16, 16) RG_CASE(16, 32)
         RG_CASE(32, 8) RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(64, 8) RG_CASE(64, 16) RG_CASE(64, 32)
         {

@@ -15,25 +15,15 @@ RING_HD static inline int ring_nsteps(int Cin) { return Cin >= 16 ? 9 * (Cin / 1
 
 int ring_npad(int Cin, int Cout);
 size_t ring_weight_bytes(int Cin, int Cout);
-int ring_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
+int ring_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cudaStream_t st);
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed);
-// second head of a dual launch: a 16-channel stride-2 convolution of the same input (see RingParams::dual)
-struct RingDual {
-    void* out2;            // (B, D/2, H/2, W/2, 16) raw, same dtype as the first head
-    double* stats2;        // 32 doubles or NULL
-    const float* bias2;    // (B, 3, H/2, W/2, 16) f32 or NULL
-};
-int ring_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
-              int raw16, double* stats, const float* bias, cudaStream_t st, const RingDual* dual = nullptr);
-
-int ring_dual_cp(int Cin);
-size_t ring_dual_weight_bytes(int Cin);
-int ring_dual_pack(const float* kernel32, int Cin, void* wimg, cudaStream_t st);
+int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+              int raw16, double* stats, const float* bias, cudaStream_t st);
 
 // stride-2 variant (conv_ring_s2.cu)
 bool ring_s2_supported(int Cin, int Cout);
 size_t ring_s2_weight_bytes(int Cin, int Cout);
-int ring_s2_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st);
+int ring_s2_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cudaStream_t st);
 bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout);
-int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
                  int raw16, double* stats, const float* bias, cudaStream_t st);

@@ -35,6 +35,7 @@ struct S2Params {
     int Do, Ho, Wo;
     int Cout, coff, ncols;
     int raw16;                  // raw output dtype: 0 fp32, 1 saturated fp16
+    uint32_t fmt;               // operand format bits of the instruction descriptor (tc_fmt_bits)
     int nXT, nYT, nZS, ZS;
     int nring;
     int wbytes;
@@ -84,7 +85,7 @@ __host__ __device__ constexpr int s2_pair_b(int s) { return s == 0 ? 1 : s == 1 
 
 template <int CIN, int CP, int MINB>
 __global__ void __launch_bounds__(S2_THREADS, MINB)
-k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2Params p,
+k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Params p,
                  const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
                  const float* __restrict__ bias) {
     using Cfg = S2Cfg<CIN, CP>;
@@ -176,7 +177,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
                 const bool ok = gy < p.H && gx < p.W;
                 goff[k] = (j >= Cfg::NKC * NVOX) ? -2 : (ok ? (gy * p.W + gx) * CIN + c * 8 : -1);
             }
-            const __nv_bfloat16* zbase = x + ((size_t)un.b * p.D + 2 * un.z0) * zstride_in;
+            const uint16_t* zbase = x + ((size_t)un.b * p.D + 2 * un.z0) * zstride_in;
             for (int i = 0; i <= iend; ++i, zbase += zstride_in) {
                 mbar_wait(&empty[slot], sphase ^ 1);
                 const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
@@ -189,7 +190,7 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
                         const uint32_t soff = (uint32_t)(c * S2_PITCH +
                                                          ((((iy & 1) << 1) | (ix & 1)) * S2_SUB + (iy >> 1) * S2_SC + (ix >> 1)) * 16);
                         const bool ok = goff[k] >= 0;
-                        const __nv_bfloat16* src = ok ? zbase + goff[k] : x;
+                        const uint16_t* src = ok ? zbase + goff[k] : x;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + soff), "l"(src),
                                      "r"(ok ? 16 : 0)
                                      : "memory");
@@ -248,16 +249,16 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
                     const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
                     const uint32_t gprev = (gcur == 0) ? (uint32_t)G - 1 : gcur - 1;
                     if (!even) {
-                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W1 * 16u) >> 4), ring_idesc(CP));
+                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W1 * 16u) >> 4), ring_idesc(CP) | p.fmt);
                     } else if (j == 0) {
-                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP));
+                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
                     } else if (j >= un.zlen) {
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP));
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
                     } else if (gcur != 0) {
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(2 * CP));
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(2 * CP) | p.fmt);
                     } else {                           // the pair wraps around the accumulator ring
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP));
-                        issue_plane(tmem_base, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP));
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
+                        issue_plane(tmem_base, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
                     }
                     tc_commit(&empty[slot]);
                     if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
@@ -358,11 +359,11 @@ k_conv3d_ring_s2(const __nv_bfloat16* __restrict__ x, const __grid_constant__ S2
 }
 
 // weight image of one Cout slab: [step][2 chunks][w_dz2 | w_dz0 | w_dz1 rows of CP][8 channels] bf16
-__global__ void k_pack_ring_s2(const float* __restrict__ w, int Cin, int Cout, int cp, __nv_bfloat16* __restrict__ out) {
+__global__ void k_pack_ring_s2(const float* __restrict__ w, int Cin, int Cout, int cp, int f16, unsigned short* __restrict__ out) {
     const int nsteps = ring_nsteps(Cin);
     const int nrows = 3 * cp;
     const int slab = blockIdx.x / nsteps, step = blockIdx.x % nsteps;
-    __nv_bfloat16* o = out + ((size_t)slab * nsteps + step) * 2 * nrows * 8;
+    unsigned short* o = out + ((size_t)slab * nsteps + step) * 2 * nrows * 8;
     for (int i = threadIdx.x; i < 2 * nrows * 8; i += blockDim.x) {
         const int chunk = i / (nrows * 8), r = (i / 8) % nrows, e = i % 8;
         const int grp = r / cp, n = r % cp;
@@ -378,12 +379,12 @@ __global__ void k_pack_ring_s2(const float* __restrict__ w, int Cin, int Cout, i
         const int co = slab * cp + n;
         float val = 0.f;
         if (tap2d >= 0 && co < Cout) val = w[((size_t)(dz * 9 + tap2d) * Cin + k) * Cout + co];
-        o[i] = __float2bfloat16_rn(val);
+        o[i] = tc_cvt16(val, f16);
     }
 }
 
 template <int CIN, int CP, int MINB>
-int launch_s2(const __nv_bfloat16* x, const S2Params& p, const uint8_t* wimg, float* out, double* stats,
+int launch_s2(const uint16_t* x, const S2Params& p, const uint8_t* wimg, float* out, double* stats,
               const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -408,10 +409,10 @@ size_t ring_s2_weight_bytes(int Cin, int Cout) {
     return (size_t)((Cout + cp - 1) / cp) * s2_slab_bytes(Cin, cp);
 }
 
-int ring_s2_pack(const float* kernel, int Cin, int Cout, void* wimg, cudaStream_t st) {
+int ring_s2_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cudaStream_t st) {
     const int cp = s2_cp(Cout);
     const int nslabs = (Cout + cp - 1) / cp;
-    k_pack_ring_s2<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, cp, (__nv_bfloat16*)wimg);
+    k_pack_ring_s2<<<nslabs * ring_nsteps(Cin), 128, 0, st>>>(kernel, Cin, Cout, cp, dtype == ATVS_F16, (unsigned short*)wimg);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -426,7 +427,7 @@ bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout) {
            getenv("ATVS_NO_RING_S2") == nullptr;
 }
 
-int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
+int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
                  int raw16, double* stats, const float* bias, cudaStream_t st) {
     const int cp = s2_cp(Cout);
     const int nslabs = (Cout + cp - 1) / cp;
@@ -435,6 +436,7 @@ int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int 
     memset(&p, 0, sizeof(p));
     p.B = B; p.D = D; p.H = H; p.W = W; p.Do = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Cout = Cout;
     p.raw16 = raw16;
+    p.fmt = tc_fmt_bits(dtype);
     p.nXT = (p.Wo + S2_TX - 1) / S2_TX;
     p.nYT = (p.Ho + S2_TY - 1) / S2_TY;
     p.wbytes = (int)s2_slab_bytes(Cin, cp);
@@ -475,8 +477,8 @@ int ring_s2_conv(const void* x_bf16, const void* wimg, int B, int D, int H, int 
         int rc = 0;
 #define S2_CASE(CI, CPV)                                                                                             \
     if (Cin == CI && cp == CPV) {                                                                                    \
-        rc = (minb == 2) ? launch_s2<CI, CPV, 2>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st) \
-                         : launch_s2<CI, CPV, 1>((const __nv_bfloat16*)x_bf16, p, wi, raw_out, stats, bias, smem, grid, st); \
+        rc = (minb == 2) ? launch_s2<CI, CPV, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st) \
+                         : launch_s2<CI, CPV, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st); \
     } else
         S2_CASE(8, 16) S2_CASE(8, 32) S2_CASE(16, 16) S2_CASE(16, 32) S2_CASE(32, 16) S2_CASE(32, 32)
         {

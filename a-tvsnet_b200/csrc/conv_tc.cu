@@ -45,6 +45,7 @@ struct TcParams {
     int nTD, nTH, nTW;
     int Cout, coff, ncols;     // real channel count, slab offset, real columns in this slab
     int raw16;                 // raw output dtype: 0 fp32, 1 saturated fp16
+    uint32_t fmt;              // operand format bits of the instruction descriptor (tc_fmt_bits)
     int nstages;
     long long ntiles;
 };
@@ -72,7 +73,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
     using Cfg = TcCfg<CIN>;
     constexpr int WTAP_BYTES = NPAD * CIN * 2;
     constexpr uint32_t TMEM_COLS = (2 * NPAD < 32) ? 32u : (uint32_t)(2 * NPAD);
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t IDESC = (1u << 4) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24) | p.fmt;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -238,7 +239,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
 // ------------------------------------------------------------------ weight packing
 // packed image: for each class, for each (padded) tap, for each slab: [NPAD][Cin] bf16, K-major.
 __global__ void k_pack_weights(const float* __restrict__ w, int Cin, int Cout, int transposed, int npad, int nslabs,
-                               int ncls, __nv_bfloat16* __restrict__ out) {
+                               int ncls, int f16, unsigned short* __restrict__ out) {
     // one block per (class, slab, tap); taps follow make_conv_geom order
     const int tps = (Cin == 8) ? 2 : 1;
     int cls = 0, slab = 0, tap = 0, ntaps_pad = 0;
@@ -264,14 +265,14 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cin, int Cout, i
         const int tx = tap % g.nt[2], ty = (tap / g.nt[2]) % g.nt[1], tz = tap / (g.nt[2] * g.nt[1]);
         kidx = (g.kidx[0][tz] * 3 + g.kidx[1][ty]) * 3 + g.kidx[2][tx];
     }
-    __nv_bfloat16* o = out + base + ((size_t)slab * ntaps_pad + tap) * npad * Cin;
+    unsigned short* o = out + base + ((size_t)slab * ntaps_pad + tap) * npad * Cin;
     for (int i = threadIdx.x; i < npad * Cin; i += blockDim.x) {
         const int n = i / Cin, k = i % Cin;
         const int co = slab * npad + n;
         float val = 0.f;
         if (kidx >= 0 && co < Cout)
             val = transposed ? w[((size_t)kidx * Cout + co) * Cin + k] : w[((size_t)kidx * Cin + k) * Cout + co];
-        o[i] = __float2bfloat16_rn(val);
+        o[i] = tc_cvt16(val, f16);
     }
 }
 
@@ -326,7 +327,10 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
     for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
     size_t bytes = (elems * 2 + 255) & ~(size_t)255;          // per-tap TMA image
     if (!transposed) bytes += ring_weight_bytes(Cin, Cout) + ring_s2_weight_bytes(Cin, Cout);   // halo-ring images (stride 1 | 2)
-    else if (deconv_fused_applicable(Cin, Cout)) bytes += deconv_fused_weight_bytes(Cin, Cout);   // 8-class deconv image
+    else {
+        if (deconv_fused_applicable(Cin, Cout)) bytes += (deconv_fused_weight_bytes(Cin, Cout) + 255) & ~(size_t)255;   // 8-class deconv image
+        if (deconv_ring_supported(Cin, Cout)) bytes += deconv_ring_weight_bytes(Cin, Cout);     // plane-ring deconv image
+    }
     return bytes;
 }
 
@@ -338,113 +342,97 @@ static size_t tap_image_bytes(int Cin, int Cout, int transposed) {
     return (elems * 2 + 255) & ~(size_t)255;
 }
 
-extern "C" int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed, void* wpacked,
-                                           atvs_stream_t stream) {
-    ATVS_CHECK_ARG(kernel && wpacked, ATVS_E_NULL, "atvs_pack_conv_weights_bf16: NULL pointer");
+extern "C" int atvs_pack_conv_weights_tc(const float* kernel, int Cin, int Cout, int transposed, int dtype, void* wpacked,
+                                         atvs_stream_t stream) {
+    ATVS_CHECK_ARG(kernel && wpacked, ATVS_E_NULL, "atvs_pack_conv_weights_tc: NULL pointer");
+    ATVS_CHECK_ARG(dtype == ATVS_BF16 || dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_pack_conv_weights_tc: dtype %d (ATVS_BF16 | ATVS_F16)", dtype);
     ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
-                   "atvs_pack_conv_weights_bf16: Cin=%d (8, 16, 32 or 64)", Cin);
-    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_pack_conv_weights_bf16: Cout=%d (1..64)", Cout);
+                   "atvs_pack_conv_weights_tc: Cin=%d (8, 16, 32 or 64)", Cin);
+    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_pack_conv_weights_tc: Cout=%d (1..64)", Cout);
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     const int ncls = transposed ? 8 : 1;
     int blocks = 0;
     for (int c = 0; c < ncls; ++c) blocks += ntaps_padded(Cin, transposed, c) * sp.nslabs;
     k_pack_weights<<<blocks, 128, 0, (cudaStream_t)stream>>>(kernel, Cin, Cout, transposed, sp.npad, sp.nslabs, ncls,
-                                                            (__nv_bfloat16*)wpacked);
+                                                            dtype == ATVS_F16, (unsigned short*)wpacked);
     ATVS_LAUNCH_CHECK();
     if (!transposed) {
-        int rc = ring_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
+        int rc = ring_pack(kernel, Cin, Cout, dtype, (char*)wpacked + tap_image_bytes(Cin, Cout, 0), (cudaStream_t)stream);
         if (rc == 0 && ring_s2_supported(Cin, Cout))
-            rc = ring_s2_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout),
-                              (cudaStream_t)stream);
+            rc = ring_s2_pack(kernel, Cin, Cout, dtype,
+                              (char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout), (cudaStream_t)stream);
         return rc;
     }
-    if (deconv_fused_applicable(Cin, Cout))
-        return deconv_fused_pack(kernel, Cin, Cout, (char*)wpacked + tap_image_bytes(Cin, Cout, 1), (cudaStream_t)stream);
-    return 0;
+    int rc = 0;
+    size_t off = tap_image_bytes(Cin, Cout, 1);
+    if (deconv_fused_applicable(Cin, Cout)) {
+        rc = deconv_fused_pack(kernel, Cin, Cout, dtype, (char*)wpacked + off, (cudaStream_t)stream);
+        off += (deconv_fused_weight_bytes(Cin, Cout) + 255) & ~(size_t)255;
+    }
+    if (rc == 0 && deconv_ring_supported(Cin, Cout))
+        rc = deconv_ring_pack(kernel, Cin, Cout, dtype, (char*)wpacked + off, (cudaStream_t)stream);
+    return rc;
 }
 
-static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
-                           int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
-                           double* stats, atvs_stream_t stream);
+static int conv3d_tc_impl(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
+                          int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
+                          double* stats, atvs_stream_t stream);
 
-extern "C" int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                                int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
-                                atvs_stream_t stream) {
-    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, transposed, nullptr, raw_out, raw_dtype, stats,
-                            stream);
+extern "C" int atvs_conv3d_tc(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin,
+                              int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
+                              atvs_stream_t stream) {
+    return conv3d_tc_impl(x16, x_dtype, wpacked, B, D, H, W, Cin, Cout, stride, transposed, nullptr, raw_out, raw_dtype, stats,
+                          stream);
 }
 
-extern "C" int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                                     int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
-                                     double* stats, atvs_stream_t stream) {
-    ATVS_CHECK_ARG(plane_bias, ATVS_E_NULL, "atvs_conv3d_bf16_bias: plane_bias is NULL");
-    ATVS_CHECK_ARG(((uintptr_t)plane_bias & 15) == 0, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: plane_bias must be 16-byte aligned");
-    ATVS_CHECK_ARG((D + stride - 1) / stride >= 2, ATVS_E_SHAPE, "atvs_conv3d_bf16_bias: needs at least 2 output planes");
-    return conv3d_bf16_impl(x_bf16, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, raw_dtype, stats, stream);
+extern "C" int atvs_conv3d_tc_bias(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin,
+                                   int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
+                                   double* stats, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(plane_bias, ATVS_E_NULL, "atvs_conv3d_tc_bias: plane_bias is NULL");
+    ATVS_CHECK_ARG(((uintptr_t)plane_bias & 15) == 0, ATVS_E_SHAPE, "atvs_conv3d_tc_bias: plane_bias must be 16-byte aligned");
+    ATVS_CHECK_ARG((D + stride - 1) / stride >= 2, ATVS_E_SHAPE, "atvs_conv3d_tc_bias: needs at least 2 output planes");
+    return conv3d_tc_impl(x16, x_dtype, wpacked, B, D, H, W, Cin, Cout, stride, 0, plane_bias, raw_out, raw_dtype, stats, stream);
 }
 
-extern "C" int atvs_conv3d_bf16_dual_supported(int B, int D, int H, int W, int Cin) {
-    return (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && ((D | H | W) & 1) == 0 && ring_applicable(B, D, H, W, 1, 0) ? 1 : 0;
-}
-
-extern "C" size_t atvs_dual_weight_bytes(int Cin) { return ring_dual_weight_bytes(Cin); }
-
-extern "C" int atvs_pack_conv_weights_dual(const float* kernel32, int Cin, void* wpacked, atvs_stream_t stream) {
-    ATVS_CHECK_ARG(kernel32 && wpacked, ATVS_E_NULL, "atvs_pack_conv_weights_dual: NULL pointer");
-    ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP, "atvs_pack_conv_weights_dual: Cin=%d", Cin);
-    return ring_dual_pack(kernel32, Cin, wpacked, (cudaStream_t)stream);
-}
-
-extern "C" int atvs_conv3d_bf16_dual(const void* x_bf16, const void* wpacked32, int B, int D, int H, int W, int Cin,
-                                     const float* plane_bias1, const float* plane_bias2, void* raw_out1, void* raw_out2,
-                                     int raw_dtype, double* stats1, double* stats2, atvs_stream_t stream) {
-    ATVS_CHECK_ARG(x_bf16 && wpacked32 && raw_out1 && raw_out2, ATVS_E_NULL, "atvs_conv3d_bf16_dual: NULL pointer");
-    ATVS_CHECK_ARG(raw_dtype == ATVS_F32 || raw_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_conv3d_bf16_dual: raw_dtype %d", raw_dtype);
-    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16_dual: bad shape");
-    ATVS_CHECK_ARG(atvs_conv3d_bf16_dual_supported(B, D, H, W, Cin), ATVS_E_UNSUP,
-                   "atvs_conv3d_bf16_dual: needs Cin in {8,16,32,64}, even D,H,W and a ring-sized volume (got Cin=%d %dx%dx%d)",
-                   Cin, D, H, W);
-    ATVS_CHECK_ARG((((uintptr_t)x_bf16 | (uintptr_t)wpacked32 | (uintptr_t)plane_bias1 | (uintptr_t)plane_bias2) & 15) == 0 &&
-                       (((uintptr_t)raw_out1 | (uintptr_t)raw_out2) & 31) == 0,
-                   ATVS_E_SHAPE, "atvs_conv3d_bf16_dual: inputs must be 16-byte, outputs 32-byte aligned");
-    RingDual d;
-    d.out2 = raw_out2; d.stats2 = stats2; d.bias2 = plane_bias2;
-    return ring_conv(x_bf16, wpacked32, B, D, H, W, Cin, 8, (float*)raw_out1,
-                     raw_dtype == ATVS_F16, stats1, plane_bias1, (cudaStream_t)stream, &d);
-}
-
-static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
-                           int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
-                           double* stats, atvs_stream_t stream) {
+static int conv3d_tc_impl(const void* x_bf16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin, int Cout,
+                          int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
+                          double* stats, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x_dtype == ATVS_BF16 || x_dtype == ATVS_F16, ATVS_E_DTYPE,
+                   "atvs_conv3d_tc: x_dtype %d (ATVS_BF16 or ATVS_F16)", x_dtype);
     float* raw_out = (float*)raw_out_v;        // element offsets are dtype independent; kernels re-type the base
-    ATVS_CHECK_ARG(x_bf16 && wpacked && raw_out, ATVS_E_NULL, "atvs_conv3d_bf16: NULL pointer");
+    ATVS_CHECK_ARG(x_bf16 && wpacked && raw_out, ATVS_E_NULL, "atvs_conv3d_tc: NULL pointer");
     ATVS_CHECK_ARG(raw_dtype == ATVS_F32 || raw_dtype == ATVS_F16, ATVS_E_DTYPE,
-                   "atvs_conv3d_bf16: raw_dtype %d (ATVS_F32 or ATVS_F16)", raw_dtype);
+                   "atvs_conv3d_tc: raw_dtype %d (ATVS_F32 or ATVS_F16)", raw_dtype);
     const int raw16 = raw_dtype == ATVS_F16;
-    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_bf16: bad shape");
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_conv3d_tc: bad shape");
     ATVS_CHECK_ARG(Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64, ATVS_E_UNSUP,
-                   "atvs_conv3d_bf16: Cin=%d (8, 16, 32 or 64)", Cin);
-    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_conv3d_bf16: Cout=%d (1..64)", Cout);
+                   "atvs_conv3d_tc: Cin=%d (8, 16, 32 or 64)", Cin);
+    ATVS_CHECK_ARG(Cout >= 1 && Cout <= 64, ATVS_E_UNSUP, "atvs_conv3d_tc: Cout=%d (1..64)", Cout);
     ATVS_CHECK_ARG(transposed ? stride == 2 : (stride == 1 || stride == 2), ATVS_E_UNSUP,
-                   "atvs_conv3d_bf16: stride=%d transposed=%d", stride, transposed);
+                   "atvs_conv3d_tc: stride=%d transposed=%d", stride, transposed);
     ATVS_CHECK_ARG(transposed || stride == 1 || ((D | H | W) & 1) == 0, ATVS_E_DIV8,
-                   "atvs_conv3d_bf16: stride-2 convolution needs even D,H,W (got %d,%d,%d)", D, H, W);
+                   "atvs_conv3d_tc: stride-2 convolution needs even D,H,W (got %d,%d,%d)", D, H, W);
     ATVS_CHECK_ARG(((uintptr_t)x_bf16 & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)raw_out & 15) == 0,
-                   ATVS_E_SHAPE, "atvs_conv3d_bf16: buffers must be 16-byte aligned");
+                   ATVS_E_SHAPE, "atvs_conv3d_tc: buffers must be 16-byte aligned");
     EncodeTiledFn encode = get_encode();
     if (!encode) {
-        atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled entry point not available");
+        atvs_set_error("atvs_conv3d_tc: cuTensorMapEncodeTiled entry point not available");
         return ATVS_E_UNSUP;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (transposed && deconv_ring_supported(Cin, Cout) && deconv_ring_applicable(B, D, H, W)) {
+        size_t off = tap_image_bytes(Cin, Cout, 1);
+        if (deconv_fused_applicable(Cin, Cout)) off += (deconv_fused_weight_bytes(Cin, Cout) + 255) & ~(size_t)255;
+        return deconv_ring(x_bf16, x_dtype, (const char*)wpacked + off, B, D, H, W, Cin, Cout, raw_out, raw16, stats, st);
+    }
     if (transposed && deconv_fused_applicable(Cin, Cout))
-        return deconv_fused(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 1), B, D, H, W, Cin, Cout, raw_out,
+        return deconv_fused(x_bf16, x_dtype, (const char*)wpacked + tap_image_bytes(Cin, Cout, 1), B, D, H, W, Cin, Cout, raw_out,
                             raw16, stats, st);
     if (!transposed && stride == 2 && ring_s2_applicable(B, D, H, W, Cin, Cout))
-        return ring_s2_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout), B, D, H,
+        return ring_s2_conv(x_bf16, x_dtype, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0) + ring_weight_bytes(Cin, Cout), B, D, H,
                             W, Cin, Cout, raw_out, raw16, stats, plane_bias, st);
     if (ring_applicable(B, D, H, W, stride, transposed))
-        return ring_conv(x_bf16, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
+        return ring_conv(x_bf16, x_dtype, (const char*)wpacked + tap_image_bytes(Cin, Cout, 0), B, D, H, W, Cin, Cout, raw_out,
                          raw16, stats, plane_bias, st);
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     const int ncls = transposed ? 8 : 1;
@@ -467,6 +455,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
         p.os = g.os;
         p.Cout = Cout;
         p.raw16 = raw16;
+        p.fmt = tc_fmt_bits(x_dtype);
         p.ncls = c1 - c0;
         // brick shape: 128 voxels, minimise padded volume, prefer a wide x extent
         {
@@ -530,7 +519,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
-                atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled(input, map %d) failed: %d", m, (int)r);
+                atvs_set_error("atvs_conv3d_tc: cuTensorMapEncodeTiled(input, map %d) failed: %d", m, (int)r);
                 return (int)r;
             }
         }
@@ -547,7 +536,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) {
-                    atvs_set_error("atvs_conv3d_bf16: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+                    atvs_set_error("atvs_conv3d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
                     return (int)r;
                 }
             }
@@ -555,7 +544,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
             const size_t stage_bytes = (size_t)128 * Cin * 2 * tps;
             const size_t budget = 200 * 1024;
             if (wbytes + 2 * stage_bytes > budget) {
-                atvs_set_error("atvs_conv3d_bf16: weights do not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
+                atvs_set_error("atvs_conv3d_tc: weights do not fit in shared memory (Cin=%d Cout=%d)", Cin, Cout);
                 return ATVS_E_UNSUP;
             }
             int nst = (int)((budget - wbytes) / stage_bytes);
@@ -571,7 +560,7 @@ static int conv3d_bf16_impl(const void* x_bf16, const void* wpacked, int B, int 
             TC_CASE(8, 16) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32) TC_CASE(32, 64)
             TC_CASE(64, 16) TC_CASE(64, 32) TC_CASE(8, 32) TC_CASE(8, 64) TC_CASE(16, 64) TC_CASE(64, 64)
             {
-                atvs_set_error("atvs_conv3d_bf16: no kernel for Cin=%d N=%d", Cin, sp.npad);
+                atvs_set_error("atvs_conv3d_tc: no kernel for Cin=%d N=%d", Cin, sp.npad);
                 return ATVS_E_UNSUP;
             }
 #undef TC_CASE

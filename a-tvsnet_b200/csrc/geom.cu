@@ -291,6 +291,17 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
     pk.y = *reinterpret_cast<unsigned*>(&hi);
     __stcs(reinterpret_cast<uint2*>(p), pk);
 }
+__device__ __forceinline__ unsigned f16x2_sat(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+    uint2 pk;
+    pk.x = f16x2_sat(v.x, v.y);
+    pk.y = f16x2_sat(v.z, v.w);
+    __stcs(reinterpret_cast<uint2*>(p), pk);
+}
 
 #ifndef ATVS_K1_DCHUNK
 #define ATVS_K1_DCHUNK 8      // depth planes per block of K1 (measured: 4 / 8 / 16)
@@ -443,14 +454,27 @@ k_build_cost_volume(const float* __restrict__ ref, const float* __restrict__ vie
 // pixel needs F/8 lanes: half the L1 wavefronts, shuffles and instructions per output byte of the
 // fp32-source kernel, and 16-byte streaming stores.  Same sample sharing scheme (lane g evaluates the
 // homography of planes g, g+G8, ... of the 8-plane chunk).
+template <bool F16>
 __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+    if (F16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+        return;
+    }
     // bf16 -> fp32 is a 16-bit shift: one SHL for the low half, one AND for the high half
     f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
     f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
     f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float* f) {
+    if (F16) {
+        uint4 u;
+        u.x = f16x2_sat(f[0], f[1]); u.y = f16x2_sat(f[2], f[3]); u.z = f16x2_sat(f[4], f[5]); u.w = f16x2_sat(f[6], f[7]);
+        return u;
+    }
     __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
     __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
     uint4 u;
@@ -459,10 +483,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return u;
 }
 
-template <int MODE, int G8>
+template <int MODE, int G8, bool F16>
 __global__ void __launch_bounds__(256)
-k_build_cost_volume_h(const float* __restrict__ ref, const __nv_bfloat16* __restrict__ view, const float* __restrict__ hv,
-                      int D, int h, int w, __nv_bfloat16* __restrict__ out) {
+k_build_cost_volume_h(const float* __restrict__ ref, const uint16_t* __restrict__ view, const float* __restrict__ hv,
+                      int D, int h, int w, uint16_t* __restrict__ out) {
     constexpr int F = 8 * G8;
     constexpr int NS = (G8 >= K1_DCHUNK) ? 1 : K1_DCHUNK / G8;
     const int hw = h * w;
@@ -474,7 +498,7 @@ k_build_cost_volume_h(const float* __restrict__ ref, const __nv_bfloat16* __rest
     const bool live = x < w && y < h;
     const int pix = live ? y * w + x : hw - 1;
     const int b = blockIdx.z;
-    const __nv_bfloat16* viewb = view + (size_t)b * hw * F;
+    const uint16_t* viewb = view + (size_t)b * hw * F;
     constexpr int CO = (MODE == 0) ? 2 * F : F;
     float r[8];
 #pragma unroll
@@ -504,11 +528,11 @@ k_build_cost_volume_h(const float* __restrict__ ref, const __nv_bfloat16* __rest
             wc[k] = s.valid ? s.wc : bad; wd[k] = s.valid ? s.wd : bad;
         }
     }
-    const __nv_bfloat16* vbase = viewb + g * 8;
+    const uint16_t* vbase = viewb + g * 8;
     const int rowpitch = w * F;
-    __nv_bfloat16* oj = out + (((size_t)b * D + d0) * hw + pix) * CO + g * 8;
+    uint16_t* oj = out + (((size_t)b * D + d0) * hw + pix) * CO + g * 8;
     const size_t ostride = (size_t)hw * CO;
-    const uint4 rpk = pack8(r);
+    const uint4 rpk = pack8<F16>(r);
 #pragma unroll
     for (int j = 0; j < K1_DCHUNK; ++j, oj += ostride) {
         const int k = (G8 >= K1_DCHUNK) ? 0 : j / G8;
@@ -517,36 +541,42 @@ k_build_cost_volume_h(const float* __restrict__ ref, const __nv_bfloat16* __rest
         const float a0 = __shfl_sync(0xffffffffu, wa[k], src, G8), a1 = __shfl_sync(0xffffffffu, wb[k], src, G8);
         const float a2 = __shfl_sync(0xffffffffu, wc[k], src, G8), a3 = __shfl_sync(0xffffffffu, wd[k], src, G8);
         if (d0 + j >= D) break;
-        const __nv_bfloat16* p = vbase + (ptrdiff_t)max(c, 0) * F;
+        const uint16_t* p = vbase + (ptrdiff_t)max(c, 0) * F;
         float A[8], Bq[8], C[8], Dq[8], wv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p)), A);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p + F)), Bq);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p + rowpitch)), C);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p + rowpitch + F)), Dq);
+        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(p)), A);
+        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(p + F)), Bq);
+        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(p + rowpitch)), C);
+        unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(p + rowpitch + F)), Dq);
 #pragma unroll
         for (int i = 0; i < 8; ++i) wv[i] = fmaf(a3, Dq[i], fmaf(a2, C[i], fmaf(a1, Bq[i], a0 * A[i])));
         if (!live) continue;
         if (MODE == 0) {
             __stcs(reinterpret_cast<uint4*>(oj), rpk);
-            __stcs(reinterpret_cast<uint4*>(oj + F), pack8(wv));
+            __stcs(reinterpret_cast<uint4*>(oj + F), pack8<F16>(wv));
         } else if (MODE == 1) {
-            __stcs(reinterpret_cast<uint4*>(oj), pack8(wv));
+            __stcs(reinterpret_cast<uint4*>(oj), pack8<F16>(wv));
         } else {
             const float m = (c >= 0) ? 1.0f : 0.0f;   // model.py:277-278
 #pragma unroll
             for (int i = 0; i < 8; ++i) wv[i] = fabsf(wv[i] - r[i]) * m;
-            __stcs(reinterpret_cast<uint4*>(oj), pack8(wv));
+            __stcs(reinterpret_cast<uint4*>(oj), pack8<F16>(wv));
         }
     }
 }
 
-__global__ void k_f32_to_bf16(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n4) {
+template <bool F16>
+__global__ void k_f32_to_16(const float* __restrict__ s, uint16_t* __restrict__ d, long long n4) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
         uint2 pk;
-        pk.x = *reinterpret_cast<unsigned*>(&lo);
-        pk.y = *reinterpret_cast<unsigned*>(&hi);
+        if (F16) {
+            pk.x = f16x2_sat(v.x, v.y);
+            pk.y = f16x2_sat(v.z, v.w);
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            pk.x = *reinterpret_cast<unsigned*>(&lo);
+            pk.y = *reinterpret_cast<unsigned*>(&hi);
+        }
         reinterpret_cast<uint2*>(d)[i] = pk;
     }
 }
@@ -1142,27 +1172,31 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
     ATVS_CHECK_ARG(B > 0 && B < 65536 && D > 0 && h > 1 && w > 1 && F > 0, ATVS_E_SHAPE,
                    "atvs_build_cost_volume: bad shape B=%d D=%d h=%d w=%d F=%d", B, D, h, w, F);
     ATVS_CHECK_ARG(mode >= 0 && mode <= 2, ATVS_E_UNSUP, "atvs_build_cost_volume: mode %d", mode);
-    ATVS_CHECK_ARG(F % 4 == 0 && (out_dtype != ATVS_BF16 || F % 8 == 0), ATVS_E_SHAPE,
-                   "atvs_build_cost_volume: F=%d must be a multiple of 4 (8 for bf16)", F);
+    ATVS_CHECK_ARG(F % 4 == 0 && (out_dtype == ATVS_F32 || F % 8 == 0), ATVS_E_SHAPE,
+                   "atvs_build_cost_volume: F=%d must be a multiple of 4 (8 for 16-bit volumes)", F);
     ATVS_CHECK_ARG((((uintptr_t)ref_feature | (uintptr_t)view_feature | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
                    "atvs_build_cost_volume: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == ATVS_F32)
         return launch_k1<float>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
                                 (float*)out, st);
-    if (out_dtype == ATVS_BF16 && !ref_homographies && F % 8 == 0 && (F == 8 || F == 16 || F == 32 || F == 64 || F == 128) &&
+    const bool half_out = out_dtype == ATVS_BF16 || out_dtype == ATVS_F16;
+    if (half_out && !ref_homographies && F % 8 == 0 && (F == 8 || F == 16 || F == 32 || F == 64 || F == 128) &&
         getenv("ATVS_K1_F32SRC") == nullptr) {
-        // bf16 volume: gather from a bf16 copy of the source feature map (stream-ordered scratch)
-        __nv_bfloat16* vb = nullptr;
+        // 16-bit volume: gather from a 16-bit copy of the source feature map (stream-ordered scratch)
+        uint16_t* vb = nullptr;
         const long long n = (long long)B * h * w * F;
-        ATVS_CUDA(cudaMallocAsync(&vb, sizeof(__nv_bfloat16) * n, st));
-        k_f32_to_bf16<<<(unsigned)((n / 4 + 255) / 256 < 2048 ? (n / 4 + 255) / 256 : 2048), 256, 0, st>>>(view_feature, vb, n / 4);
+        ATVS_CUDA(cudaMallocAsync(&vb, sizeof(uint16_t) * n, st));
+        const unsigned cgrid = (unsigned)((n / 4 + 255) / 256 < 2048 ? (n / 4 + 255) / 256 : 2048);
+        if (out_dtype == ATVS_F16) k_f32_to_16<true><<<cgrid, 256, 0, st>>>(view_feature, vb, n / 4);
+        else k_f32_to_16<false><<<cgrid, 256, 0, st>>>(view_feature, vb, n / 4);
         ATVS_LAUNCH_CHECK();
         const int G8 = F / 8;
         const int ppb = 256 / G8, ph = ppb >= 8 ? ppb / 8 : 1, pw = ppb / ph;
         dim3 grid((unsigned)(((w + pw - 1) / pw) * ((h + ph - 1) / ph)), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
-        __nv_bfloat16* o = (__nv_bfloat16*)out;
-#define K1H(M, G) k_build_cost_volume_h<M, G><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o)
+        uint16_t* o = (uint16_t*)out;
+#define K1H(M, G) do { if (out_dtype == ATVS_F16) k_build_cost_volume_h<M, G, true><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); \
+                       else k_build_cost_volume_h<M, G, false><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); } while (0)
 #define K1H_G(M) do { switch (G8) { case 1: K1H(M, 1); break; case 2: K1H(M, 2); break; case 4: K1H(M, 4); break; \
                                      case 8: K1H(M, 8); break; default: K1H(M, 16); break; } } while (0)
         if (mode == 0) K1H_G(0);
@@ -1177,6 +1211,9 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
     if (out_dtype == ATVS_BF16)
         return launch_k1<__nv_bfloat16>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
                                         (__nv_bfloat16*)out, st);
+    if (out_dtype == ATVS_F16)
+        return launch_k1<__half>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
+                                 (__half*)out, st);
     atvs_set_error("atvs_build_cost_volume: out_dtype %d", out_dtype);
     return ATVS_E_DTYPE;
 }

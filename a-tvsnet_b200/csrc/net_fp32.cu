@@ -135,8 +135,47 @@ struct Vec4<__nv_bfloat16> {
     static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+__device__ __forceinline__ unsigned h2_sat(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 h2_f2(unsigned u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+template <>
+struct Vec4<__half> {
+    static __device__ __forceinline__ float4 ld(const __half* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = h2_f2(u.x), b = h2_f2(u.y);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ void st(__half* p, float4 v) {
+        uint2 u;
+        u.x = h2_sat(v.x, v.y);
+        u.y = h2_sat(v.z, v.w);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+    static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+    static __device__ __forceinline__ void st1(__half* p, float v) {
+        *reinterpret_cast<unsigned short*>(p) = (unsigned short)(h2_sat(v, 0.f) & 0xffffu);
+    }
+};
+
 template <typename T>
 struct Vec8 {};
+template <>
+struct Vec8<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float4& a, float4& b) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const float2 x = h2_f2(u.x), y = h2_f2(u.y), z = h2_f2(u.z), w = h2_f2(u.w);
+        a = make_float4(x.x, x.y, y.x, y.y);
+        b = make_float4(z.x, z.y, w.x, w.y);
+    }
+    static __device__ __forceinline__ void st(__half* p, float4 a, float4 b) {
+        uint4 u;
+        u.x = h2_sat(a.x, a.y); u.y = h2_sat(a.z, a.w); u.z = h2_sat(b.x, b.y); u.w = h2_sat(b.z, b.w);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
 template <>
 struct Vec8<float> {
     static __device__ __forceinline__ void ld(const float* p, float4& a, float4& b) {
@@ -614,6 +653,10 @@ static int bn_relu_add_launch(const RawT* raw, const double* stats, const RawT* 
         k_bn_relu_add<__nv_bfloat16, RawT><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu,
                                                                  (const __nv_bfloat16*)skip1, (const __nv_bfloat16*)skip2,
                                                                  (__nv_bfloat16*)out_plain, (__nv_bfloat16*)out_sum);
+    } else if (act_dtype == ATVS_F16) {
+        const unsigned grid = grid_resident(k_bn_relu_add<__half, RawT>, count * C / 8 + 1, 256);
+        k_bn_relu_add<__half, RawT><<<grid, 256, 0, st>>>(raw, stats, raw2, stats2, count, C, eps, relu, (const __half*)skip1,
+                                                          (const __half*)skip2, (__half*)out_plain, (__half*)out_sum);
     } else {
         atvs_set_error("%s: act_dtype %d", who, act_dtype);
         return ATVS_E_DTYPE;
@@ -667,6 +710,12 @@ extern "C" int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
         k_cast<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
     else if (src_dtype == ATVS_BF16 && dst_dtype == ATVS_BF16)
         k_cast<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    else if (src_dtype == ATVS_F32 && dst_dtype == ATVS_F16)
+        k_cast<float, __half><<<grid, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+    else if (src_dtype == ATVS_F16 && dst_dtype == ATVS_F32)
+        k_cast<__half, float><<<grid, 256, 0, st>>>((const __half*)src, (float*)dst, n);
+    else if (src_dtype == ATVS_F16 && dst_dtype == ATVS_F16)
+        k_cast<__half, __half><<<grid, 256, 0, st>>>((const __half*)src, (__half*)dst, n);
     else {
         atvs_set_error("atvs_cast: dtype %d -> %d", src_dtype, dst_dtype);
         return ATVS_E_DTYPE;
@@ -683,6 +732,8 @@ extern "C" int atvs_add(const void* a, const void* b, void* out, int dtype, long
     if (dtype == ATVS_F32) k_add<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n);
     else if (dtype == ATVS_BF16)
         k_add<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+    else if (dtype == ATVS_F16)
+        k_add<__half><<<grid, 256, 0, st>>>((const __half*)a, (const __half*)b, (__half*)out, n);
     else {
         atvs_set_error("atvs_add: dtype %d", dtype);
         return ATVS_E_DTYPE;
@@ -703,6 +754,8 @@ static int launch_att(const void* act, const void* x, int N, long long V, int C,
     else if (dtype == ATVS_BF16)
         k_attention<__nv_bfloat16, MODE><<<grid, 256, 0, st>>>((const __nv_bfloat16*)act, (const __nv_bfloat16*)x, N, V,
                                                                C, gmax, out);
+    else if (dtype == ATVS_F16)
+        k_attention<__half, MODE><<<grid, 256, 0, st>>>((const __half*)act, (const __half*)x, N, V, C, gmax, out);
     else {
         atvs_set_error("%s: dtype %d", who, dtype);
         return ATVS_E_DTYPE;
@@ -764,6 +817,8 @@ extern "C" int atvs_attention_raw(const void* act_raw, int act_dtype, const void
         if (mode == 0) ATT_RAW(float, 0); else if (mode == 1) ATT_RAW(float, 1); else ATT_RAW(float, 2);
     } else if (x_dtype == ATVS_BF16) {
         if (mode == 0) ATT_RAW(__nv_bfloat16, 0); else ATT_RAW(__nv_bfloat16, 2);
+    } else if (x_dtype == ATVS_F16) {
+        if (mode == 0) ATT_RAW(__half, 0); else ATT_RAW(__half, 2);
     } else {
         atvs_set_error("atvs_attention_raw: x_dtype %d", x_dtype);
         return ATVS_E_DTYPE;

@@ -58,8 +58,9 @@ __device__ __forceinline__ void tc_st8_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// instruction descriptor WITHOUT the operand format bits (OR tc_fmt_bits(dtype) in): D = f32, M = 128, N = n
 __host__ __device__ constexpr uint32_t ring_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 

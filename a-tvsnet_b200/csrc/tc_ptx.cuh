@@ -9,6 +9,16 @@ namespace {
 
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 27;   // bounded waits: trap instead of hanging the GPU
 
+// ------------------------------------------------------------------ 16-bit operand format
+// The tensor path moves its operands as opaque 16-bit words; the only places that know whether they are
+// bf16 or fp16 are the instruction descriptor of tcgen05.mma.kind::f16 (A format bits [7,10), B format bits
+// [10,13): 0 = f16, 1 = bf16) and the float -> 16-bit conversions of the weight packers.
+__host__ __device__ constexpr uint32_t tc_fmt_bits(int dtype) { return dtype == ATVS_BF16 ? ((1u << 7) | (1u << 10)) : 0u; }
+__device__ __forceinline__ unsigned short tc_cvt16(float v, int f16) {
+    if (f16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -2,10 +2,9 @@
 cnn_wrapper/network.py:142-215 conv / conv_bn, :552-616 bottleneck / res_block, :650-671 image_resize / avg_pool,
 :690-697 concat / add) on torch CUDA tensors, NHWC fp32, through the C ABI (csrc/fem2d.cu).
 
-First CUDA path of SURVEY.md 8(f) row N1: fp32 CUDA-core kernels, checked against oracle/fem.py and the reference-graph
-golden vectors.  Variables are looked up under the checkpoint names (tests/golden/fem_variables.json).  The tensor-core
-version is future work, so the hot-path entry points keep taking features; ``extract_features`` is the image-side
-entry that produces them (model.py:420-425 TVSNet_feature_extraction)."""
+SURVEY.md 8(f) row N1: checked against oracle/fem.py and the reference-graph golden vectors.  Variables are looked up
+under the checkpoint names (tests/golden/fem_variables.json).  ``extract_features`` is the image-side entry that feeds
+the hot path (model.py:420-425 TVSNet_feature_extraction over all views)."""
 import torch
 
 from . import _lib as L
@@ -62,6 +61,10 @@ def conv_bn(x, name, stride=1, rate=1):
 
 
 def add(a, b):
+    if tuple(a.shape) != tuple(b.shape) or a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise ValueError("add: operands must be fp32 tensors of one shape, got %s %s and %s %s"
+                         % (tuple(a.shape), a.dtype, tuple(b.shape), b.dtype))
+    a, b = a.contiguous(), b.contiguous()
     out = torch.empty_like(a)
     L.call("atvs_add", L.ptr(a), L.ptr(b), L.ptr(out), L.F32, a.numel(), L.stream())
     return out
@@ -137,7 +140,7 @@ def ResNetDS2SPP(image, return_layers=False):
 
 def extract_features(images):
     """model.py:420-425 TVSNet_feature_extraction over all views: images (B,N,H,W,3) -> features (B,N,H/4,W/4,32).
-    Every view is a separate batch of ONE for the batch statistics, as in the reference's per-view towers."""
-    B, N = images.shape[0], images.shape[1]
-    feats = [torch.stack([ResNetDS2SPP(images[b:b + 1, n])[0] for n in range(N)], dim=0) for b in range(B)]
-    return torch.stack(feats, dim=0)
+    One tower per VIEW on the (B,H,W,3) slice, as in the reference: batch statistics are taken over the whole batch B
+    of that view (B = 1 in example.py), never across views."""
+    N = images.shape[1]
+    return torch.stack([ResNetDS2SPP(images[:, n]) for n in range(N)], dim=1)

@@ -1,11 +1,13 @@
 """Drop-in for the hot-path functions of /root/reference/atvsnet/model.py on torch CUDA
 tensors: get_propability_map :13, prob2depth :80, prob2depth_upsample :113, output_conv
 :132, build_cost_volume :157, cost_volume_reasoning :204, TVSNet_base :380,
-TVSNet_base_siamese :398, cost_volume_aggregation(_refine) :445/:460.  Same names,
-positional argument order, layouts and depth-plane conventions; ``reuse`` is accepted and
-ignored.  Until the 2-D feature extractor (ResNetDS2SPP) is built, the
-TVSNet_* entry points take the (B,N,h,w,32) *feature* tensor where the reference takes
-images."""
+TVSNet :346, TVSNet_base :380, TVSNet_base_siamese :398, TVSNet_feature_extraction :420,
+TVSNet_refine :428, cost_volume_aggregation(_refine) :445/:460.  Same names, positional
+argument order, layouts and depth-plane conventions; ``reuse`` is accepted and ignored.
+The TVSNet_* entry points take ``images`` (B,N,H,W,3) as the reference does and run the 2-D
+feature extractor (fem.ResNetDS2SPP) on the two views they use; a tensor whose last
+dimension is not 3 is taken to be the (B,N,h,w,32) FEATURE tensor (extension: lets a caller
+that already holds the features skip the FEM, e.g. pipeline.run_multiview)."""
 import torch
 
 from . import _lib as L
@@ -125,9 +127,24 @@ def _cost_dtype():
     return act_dtype()
 
 
-def TVSNet_base(features, cams, depth_num, depth_start, depth_interval, view_i, ref_i=0):
-    """model.py:380-395 with features (B,N,h,w,F) in place of images."""
-    ref, view = features[:, ref_i], features[:, view_i]
+def TVSNet_feature_extraction(images, view_i):
+    """model.py:420-425: images (B,N,H,W,3) -> FEM feature of view ``view_i`` (B,H/4,W/4,32)."""
+    from . import fem
+    L.require_cuda(images)
+    if images.shape[-1] != 3:
+        raise ValueError("TVSNet_feature_extraction expects images (B,N,H,W,3), got %s" % (tuple(images.shape),))
+    return fem.ResNetDS2SPP(images[:, view_i])
+
+
+def _pair_features(images, ref_i, view_i):
+    """(ref_feature, view_feature) of an image tensor (B,N,H,W,3) through the FEM, or slices of a feature tensor
+    (B,N,h,w,F) when the caller already holds features."""
+    if images.shape[-1] == 3:
+        return TVSNet_feature_extraction(images, ref_i), TVSNet_feature_extraction(images, view_i)
+    return images[:, ref_i], images[:, view_i]
+
+
+def _tvsnet_base(ref, view, cams, depth_num, depth_start, depth_interval, view_i):
     cost_vol = build_cost_volume(ref, view, cams, depth_num, depth_start, depth_interval, ref_id=0, view_id=view_i,
                                  out_dtype=_cost_dtype())
     prob_vol_b2, filtered = cost_volume_reasoning(cost_vol, output_filtered_cost=True)
@@ -135,13 +152,48 @@ def TVSNet_base(features, cams, depth_num, depth_start, depth_interval, view_i, 
     return depth_b2, prob_vol_b2, filtered
 
 
-def TVSNet_base_siamese(features, cams, depth_num, depth_start, depth_interval, view_i, ref_i=0):
-    """model.py:398-417 with features in place of images: forward volume (ref <- view_i) and
-    the reverse one (view_i as reference) for ``depth_view``."""
-    depth_b2, prob_vol_b2, filtered = TVSNet_base(features, cams, depth_num, depth_start, depth_interval, view_i, ref_i)
-    ref, view = features[:, ref_i], features[:, view_i]
+def _tvsnet_reverse(ref, view, cams, depth_num, depth_start, depth_interval, view_i):
     cost_vol_view = build_cost_volume(view, ref, cams, depth_num, depth_start, depth_interval, ref_id=view_i, view_id=0,
                                       out_dtype=_cost_dtype())
     prob_vol_view = cost_volume_reasoning(cost_vol_view, output_filtered_cost=False, reuse=AUTO_REUSE)
-    depth_view = prob2depth(prob_vol_view, depth_num, depth_start, depth_interval, out_prob_map=False)
+    return prob2depth(prob_vol_view, depth_num, depth_start, depth_interval, out_prob_map=False)
+
+
+def TVSNet_base(images, cams, depth_num, depth_start, depth_interval, view_i, ref_i=0):
+    """model.py:380-395: images (B,N,H,W,3), cams (B,N,2,4,4) -> (depth_b2 (B,h,w,1), prob_vol_b2 (B,D,h,w),
+    filtered_cost_volume (B,D,h,w,8))."""
+    ref, view = _pair_features(images, ref_i, view_i)
+    return _tvsnet_base(ref, view, cams, depth_num, depth_start, depth_interval, view_i)
+
+
+def TVSNet_base_siamese(images, cams, depth_num, depth_start, depth_interval, view_i, ref_i=0):
+    """model.py:398-417: forward volume (ref <- view_i) and the reverse one (view_i as reference) for
+    ``depth_view``; -> (depth_b2, prob_vol_b2, filtered_cost_volume, depth_view)."""
+    ref, view = _pair_features(images, ref_i, view_i)
+    depth_b2, prob_vol_b2, filtered = _tvsnet_base(ref, view, cams, depth_num, depth_start, depth_interval, view_i)
+    depth_view = _tvsnet_reverse(ref, view, cams, depth_num, depth_start, depth_interval, view_i)
     return depth_b2, prob_vol_b2, filtered, depth_view
+
+
+def TVSNet(images, cams, depth_num, depth_start, depth_interval, view_i, ref_i=0):
+    """model.py:346-377, the two-view network: FEM on both images, both directions of the cost volume + CRM, then the
+    refinement stage on (depth_b2, depth_view) -> refined_prob_vol (B,D,h,w) = prob_vol_b2 + residual."""
+    from . import refine
+    if images.shape[-1] != 3:
+        raise ValueError("TVSNet (two-view, with refinement) needs the images (B,N,H,W,3), got %s" % (tuple(images.shape),))
+    ref, view = _pair_features(images, ref_i, view_i)
+    depth_view = _tvsnet_reverse(ref, view, cams, depth_num, depth_start, depth_interval, view_i)
+    depth_b2, prob_vol_b2, _ = _tvsnet_base(ref, view, cams, depth_num, depth_start, depth_interval, view_i)
+    init = torch.stack([L.f32c(depth_b2), L.f32c(depth_view)], dim=1).contiguous()
+    _, prob_residual = refine.refinement(init, cams, depth_num, depth_start, depth_interval, images, prob_vol_b2,
+                                         ref_id=ref_i, view_id=view_i, view_homographies=None, num_depths=2,
+                                         depth_ref_id=0, depth_view_id=1)
+    return refine.fem.add(L.f32c(prob_vol_b2), prob_residual.contiguous())
+
+
+def TVSNet_refine(depth_b2, depth_view, prob_vol_b2, filtered_cost_volume, images, cams, depth_num, depth_start,
+                  depth_interval, view_i, ref_i=0):
+    """model.py:428-441 -> (refined_prob_vol (B,D,h,w), refined_cost_volume (B,D,h,w,8))."""
+    from . import refine
+    return refine.TVSNet_refine(depth_b2, depth_view, prob_vol_b2, filtered_cost_volume, images, cams, depth_num,
+                                depth_start, depth_interval, view_i, ref_i)

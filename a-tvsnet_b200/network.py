@@ -7,9 +7,9 @@ Differences that are deliberate and invisible at the call surface:
     that batch-norm (batch statistics, no affine: network.py:206-212 with
     ``training=True, center=False, scale=False``), ReLU and the ``add`` skip joins run as ONE
     fused elementwise kernel per conv layer instead of separate graph ops;
-  * activations between layers are bf16 when ``FLAGS.precision == 'bf16'`` (tcgen05 path)
-    and fp32 when ``'fp32'`` (CUDA-core parity path); BN moments always come from the fp32
-    accumulators;
+  * activations between layers are fp16 (default) or bf16 when ``FLAGS.precision`` is
+    ``'fp16'`` / ``'bf16'`` (tcgen05 path) and fp32 when ``'fp32'`` (CUDA-core parity path); BN
+    moments always come from the fp32 accumulators;
   * variables are looked up by their TF checkpoint names in ``variables``.
 """
 from collections import OrderedDict
@@ -27,8 +27,25 @@ BN_EPS = 1e-3   # tf.layers.batch_normalization default (network.py:206)
 PROFILE = None
 
 
+_ACT = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}
+HALF_DTYPES = (torch.bfloat16, torch.float16)
+
+
 def act_dtype():
-    return torch.bfloat16 if FLAGS.precision == 'bf16' else torch.float32
+    try:
+        return _ACT[FLAGS.precision]
+    except KeyError:
+        raise ValueError("FLAGS.precision must be 'fp16', 'bf16' or 'fp32' (got %r)" % (FLAGS.precision,))
+
+
+def _same_shape(who, tensors):
+    """every operand of a skip join must have the lead tensor's shape (TF raises on a mismatch; the fused kernels size
+    their launch from the lead tensor)."""
+    lead = tuple(tensors[0].shape)
+    for t in tensors[1:]:
+        if t is not None and tuple(t.shape) != lead:
+            raise ValueError("%s: operand shapes differ: %s vs %s (volumes must be divisible by 8 in D, H and W for the "
+                             "stride-2 down / up path to line up)" % (who, lead, tuple(t.shape)))
 
 
 def to_act(t):
@@ -38,19 +55,33 @@ def to_act(t):
     t = t.contiguous()
     if t.dtype == dt:
         return t
-    if t.dtype not in (torch.float32, torch.bfloat16):
+    if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         t = t.float()
+    if t.dtype in HALF_DTYPES and dt in HALF_DTYPES:      # bf16 <-> fp16: through fp32
+        t = to_dtype(t, torch.float32)
+    return to_dtype(t, dt)
+
+
+def to_dtype(t, dt):
+    if t.dtype == dt:
+        return t
     out = torch.empty(t.shape, dtype=dt, device=t.device)
     L.call("atvs_cast", L.ptr(t), L.dtype_code(t), L.ptr(out), L.dtype_code(out), t.numel(), L.stream())
     return out
 
 
-def _packed_weight(key, w, cin, cout, transposed):
+def _dt_code(dt):
+    return {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}[dt]
+
+
+def _packed_weight(key, w, cin, cout, transposed, dt):
+    """16-bit weight images of one layer (all kernel formulations), cached per (variable, format)."""
     cache = V.packed_cache()
+    key = key + ('|bf16' if dt == torch.bfloat16 else '|f16')
     if key not in cache:
         nbytes = L.load().atvs_packed_weight_bytes(cin, cout, transposed)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        L.call("atvs_pack_conv_weights_bf16", L.ptr(w), cin, cout, transposed, L.ptr(buf), L.stream())
+        L.call("atvs_pack_conv_weights_tc", L.ptr(w), cin, cout, transposed, _dt_code(dt), L.ptr(buf), L.stream())
         cache[key] = buf
     return cache[key]
 
@@ -60,21 +91,22 @@ class SplitCostVolume(object):
     its two parts: ``ref`` (B,h,w,F) and ``warped`` (B,D,h,w,F).  A convolution over the concatenation
     is linear in the halves, and the ``tile(ref, D)`` half is the same 2-D result on every interior
     plane, so the first CRM layers run on the F warped channels only and add the reference part as a
-    per-plane-class bias in their epilogue (atvs_conv3d_bf16_bias).  Halves the dominant layer's work
+    per-plane-class bias in their epilogue (atvs_conv3d_tc_bias).  Halves the dominant layer's work
     and the volume K1 has to write; results equal the concatenated form up to fp32 summation order."""
 
     def __init__(self, ref, warped):
-        if warped.dtype != torch.bfloat16:
-            raise ValueError("SplitCostVolume is a bf16 tensor-core path construct")
+        if warped.dtype not in HALF_DTYPES:
+            raise ValueError("SplitCostVolume is a tensor-core path construct (fp16 / bf16 volumes)")
         self.ref, self.warped = ref, warped
         self.shape = tuple(warped.shape[:-1]) + (warped.shape[-1] + ref.shape[-1],)
         self.device = warped.device
+        self.dtype = warped.dtype
         self._tiled = {}
 
     def ref_tiled(self, planes):
         if planes not in self._tiled:
             B, h, w, F = self.ref.shape
-            r = to_act(self.ref)
+            r = to_dtype(self.ref.contiguous(), self.warped.dtype)
             self._tiled[planes] = r[:, None].expand(B, planes, h, w, F).contiguous()
         return self._tiled[planes]
 
@@ -94,15 +126,7 @@ def conv3d_split(cv, wkey, w, cout, stride, stats_buf):
     w_ref, w_warp = _split_weights(wkey, w, F)
     bias = _split_bias(cv, wkey, w_ref, cout, stride)
     return conv3d_raw(cv.warped, wkey + '/warp', w_warp, cout, stride, False, True, stats_buf, bias=bias,
-                      raw_dtype=raw_dtype_for_bn(cv.warped))
-
-
-# fuse the two convolutions that open every U-Net block (8 ch stride 1 + 16 ch stride 2 on the same tensor) into
-# one pass over the input (atvs_conv3d_bf16_dual).  Correct (tests/test_gpu_parity.py::test_conv3d_dual_head) but
-# NOT faster on B200 as built: at cfg2 the fused launch takes 101 us (Cin 8) / 175 us (Cin 32) against 45 + 47 /
-# 97 + 85 us for the two separate kernels - the accumulator ring that fits two CTAs per SM is only 5 planes deep
-# and the 4 epilogue warps become the critical path (profiles/r01_dual_head_probe.txt).  Opt-in: ATVS_DUAL=1.
-DUAL_HEAD = __import__('os').environ.get('ATVS_DUAL') is not None
+                      raw_dtype=raw_dtype_for_bn(cv.warped, first=True))
 
 
 def _split_bias(cv, wkey, w_ref, cout, stride):
@@ -114,59 +138,12 @@ def _split_bias(cv, wkey, w_ref, cout, stride):
     return bias
 
 
-def dual_supported(x):
-    xin = x.warped if isinstance(x, SplitCostVolume) else x
-    if xin.dtype != torch.bfloat16:
-        return False
-    B, D, H, W, cin = xin.shape
-    return bool(L.load().atvs_conv3d_bf16_dual_supported(B, D, H, W, cin))
-
-
-def conv3d_dual(x, wkey1, w1, wkey2, w2, stats1, stats2):
-    """conv(x, w1) with 8 channels, stride 1 and conv(x, w2) with 16 channels, stride 2 in ONE pass over x (tensor or
-    SplitCostVolume).  Returns (raw1, stats1), (raw2, stats2); raw dtype = raw_dtype_for_bn."""
-    if w1.shape[-1] != 8 or w2.shape[-1] != 16:
-        raise ValueError("conv3d_dual: heads must have 8 and 16 output channels")
-    bias1 = bias2 = None
-    if isinstance(x, SplitCostVolume):
-        F = x.ref.shape[-1]
-        w1r, w1w = _split_weights(wkey1, w1, F)
-        w2r, w2w = _split_weights(wkey2, w2, F)
-        bias1 = _split_bias(x, wkey1, w1r, 8, 1)
-        bias2 = _split_bias(x, wkey2, w2r, 16, 2)
-        xin, wa, wb = x.warped, w1w, w2w
-    else:
-        xin, wa, wb = x, w1, w2
-    B, D, H, W, cin = xin.shape
-    cache = V.packed_cache()
-    ck = wkey1 + '|' + wkey2 + '/dual'
-    if ck not in cache:
-        cache[ck] = torch.cat([wa, wb, torch.zeros(wa.shape[:-1] + (8,), dtype=wa.dtype, device=wa.device)], dim=-1).contiguous()
-    if ck + '/packed' not in cache:
-        buf = torch.empty(L.load().atvs_dual_weight_bytes(cin), dtype=torch.uint8, device=xin.device)
-        L.call("atvs_pack_conv_weights_dual", L.ptr(cache[ck]), cin, L.ptr(buf), L.stream())
-        cache[ck + '/packed'] = buf
-    pk = cache[ck + '/packed']
-    rd = raw_dtype_for_bn(xin)
-    raw1 = torch.empty((B, D, H, W, 8), dtype=rd, device=xin.device)
-    raw2 = torch.empty((B, D // 2, H // 2, W // 2, 16), dtype=rd, device=xin.device)
-    s1, s2 = stats1[:16], stats2[:32]
-    prof = PROFILE is not None and PROFILE[0](wkey1)
-    if prof:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    L.call("atvs_conv3d_bf16_dual", L.ptr(xin), L.ptr(pk), B, D, H, W, cin, L.ptr(bias1), L.ptr(bias2), L.ptr(raw1),
-           L.ptr(raw2), _raw_code(raw1), L.ptr(s1), L.ptr(s2), L.stream())
-    if prof:
-        e1.record()
-        PROFILE[1].append((wkey1 + '+' + wkey2, e0, e1, raw1.numel() // 8, cin, 24))
-    return (raw1, s1), (raw2, s2)
-
-
-def raw_dtype_for_bn(x):
+def raw_dtype_for_bn(x, first=False):
     """dtype of a raw convolution output that only feeds the BN pass: fp16 on the tensor-core path
-    (FLAGS.raw_dtype = 'f16': saturated, moments still from the fp32 accumulators), fp32 otherwise."""
-    if x.dtype == torch.bfloat16 and getattr(FLAGS, 'raw_dtype', 'f16') == 'f16':
+    (FLAGS.raw_dtype = 'f16': saturated, moments still from the fp32 accumulators), fp32 otherwise.
+    ``first``: the layer reads the un-normalised cost volume (FLAGS.first_raw_dtype)."""
+    flag = getattr(FLAGS, 'first_raw_dtype', 'f32') if first else getattr(FLAGS, 'raw_dtype', 'f16')
+    if x.dtype in HALF_DTYPES and flag == 'f16':
         return torch.float16
     return torch.float32
 
@@ -202,12 +179,12 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None,
         L.call("atvs_conv3d_fp32", L.ptr(x), L.ptr(w), B, D, H, W, cin, cout, stride, int(transposed),
                L.ptr(raw), L.ptr(stats), L.stream())
     else:
-        pk = _packed_weight(wkey, w, cin, cout, int(transposed))
+        pk = _packed_weight(wkey, w, cin, cout, int(transposed), x.dtype)
         if bias is not None:
-            L.call("atvs_conv3d_bf16_bias", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, L.ptr(bias),
+            L.call("atvs_conv3d_tc_bias", L.ptr(x), L.dtype_code(x), L.ptr(pk), B, D, H, W, cin, cout, stride, L.ptr(bias),
                    L.ptr(raw), _raw_code(raw), L.ptr(stats), L.stream())
         else:
-            L.call("atvs_conv3d_bf16", L.ptr(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
+            L.call("atvs_conv3d_tc", L.ptr(x), L.dtype_code(x), L.ptr(pk), B, D, H, W, cin, cout, stride, int(transposed),
                    L.ptr(raw), _raw_code(raw), L.ptr(stats), L.stream())
     if prof:
         e1.record()
@@ -221,8 +198,12 @@ def bn_relu_add(raw, stats, relu, skips, want_plain, want_sum, dtype):
     summ = torch.empty(raw.shape, dtype=dtype, device=raw.device) if want_sum else None
     s1 = skips[0] if len(skips) > 0 else None
     s2 = skips[1] if len(skips) > 1 else None
+    _same_shape("add", [raw, s1, s2])
+    for sk in (s1, s2):
+        if sk is not None and sk.dtype != dtype:
+            raise RuntimeError("bn_relu_add: skip dtype %s != activation dtype %s" % (sk.dtype, dtype))
     L.call("atvs_bn_relu_add", L.ptr(raw), _raw_code(raw), L.ptr(stats), count, raw.shape[-1], BN_EPS, int(relu), L.ptr(s1),
-           L.ptr(s2), L.ptr(plain), L.ptr(summ), L.F32 if dtype == torch.float32 else L.BF16, L.stream())
+           L.ptr(s2), L.ptr(plain), L.ptr(summ), _dt_code(dtype), L.stream())
     return plain, summ
 
 
@@ -241,9 +222,9 @@ def bn_relu_add_pair(raw_a, stats_a, pend, relu, skip, want_plain, dtype):
     summ = torch.empty(raw_a.shape, dtype=dtype, device=raw_a.device)
     if pend.raw.dtype != raw_a.dtype:
         raise RuntimeError("bn_relu_add_pair: raw dtypes differ")
+    _same_shape("add", [raw_a, pend.raw, skip])
     L.call("atvs_bn_relu_add_pair", L.ptr(raw_a), L.ptr(stats_a), L.ptr(pend.raw), L.ptr(pend.stats), _raw_code(raw_a), count,
-           raw_a.shape[-1], BN_EPS, int(relu), L.ptr(skip), L.ptr(plain), L.ptr(summ),
-           L.F32 if dtype == torch.float32 else L.BF16, L.stream())
+           raw_a.shape[-1], BN_EPS, int(relu), L.ptr(skip), L.ptr(plain), L.ptr(summ), _dt_code(dtype), L.stream())
     return plain, summ
 
 
@@ -384,7 +365,6 @@ class Network(object):
                 nodes[name].value = v      # cast once
             return v
 
-        precomputed = {}     # conv_bn node -> (raw, stats) already produced by its partner's dual-head launch
         for name in order:
             node = nodes[name]
             if name in done:
@@ -393,35 +373,13 @@ class Network(object):
                 x = act_in(node.inputs[0])
                 transposed = node.kind == 'deconv_bn'
                 wname = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
-                partner = None
-                if DUAL_HEAD and not transposed and name not in precomputed and dual_supported(x):
-                    # the other convolution that opens this block: same input, (8 ch, stride 1) <-> (16 ch, stride 2)
-                    want = (8, 1) if (node.params['filters'], node.params['stride']) == (16, 2) else \
-                        ((16, 2) if (node.params['filters'], node.params['stride']) == (8, 1) else None)
-                    if want is not None:
-                        for other in consumers[node.inputs[0]]:
-                            on = nodes[other]
-                            if (other != name and other not in done and other not in precomputed and on.kind == 'conv_bn'
-                                    and on.inputs[0] == node.inputs[0]
-                                    and (on.params['filters'], on.params['stride']) == want):
-                                partner = other
-                                break
-                if name in precomputed:
-                    raw, stats = precomputed.pop(name)
-                elif partner is not None:
-                    n1, n2 = (name, partner) if node.params['stride'] == 1 else (partner, name)
-                    k1, k2 = n1 + '/conv3d/kernel', n2 + '/conv3d/kernel'
-                    r1, r2 = conv3d_dual(x, k1, V.get_variable(k1), k2, V.get_variable(k2), arena[arena_slot[n1]],
-                                         arena[arena_slot[n2]])
-                    raw, stats = r1 if n1 == name else r2
-                    precomputed[partner] = r2 if n1 == name else r1
-                elif isinstance(x, SplitCostVolume):
+                if isinstance(x, SplitCostVolume):
                     raw, stats = conv3d_split(x, wname, V.get_variable(wname), node.params['filters'],
                                               node.params['stride'], arena[arena_slot[name]])
                 else:
                     raw, stats = conv3d_raw(x, wname, V.get_variable(wname), node.params['filters'],
                                             node.params['stride'], transposed, True, arena[arena_slot[name]],
-                                            raw_dtype=raw_dtype_for_bn(x))
+                                            raw_dtype=raw_dtype_for_bn(x, first=nodes[node.inputs[0]].kind == 'input'))
                 # a layer that only feeds an `add` led by a LATER conv layer is normalised inside that
                 # layer's fused pass: keep its raw output and moments until then
                 cons = consumers[name]
@@ -430,7 +388,8 @@ class Network(object):
                         and nodes[nodes[cons[0]].inputs[0]].kind in ('conv_bn', 'deconv_bn')
                         and pos[nodes[cons[0]].inputs[0]] > pos[name]
                         and not any(isinstance(nodes[i].value, _PendingRaw) for i in nodes[cons[0]].inputs)
-                        and nodes[nodes[cons[0]].inputs[0]].params['relu'] == node.params['relu']):
+                        and nodes[nodes[cons[0]].inputs[0]].params['relu'] == node.params['relu']
+                        and raw.dtype == raw_dtype_for_bn(x)):
                     node.value = _PendingRaw(raw, stats, node.params['relu'])
                     done.add(name)
                     release(node.inputs)
@@ -472,6 +431,7 @@ class Network(object):
                 release(node.inputs)
             elif node.kind == 'add':
                 vals = [act_in(i) for i in node.inputs]
+                _same_shape("add(%s)" % name, vals)
                 out = torch.empty_like(vals[0])
                 L.call("atvs_add", L.ptr(vals[0]), L.ptr(vals[1]), L.ptr(out), L.dtype_code(out), out.numel(),
                        L.stream())
@@ -550,7 +510,7 @@ def attention_activations(views, scope):
     dt = views[0].dtype
     act = torch.empty(raw.shape, dtype=dt, device=raw.device)
     L.call("atvs_bn_relu_add", L.ptr(raw), _raw_code(raw), None, raw.shape[0] * raw.shape[1], raw.shape[2], BN_EPS, 1, None, None,
-           L.ptr(act), None, L.F32 if dt == torch.float32 else L.BF16, L.stream())
+           L.ptr(act), None, _dt_code(dt), L.stream())
     return act
 
 

@@ -2,7 +2,9 @@
 view, stage II = AAM1 -> output_conv -> prob2depth) run entirely on the device: the
 filtered cost volumes stay in HBM (no np.stack / feed_dict round trips), and source views
 can be sharded over ranks with one max + one sum all-reduce of the attention partials
-(SURVEY.md section 8(e)).  Stages III/IV (refinement) are outside the current scope."""
+(SURVEY.md section 8(e)).  run_example_schedule adds stages III/IV (refinement, example.py:163-181),
+run_twoview is the single-shot two-view schedule (example.py:219-303).  Entry points take IMAGES
+(B,N,H,W,3) or, to skip the 2-D feature extractor, FEATURES (B,N,h,w,32)."""
 import torch
 
 from . import _lib as L
@@ -10,7 +12,7 @@ from . import network as N
 from .atvsnet import OutputConv, StackedUNet_prob
 from .model import _prob2depth, build_cost_volume
 
-# bf16 path: run the first CRM layers on the warped half only (network.SplitCostVolume)
+# tensor-core path: run the first CRM layers on the warped half only (network.SplitCostVolume)
 SPLIT_COST_VOLUME = True
 # number of CUDA streams the independent stage-I passes are spread over
 CONCURRENT_PASSES = int(__import__('os').environ.get('ATVS_PASSES', '4'))
@@ -18,7 +20,7 @@ CONCURRENT_PASSES = int(__import__('os').environ.get('ATVS_PASSES', '4'))
 
 def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid):
     dt = N.act_dtype()
-    if dt == torch.bfloat16 and SPLIT_COST_VOLUME:
+    if dt in N.HALF_DTYPES and SPLIT_COST_VOLUME:
         # [tile(ref) | warped] kept as its halves: K1 writes only the warped 32 channels
         warped = build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
                                    mode='warped_only', out_dtype=dt)
@@ -50,6 +52,7 @@ def stage1_view(features, cams, depth_num, depth_start, depth_interval, view_i, 
 
 
 _STREAMS = {}
+_WARM = set()      # (weights generation, precision, raw dtypes, split mode, device) whose weight images are packed
 
 
 def _side_streams(device, n):
@@ -157,11 +160,15 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
         for v, kind in tasks:
             results[(v, kind)] = run_task(v, kind)
     else:
-        if not N.V.packed_cache():
-            # first call after load_weights: run one pass on the main stream so that the packed bf16 weight
-            # images exist before other streams read them
+        warm = (N.V.generation(), N.FLAGS.precision, N.FLAGS.raw_dtype, N.FLAGS.first_raw_dtype, SPLIT_COST_VOLUME,
+                features.device.index)
+        if tasks and warm not in _WARM:
+            # first call with these weights in this precision / split mode: run one forward pass on the calling stream,
+            # so that every packed 16-bit weight image it needs (CRM, split halves, attention pair) is produced by
+            # kernels the side streams are ordered behind (st.wait_stream(main) below) before they read the cache
             v, kind = tasks.pop(0)
             results[(v, kind)] = run_task(v, kind)
+            _WARM.add(warm)
         streams = _side_streams(features.device, nstreams)
         for st in streams:
             st.wait_stream(main)
@@ -212,6 +219,66 @@ def run_example_schedule(images, cams, depth_num, features=None):
     out['depth_refined_up'], _ = _prob2depth(prob_ref, ds, di, 4, False)
     out.update(refined_cost_volume_agg=cost_ref, refined_prob_volume_agg=prob_ref, refined_prob_volumes=refined_probs)
     return out
+
+
+def run_twoview(images, cams, depth_num):
+    """The two-view driver of example.py:219-272 (run_test_twoview; taken when only two views exist, example.py:344-347):
+    TVSNet (FEM on both images, both directions, refinement) -> prob2depth_upsample.  images (B,2,H,W,3) raw 0..255 BGR,
+    cams (B,2,2,4,4) at feature resolution -> dict(refined_prob_volume, depth_refined, depth_refined_up)."""
+    from .model import TVSNet
+    L.require_cuda(images, cams)
+    cams = L.f32c(cams)
+    ds = cams[:, 0, 1, 3, 0].contiguous()
+    di = cams[:, 0, 1, 3, 1].contiguous()
+    refined = TVSNet(images, cams, depth_num, ds, di, view_i=1, ref_i=0)
+    est, _ = _prob2depth(refined, ds, di, 1, False)
+    est_up, _ = _prob2depth(refined, ds, di, 4, False)
+    return dict(refined_prob_volume=refined, depth_refined=est, depth_refined_up=est_up)
+
+
+def inverse_to_depth(out, twoview=False):
+    """host epilogue of example.py:183-186 (multi-view: values below 1e-10 become inf) / :269-272 (two-view: values <= 0
+    become inf), then depth = 1 / inverse depth.  Tensor in, tensor out (same device)."""
+    out = out.clone()
+    out[(out <= 0) if twoview else (out < 1e-10)] = float('inf')
+    return 1.0 / out
+
+
+def run_example(images, cams, depth_num=None):
+    """example.py:main dispatch (:344-347): the multi-view schedule for more than two views, the two-view network
+    otherwise.  Returns the final x4 inverse-depth map (B,H,W,1) and ``pred`` = depth (what example.py saves)."""
+    n_views = cams.shape[1]
+    D = int(depth_num if depth_num is not None else N.FLAGS.max_d)
+    if n_views > 2:
+        out = run_example_schedule(images, cams, D)
+        inv = out['depth_refined_up']
+    else:
+        out = run_twoview(images, cams, D)
+        inv = out['depth_refined_up']
+    out['pred'] = inverse_to_depth(inv, twoview=n_views <= 2)
+    return out
+
+
+def load_example(data_root, view_num=5):
+    """input loading of example.py:312-342: ``{i}.jpg`` (cv2.imread: BGR uint8, fed un-normalised) and ``{i}_cam.npy``
+    (2,4,4: extrinsic; intrinsic at feature resolution with depth_start / depth_interval in row 3) for i < view_num,
+    shrunk to the views that exist.  Returns (images (1,N,H,W,3) float32, cams (1,N,2,4,4) float32, depth_gt | None)
+    as NumPy arrays (host side, as in the reference)."""
+    import os
+    import cv2
+    import numpy as np
+    images, cams = [], []
+    for i in range(view_num):
+        ip, cp = os.path.join(data_root, '%d.jpg' % i), os.path.join(data_root, '%d_cam.npy' % i)
+        if not (os.path.exists(ip) and os.path.exists(cp)):
+            break
+        images.append(cv2.imread(ip))
+        cams.append(np.load(cp))
+    if not images:
+        raise FileNotFoundError("no {i}.jpg / {i}_cam.npy pairs under %s" % data_root)
+    gt = os.path.join(data_root, '0_gt.npy')
+    return (np.stack(images)[None].astype(np.float32), np.stack(cams)[None].astype(np.float32),
+            np.load(gt) if os.path.exists(gt) else None)
 
 
 class FrameStream(object):

@@ -74,6 +74,9 @@ def _conv_bn(x, name, stride=1, transposed=False):
 def CostVolRefineNet(photo_group, geo_group, prob_vol, vis_hull):
     """cnn_wrapper/atvsnet.py:295-336 -> (global_refine_3dconv6_1 (B,D,H,W,8), global_refined_cost_vol (B,D,H,W,1))."""
     p = 'global_refine_'
+    if any(int(n) % 8 for n in photo_group.shape[1:4]):
+        raise ValueError("CostVolRefineNet: D, h, w must be multiples of 8 (three stride-2 levels joined by `add`), got %s"
+                         % (tuple(photo_group.shape[1:4]),))
     cat = torch.cat([_conv_bn(photo_group, p + 'photo_3dconv'), _conv_bn(geo_group, p + 'geo_3dconv'),
                      _conv_bn(prob_vol, p + 'prob_3dconv'), _conv_bn(vis_hull, p + 'vishull_3dconv')], dim=-1).contiguous()
     c10 = _conv_bn(cat, p + '3dconv1_0', 2)

@@ -10,6 +10,7 @@ import torch
 
 _STORE = {}
 _PACKED = {}
+_GENERATION = [0]
 
 
 def load_weights(weights, device='cuda'):
@@ -18,6 +19,7 @@ def load_weights(weights, device='cuda'):
         weights = dict(np.load(weights))
     _STORE.clear()
     _PACKED.clear()
+    _GENERATION[0] += 1
     for k, v in weights.items():
         _STORE[k] = torch.as_tensor(np.asarray(v, dtype=np.float32)).to(device).contiguous()
 
@@ -35,6 +37,12 @@ def has_variable(name):
 
 def packed_cache():
     return _PACKED
+
+
+def generation():
+    """bumped by every load_weights(): consumers that derive state from the store (packed weight images, warm-up
+    bookkeeping) key it on this."""
+    return _GENERATION[0]
 
 
 def crm_layer_table():

@@ -2,20 +2,23 @@
 """bench.py - depth maps / s of the A-TVSNet inference hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload cfg2|cfg3|cfg4] [--precision bf16|fp32] [--no-graph]
+                    [--workload cfg2|cfg3|cfg4] [--precision fp16|bf16|fp32] [--no-graph]
 
-One "step" = one depth map of the workload: stage I (TVSNet_base_siamese: fused warp +
-cost volume -> 3-D CNN regularisation -> soft-argmin, forward and reverse direction) for
-every source view, stage II (attention aggregation -> output conv) and the final x4
-upsampled soft-argmin, i.e. example.py:144-158 + :109 with features in.  The 2-D feature
-extractor and the refinement stages III/IV are outside the current scope.
+One "step" = one depth map of the workload: stage I (TVSNet_base_siamese: fused warp + cost volume -> 3-D CNN
+regularisation -> soft-argmin, forward and reverse direction) for every source view, stage II (attention aggregation
+-> output conv) and the final x4 upsampled soft-argmin, i.e. example.py:144-158 + :109 with features in.
 
-N = 1   : cfg2 (1 ref + 4 src, 640x512 images -> 128x160 features, D = 128).
-N > 1   : independent reference frames data-parallel, one frame stream per rank, no data-path
-          collective ("scaling": "weak");  --workload cfg3 instead shards the 8 source views
-          of ONE 1920x1056, D=256 frame over the ranks with a max + sum NCCL all-reduce.
---impl reference : the CPU oracle (NumPy/torch-CPU restatement of the TF-1.5 reference, which
-          cannot be installed offline) on the host cores, each step a bounded sample.
+N = 1   : cfg2 (1 ref + 4 src, 640x512 images -> 128x160 features, D = 128).  The line also carries, as declared extra
+          fields, the same depth map FROM IMAGES (2-D feature extractor included) and the whole four-stage example.py
+          schedule (refinement included), the roofline of the dominant kernel, K1 / K4 against the HBM peak and the CPU
+          oracle timed on the host cores.
+N > 1   : independent reference frames data-parallel, one frame stream per rank, no data-path collective ("scaling":
+          "weak");  the SAME invocation then also runs cfg3 - ONE 1920x1056, D=256 frame whose 8 source views are
+          sharded over the ranks, completed with an NCCL max + reduce-scatter + all-gather - and reports it under
+          "sharded" (with the same frame on rank 0 alone beside it).  --workload cfg3 makes that the headline instead.
+--impl reference : the CPU oracle (NumPy/torch-CPU restatement of the TF-1.5 reference, which cannot be installed
+          offline) on all host cores; each step is the FULL workload (every depth plane, every view); the number of timed
+          steps is capped so that the run ends within a few minutes and the JSON line says how many were timed.
 """
 import argparse
 import json
@@ -36,6 +39,7 @@ WORKLOADS = {
 }
 METRIC = "depth maps/sec"
 CRM_MAC_PER_VOXEL = 29592
+REF_BUDGET_S = float(os.environ.get('ATVS_REF_BUDGET_S', '240'))
 
 
 def peaks():
@@ -58,7 +62,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -71,7 +75,7 @@ class ClockSampler(object):
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -101,45 +105,91 @@ def make_inputs(workload, frame_seed):
     return feats, cams, D
 
 
+def common_config(workload, world, sharded):
+    """the `config` object BOTH arms print: names the workload and how it is spread over the GPUs, nothing arm-specific"""
+    nv, H, W, D = WORKLOADS[workload]
+    return {"workload": "%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II + x4 "
+                        "soft-argmin" % (workload, nv - 1, W, H, H // 4, W // 4, D),
+            "frames_per_step": 1 if sharded else world,
+            "parallelism": ("source views of one frame sharded over %d ranks, NCCL all-reduce(max) + reduce-scatter(sum) + "
+                            "all-gather" % world) if sharded else ("dp%d: independent frames per rank, no collective" % world),
+            "l2": "no explicit flush: every step streams > 3 GB of intermediate volumes through HBM (L2 = 126 MB)"}
+
+
 # ============================================================================ reference arm
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path = the oracle port (TF 1.5 / py2.7 cannot be
-    installed offline).  Each step = the full stage I+II schedule on a D/8 slab of the planes."""
+    """The reference's CPU implementation of the path = the oracle port (TF 1.5 / py2.7 cannot be installed offline), all
+    host cores, FULL workload per step (all depth planes, all source views, siamese stage I + stage II + x4 soft-argmin)."""
     if rank != 0:
         return
     import numpy as np
     import torch
     import atvsnet_b200 as A
     from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)            # torchrun exports OMP_NUM_THREADS=1: undo it, rank 0 owns the host here
     workload = args.workload or 'cfg2'
+    sharded = workload == 'cfg3' and world > 1
     feats, cams, D = make_inputs(workload, 0)
-    Ds = max(8, D // 8)
     weights = A.variables.synthetic_weights()
-    cores = torch.get_num_threads()
-    times = []
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        om.run_multiview_stage12(feats, cams, Ds, weights, siamese=True)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-    t = float(np.mean(times))
-    value = (Ds / float(D)) / t
     nv, H, W, _ = WORKLOADS[workload]
-    sample = ("all %d source views, stages I+II, full %dx%d features, depth planes [0,%d) of %d; value = (%d/%d) / "
-              "seconds per step (cost is linear in D)" % (nv - 1, H // 4, W // 4, Ds, D, Ds, D))
+    ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
+    om.TVSNet_base(feats[:, :2, :16, :16], cams, 8, ds, di, 1, weights)          # touch the code paths (not a step)
+    times, warm = [], []
+    t_run = time.perf_counter()
+    nwarm = min(args.warmup, 1)             # a full-size CPU step is ~30 s: one warm-up step at most
+    steps = args.steps
+    i = 0
+    while i < nwarm + steps:
+        t0 = time.perf_counter()
+        om.run_multiview_stage12(feats, cams, D, weights, siamese=True)
+        dt = time.perf_counter() - t0
+        (warm if i < nwarm else times).append(dt)
+        i += 1
+        if i >= nwarm + 1 and time.perf_counter() - t_run + dt > REF_BUDGET_S:
+            break                           # bounded run: stop once the next step would cross the budget
+    t = float(np.mean(times))
+    value = 1.0 / t
+    sample = ("full %s workload per step (all %d depth planes, %d source views, %dx%d features), %d of %d requested steps "
+              "timed inside a %.0f s budget, %d warm-up step(s)" % (workload, D, nv - 1, H // 4, W // 4, len(times), args.steps,
+                                                                   REF_BUDGET_S, len(warm)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "depth maps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: 1 ref + %d src, %dx%d, D=%d, features in" % (workload, nv - 1, W, H, D),
-                   "sample": sample},
+        "steps": len(times), "steps_requested": args.steps, "warmup": len(warm), "ms_per_step": 1e3 * t,
+        "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": common_config(workload, world, sharded),
         "cpu_baseline": {"value": value, "unit": "depth maps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "depth maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ============================================================================ our arm
+def capture(step_fn, torch):
+    """CUDA-graph capture of one step (after eager warm-up by the caller) -> (graph, output tensor)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            out = step_fn()
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    return graph, out
+
+
+def timed_steps(fn, steps, torch, barrier):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), res
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -156,18 +206,13 @@ def run_ours(args, rank, world, local_rank):
     sharded = workload == 'cfg3' and world > 1
     group = dist.group.WORLD if sharded else None
     allw = A.variables.synthetic_weights()
-    if args.from_images:
-        allw.update(A.variables.synthetic_fem_weights())
+    allw.update(A.variables.synthetic_fem_weights())
+    allw.update(A.variables.synthetic_refine_weights())
     A.variables.load_weights(allw, device=dev)
     feats, cams, D = make_inputs(workload, frame_seed=rank if not sharded else 0)
     nv, H, W, _ = WORKLOADS[workload]
     h, w = H // 4, W // 4
     V = D * h * w
-    if args.from_images:
-        # images in (example.py:332-336 feeds raw 0..255 BGR): the step starts with the 2-D feature extraction module
-        # (fp32 CUDA-core first path, a-tvsnet_b200/fem.py); `feats` then stands for the (1,N,H,W,3) image tensor
-        rng = np.random.default_rng(1000 + (rank if not sharded else 0))
-        feats = (127.5 + 50.0 * rng.standard_normal((1, nv, H, W, 3))).clip(0, 255).astype(np.float32)
 
     # pinned host buffers (end-to-end path) and resident device inputs (kernel path)
     feats_h = torch.from_numpy(feats).pin_memory()
@@ -179,9 +224,13 @@ def run_ours(args, rank, world, local_rank):
     depth_h = torch.empty((1, H, W, 1), dtype=torch.float32).pin_memory()
 
     def step():
-        f = A.fem.extract_features(feats_d) if args.from_images else feats_d
-        return A.pipeline.run_multiview(f, cams_d, D, siamese=True, upsample=True, group=group, rank=rank,
+        return A.pipeline.run_multiview(feats_d, cams_d, D, siamese=True, upsample=True, group=group, rank=rank,
                                         world=world)['depth_up']
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # warm-up (eager): compiles nothing, but sets kernel attributes, packs weights, fills the allocator
     for _ in range(max(args.warmup, 3)):
@@ -195,16 +244,7 @@ def run_ours(args, rank, world, local_rank):
     use_graph = not args.no_graph and not sharded
     graph = None
     if use_graph:
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
-                out = step()
-        torch.cuda.current_stream().wait_stream(s)
-        for _ in range(2):
-            graph.replay()
-        torch.cuda.synchronize()
+        graph, out = capture(step, torch)
 
     def run_step():
         if graph is not None:
@@ -212,28 +252,17 @@ def run_ours(args, rank, world, local_rank):
             return out
         return step()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---------------- timed region 1: inputs resident in HBM ----------------
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        res = run_step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total, res = timed_steps(run_step, args.steps, torch, barrier)
 
     # ---------------- timed region 2: end to end from / to pinned host memory ----------------
     # the public streaming call (pipeline.FrameStream): frames arrive in pinned host memory, every step copies its
     # inputs H2D and its depth map D2H; the copies of neighbouring frames overlap the step on their own streams
     fstream = None
-    if graph is not None and not args.from_images:
+    if graph is not None:
         fstream = A.pipeline.FrameStream(tuple(feats_h.shape), tuple(cams_h.shape), D, dev, siamese=True)
         for dm in fstream.run([(feats_h, cams_h)] * 3):
             pass
@@ -264,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- dominant kernel, timed with CUDA events on its launch stream ----------------
     roof = None
-    if args.precision == 'bf16':
+    if args.precision != 'fp32':
         sink = []
         N.PROFILE = (lambda key: key in ('conv_b0_0_1/conv3d/kernel', 'conv_b0_0_1/conv3d/kernel/warp'), sink)
         for _ in range(2):
@@ -281,15 +310,55 @@ def run_ours(args, rank, world, local_rank):
                 "kernel": "k_conv3d_ring<%d,8,2> (conv_b0_0_1, %d->8 stride 1 on %d voxels%s)"
                           % (cin, cin, nvox, "; the 32 tiled-reference channels enter as an epilogue bias" if cin == 32 else ""),
                 "achieved": ach, "peak": pk['bf16_sustained'], "unit": "TFLOP/s", "frac": ach / pk['bf16_sustained'],
-                "traffic": None, "peak_source": pk['src'] + " (sustained bf16)", "ms_per_launch": t_ms,
-                "launches_timed": len(ts), "algorithmic_flops_per_launch": flops}
+                "traffic": None, "peak_source": pk['src'] + " (sustained bf16 = fp16 rate of tcgen05.mma.kind::f16)",
+                "ms_per_launch": t_ms, "launches_timed": len(ts), "algorithmic_flops_per_launch": flops}
 
     # ---------------- the HBM-bound kernels of the path (K1, K4) on this workload's shapes ----------------
     kernels = None
-    if rank == 0 and args.precision == 'bf16' and not args.from_images:
-        kernels = hbm_kernel_lines(A, feats_d, cams_d, D, h, w, res if res is not None else out)
+    if rank == 0 and args.precision != 'fp32':
+        kernels = hbm_kernel_lines(A, feats_d, cams_d, D, h, w, N.act_dtype())
         if roof is not None:
             roof["traffic"], roof["traffic_source"] = ncu_traffic("k_conv3d_ring<32, 8, 2>")
+
+    # ---------------- N = 1: the same depth map from IMAGES, and the whole four-stage schedule ----------------
+    extras = {}
+    if world == 1 and not args.no_extras and args.precision != 'fp32':
+        rng = np.random.default_rng(1000)
+        imgs_h = torch.from_numpy((127.5 + 50.0 * rng.standard_normal((1, nv, H, W, 3))).clip(0, 255).astype(np.float32)).pin_memory()
+        imgs_d = imgs_h.to(dev)
+
+        def step_images():
+            return A.pipeline.run_multiview(A.fem.extract_features(imgs_d), cams_d, D, siamese=True)['depth_up']
+
+        def step_four():
+            return A.pipeline.run_example_schedule(imgs_d, cams_d, D)['depth_refined_up']
+
+        for name, fn, what in (("from_images", step_images, "IMAGES in: 2-D feature extractor (ResNetDS2SPP) on the 5 views + stages I + II + x4 soft-argmin"),
+                               ("four_stage", step_four, "IMAGES in: the whole example.py:144-181 schedule (FEM, stages I-IV with refinement)")):
+            try:
+                for _ in range(2):
+                    o = fn()
+                torch.cuda.synchronize()
+                k = max(3, min(args.steps, 10))
+                graphed = name == "from_images" and not args.no_graph
+                if graphed:
+                    g, o = capture(fn, torch)
+                    ms, _ = timed_steps(lambda: g.replay(), k, torch, barrier)
+                    del g
+                else:           # stages III / IV go through torch glue that is not captured: eager launches
+                    ms, o = timed_steps(fn, k, torch, barrier)
+                extras[name] = {"what": what, "ms_per_step": ms / k, "value": k / (ms * 1e-3), "unit": "depth maps/s",
+                                "steps": k, "cuda_graph": graphed, "finite": bool(torch.isfinite(o).all())}
+                del o
+            except Exception as e:       # an extra must never take the headline line down with it
+                extras[name] = {"what": what, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.synchronize()
+        del imgs_d
+
+    # ---------------- N > 1: ONE cfg3 frame with its source views sharded over the ranks ----------------
+    sharded_line = None
+    if world > 1 and not sharded and not args.no_extras:
+        sharded_line = run_sharded_cfg3(A, dist, torch, dev, rank, world, local_rank, barrier)
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -299,28 +368,32 @@ def run_ours(args, rank, world, local_rank):
     maps_per_step = 1 if sharded else world
     value = maps_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = maps_per_step * args.steps / (ms_e2e * 1e-3)
+    all_clocks = [clocks]
+    if world > 1:
+        all_clocks = [None] * world
+        dist.all_gather_object(all_clocks, clocks)
 
     if rank != 0:
         return
     crm_passes = 2 * (nv - 1)
     flops_step = 2.0 * CRM_MAC_PER_VOXEL * V * crm_passes + 2.0 * 2 * 27 * 64 * V * (nv - 1) + 2.0 * 216 * V
+    # the line's clocks: the slowest rank's median, the union of the reasons, per-rank detail beside it
+    sm = [c.get("sm_mhz") for c in all_clocks if c.get("sm_mhz") is not None]
+    clk = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": all_clocks[0].get("sm_max_mhz"),
+           "reasons": sorted(set(r for c in all_clocks for r in c.get("reasons", []))),
+           "samples": min(c.get("samples", 0) for c in all_clocks), "per_rank": all_clocks}
     line = {
         "metric": METRIC, "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == 'bf16' else "f32", "data": "synthetic",
-        "config": {"workload": ("%s: 1 ref + %d src, %dx%d images -> %dx%dx32 features in, D=%d, stages I (siamese) + II "
-                                "+ x4 soft-argmin; FEM and refinement not included" % (workload, nv - 1, W, H, h, w, D))
-                   if not args.from_images else
-                   ("%s: 1 ref + %d src, %dx%d IMAGES in, FEM (fp32 CUDA-core first path) -> %dx%dx32 features, D=%d, "
-                    "stages I (siamese) + II + x4 soft-argmin; refinement not included" % (workload, nv - 1, W, H, h, w, D)),
-                   "frames_per_step": maps_per_step,
-                   "parallelism": ("source views sharded over %d ranks; NCCL all-reduce(max, bf16) + reduce-scatter(sum, fp32) + all-gather(result)" % world) if sharded
-                   else ("dp%d: independent frames per rank, no collective" % world),
-                   "l2": "no explicit flush: every step streams > 3 GB of intermediate volumes (L2 = 126 MB)",
-                   "cuda_graph": graph is not None,
-                   "tensor_flops_per_step": flops_step,
-                   "tensor_tflops_whole_step": flops_step * maps_per_step * args.steps / (ms_total * 1e-3) / 1e12 / world},
+        "dtype": {"fp16": "fp16 operands / fp32 accumulate (tcgen05 kind::f16)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": common_config(workload, world, sharded),
+        "details": {"cuda_graph": graph is not None, "tensor_flops_per_step": flops_step,
+                    "tensor_tflops_whole_step": flops_step * maps_per_step * args.steps / (ms_total * 1e-3) / 1e12 / world,
+                    "weights": "variables.synthetic_weights() (seeded He-normal under the checkpoint names, logit gain 4); "
+                               "tests/test_gpu_parity.py::test_cfg2_full_size_against_oracle checks this exact workload "
+                               "against the CPU oracle (0.1 % of the depth range)"},
         "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "pipeline.FrameStream.run (pinned host frames in, pinned host depth maps out; copies of "
@@ -328,21 +401,87 @@ def run_ours(args, rank, world, local_rank):
                        "pipeline.run_multiview bracketed by the H2D / D2H copies on one stream"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
-        "clocks": clocks,
+        "clocks": clk,
         "output_check": "depth map finite and inside the inverse-depth sweep",
     }
     if roof is not None:
         line["roofline"] = roof
     if kernels is not None:
         line["hbm_kernels"] = kernels
+    line.update(extras)
+    if sharded_line is not None:
+        line["sharded"] = sharded_line
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(workload)
     print(json.dumps(line))
 
 
+def run_sharded_cfg3(A, dist, torch, dev, rank, world, local_rank, barrier, steps=5):
+    """cfg3 = ONE 1920x1056, D = 256 frame with 8 source views: stage I of view v on rank (v-1) % world, aggregation
+    completed across ranks (all-reduce(max) of the local logit max, reduce-scatter(sum) of [num || den], all-gather of
+    the 8-channel result), output conv + soft-argmin replicated.  Timed on every rank, max over ranks; then the same
+    frame on rank 0 alone (all 8 views) for the 1-GPU time of the same build in the same run."""
+    feats, cams, D = make_inputs('cfg3', 0)
+    nv, H, W, _ = WORKLOADS['cfg3']
+    V = D * (H // 4) * (W // 4)
+    f = torch.from_numpy(feats).to(dev)
+    c = torch.from_numpy(cams).to(dev)
+    torch.cuda.empty_cache()
+
+    def step_sh():
+        return A.pipeline.run_multiview(f, c, D, siamese=True, upsample=True, group=dist.group.WORLD, rank=rank,
+                                        world=world)['depth_up']
+
+    def step_one():
+        return A.pipeline.run_multiview(f, c, D, siamese=True, upsample=True)['depth_up']
+
+    for _ in range(2):
+        o = step_sh()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms, o = timed_steps(step_sh, steps, torch, barrier)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    finite = bool(torch.isfinite(o).all())
+    ms1 = None
+    if rank == 0:
+        torch.cuda.empty_cache()
+        for _ in range(1):
+            o1 = step_one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            o1 = step_one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / 2
+        same = float((o1 - o).abs().max())
+    barrier()
+    allc = [None] * world
+    dist.all_gather_object(allc, clocks)
+    if rank != 0:
+        return None
+    per_rank_views = [len(A.pipeline.shard_views(nv, r, world)) for r in range(world)]
+    return {"workload": "cfg3: 1 ref + 8 src, 1920x1056 images -> 264x480x32 features in, D=256, stages I (siamese) + II + x4 "
+                        "soft-argmin, ONE frame, source views sharded over the ranks",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "value": steps / (ms * 1e-3), "unit": "depth maps/s",
+            "scaling": "strong", "ms_per_step_1gpu_same_run": ms1, "views_per_rank": per_rank_views,
+            "collective_bytes_per_rank": {"all_reduce_max_bf16": 2 * 8 * V, "reduce_scatter_sum_f32": 4 * 16 * V,
+                                          "all_gather_result_f16": 2 * 8 * V},
+            "max_abs_diff_vs_1gpu_depth": same, "finite": finite,
+            "clocks": {"per_rank": allc, "samples": min(x.get("samples", 0) for x in allc),
+                       "reasons": sorted(set(r for x in allc for r in x.get("reasons", [])))},
+            "what_limits_it": "one rank's share of stage I (ceil(8/N) views x ~17 ms), the replicated stage II at full "
+                              "resolution and the reduce-scatter payload; see DESIGN.md section 7"}
+
+
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed
-    `ncu --set full` capture of this round (profiles/*_traffic.json, written by tools/ncu_traffic.py)."""
+    `ncu --set full` capture (profiles/*_traffic.json, written by tools/ncu_traffic.py), newest round first."""
     import glob
     for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
         try:
@@ -354,8 +493,8 @@ def ncu_traffic(kernel_substr):
     return None, None
 
 
-def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
-    """K1 (fused homography + bilinear + cost slice, bf16 warped-only as the step uses it) and K4 (soft-argmin
+def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, act_dtype):
+    """K1 (fused homography + bilinear + cost slice, 16-bit warped-only as the step uses it) and K4 (soft-argmin
     with the fused x4 logit upsample) timed alone with CUDA events on the current stream; algorithmic bytes
     per SURVEY.md 8(d) over the measured HBM copy peak."""
     import torch
@@ -367,7 +506,7 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
 
     def k1():
         return A.build_cost_volume(feats_d[:, 0], feats_d[:, 1], cams_d, D, ds, di, 0, 1, mode='warped_only',
-                                   out_dtype=torch.bfloat16)
+                                   out_dtype=act_dtype)
 
     def k4up():
         return A.model._prob2depth(logits, ds, di, 4, False)
@@ -403,15 +542,15 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
 
     out = {}
     for name, fn, nbytes, note in (
-            ("K1 k_build_cost_volume_h (bf16, warped-only)", k1, 4 * h * w * F + 2 * V * F,
-             "reads the fp32 source feature map once, writes the (D,h,w,32) bf16 slice; the time includes K1's two "
-             "helper launches (homographies, fp32->bf16 source copy)"),
+            ("K1 k_build_cost_volume_h (16-bit, warped-only)", k1, 4 * h * w * F + 2 * V * F,
+             "reads the fp32 source feature map once, writes the (D,h,w,32) 16-bit slice; the time includes K1's two "
+             "helper launches (homographies, fp32->16-bit source copy)"),
             ("K4 k_prob2depth_up_sliced<4> (x4 upsample fused)", k4up, 4 * V + 4 * 16 * h * w,
              "reads the low-res logits once, writes the 4h x 4w depth map; instruction bound by construction (16*V "
              "interpolations + exponentials per 4*V bytes), see equivalent_unfused_gbs"),
             ("K4 k_prob2depth_sliced (volume resolution)", k4, 4 * V + 4 * h * w,
-             "reads the logits once; a 10 MB volume: launch-latency sized at this workload (69-71 % at 512x640 planes, "
-             "profiles/r01_microbench_cfg5.json)")):
+             "reads the logits once; a 10 MB volume: launch-latency sized at this workload (see the cfg5 sweep under "
+             "profiles/ for the large planes)")):
         t = timed(fn)
         out[name] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk['hbm'], "unit": "GB/s",
                      "frac": nbytes / t / 1e9 / pk['hbm'], "algorithmic_bytes": nbytes, "us_per_launch": t * 1e6,
@@ -423,25 +562,24 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, depth_any):
 
 
 def cpu_baseline(workload):
-    """the oracle port timed on the host cores on a bounded sample: the whole stage I (siamese) + II schedule of the
-    workload (all source views, attention aggregation, output conv, soft-argmin) on the first D/2 depth planes."""
+    """the oracle port timed on the host cores: ONE full step of the workload (all depth planes, all source views,
+    siamese stage I + stage II + x4 soft-argmin), ~30 s of CPU work at cfg2."""
     import torch
     import atvsnet_b200 as A
     from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     feats, cams, D = make_inputs(workload, 0)
     nv = cams.shape[1]
-    Ds = max(8, D // 2)
     weights = A.variables.synthetic_weights()
     ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
     om.TVSNet_base(feats[:, :2, :16, :16], cams, 8, ds, di, 1, weights)          # touch the code paths
     t0 = time.perf_counter()
-    om.run_multiview_stage12(feats, cams, Ds, weights, siamese=True)
+    om.run_multiview_stage12(feats, cams, D, weights, siamese=True)
     dt = time.perf_counter() - t0
-    value = (Ds / float(D)) / dt
-    return {"value": value, "unit": "depth maps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "stages I (siamese) + II for all %d source views on depth planes [0,%d) of %d, full %s feature "
-                      "resolution, %.1f s of CPU work; value = (%d/%d) / seconds (cost is linear in D)"
-                      % (nv - 1, Ds, D, workload, dt, Ds, D)}
+    return {"value": 1.0 / dt, "unit": "depth maps/s", "cores": cores, "kind": "port",
+            "sample": "one full %s step (stages I siamese + II + x4 soft-argmin, all %d source views, all %d depth planes): "
+                      "%.1f s of CPU work" % (workload, nv - 1, D, dt)}
 
 
 def main():
@@ -451,12 +589,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=None, choices=[None] + list(WORKLOADS))
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16', 'fp32'])
     ap.add_argument('--raw-dtype', default='f16', choices=['f16', 'f32'],
-                    help='storage of the raw (pre-BN) convolution outputs on the bf16 path')
+                    help='storage of the raw (pre-BN) convolution outputs on the tensor-core path')
     ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--from-images', action='store_true',
-                    help='start from images: include the 2-D feature extraction module (fp32 first path) in the step')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the extra fields (from-images / four-stage at N=1, sharded cfg3 at N>1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
 

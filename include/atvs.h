@@ -15,7 +15,9 @@
  *   - return value: 0 = ok, >0 = cudaError_t / CUresult of the failing call,
  *     <0 = argument error (ATVS_E_*); atvs_last_error() returns a thread-local message;
  *   - activations are channels-last (B,D,H,W,C), exactly the reference's NDHWC layout;
- *   - dtype codes: ATVS_F32 = 0, ATVS_BF16 = 1, ATVS_F16 = 2 (raw convolution outputs only).
+ *   - dtype codes: ATVS_F32 = 0, ATVS_BF16 = 1, ATVS_F16 = 2.  The tensor-core path keeps activations and weights
+ *     in ONE 16-bit format, ATVS_F16 (default: 11 significant bits; BN-normalised activations are bounded, so the
+ *     5-bit exponent is enough; conversions saturate) or ATVS_BF16; both run tcgen05.mma.kind::f16 at the same rate.
  */
 #ifndef ATVS_H_
 #define ATVS_H_
@@ -71,7 +73,7 @@ int atvs_homography_warping_by_depth(const float* image, const float* left_cam,
  * mode 0 CONCAT      -> out (B,D,h,w,2F)  = [ref | warp(view)]           (reference layout)
  * mode 1 WARPED_ONLY -> out (B,D,h,w,F)   = warp(view)
  * mode 2 L1_MASKED   -> out (B,D,h,w,F)   = |warp(view) - ref| * valid    (model.py:272-280)
- * out_dtype ATVS_F32 | ATVS_BF16.  F must be a multiple of 4 (8 for bf16).  Warped feature
+ * out_dtype ATVS_F32 | ATVS_BF16 | ATVS_F16.  F must be a multiple of 4 (8 for 16-bit volumes).  Warped feature
  * volumes are never materialised: each plane's slice is streamed straight to `out`.           */
 int atvs_build_cost_volume(const float* ref_feature, const float* view_feature,
                            const float* homographies, const float* ref_homographies, int B,
@@ -84,44 +86,30 @@ int atvs_build_cost_volume(const float* ref_feature, const float* view_feature,
  * (TF SAME: out = 2*in, out[2i+k] += in[i]*w[k]).  No bias.  raw_out (B,Do,Ho,Wo,Cout) f32 is
  * the PRE-batch-norm result.  stats (2*Cout doubles: sum, sum of squares; caller zeroes it)
  * receives the per-channel moments of raw_out when not NULL (batch-statistics BN, F4).
- * atvs_conv3d_fp32: CUDA-core fp32 parity path.  atvs_conv3d_bf16: tcgen05/TMEM implicit GEMM,
- * bf16 operands, fp32 accumulation; `wpacked` comes from atvs_pack_conv_weights_bf16.  The tensor
- * path writes raw_out as raw_dtype = ATVS_F32 or ATVS_F16 (saturated; for layers whose raw output only
- * feeds atvs_bn_relu_add*: the moments still come from the fp32 accumulators, the BN pass rounds to bf16
- * right after, and the bytes written here and read there are halved).                              */
+ * atvs_conv3d_fp32: CUDA-core fp32 parity path.  atvs_conv3d_tc: tcgen05/TMEM implicit GEMM,
+ * 16-bit operands (x_dtype = ATVS_F16 | ATVS_BF16, the same format as the packed weights), fp32 accumulation;
+ * `wpacked` comes from atvs_pack_conv_weights_tc.  The tensor path writes raw_out as raw_dtype = ATVS_F32 or
+ * ATVS_F16 (saturated; for layers whose raw output only feeds atvs_bn_relu_add*: the moments still come from the
+ * fp32 accumulators, the BN pass rounds to 16 bits right after, and the bytes written here and read there are
+ * halved).                                                                                          */
 int atvs_conv3d_fp32(const float* x, const float* kernel, int B, int D, int H, int W, int Cin,
                      int Cout, int stride, int transposed, float* raw_out, double* stats,
                      atvs_stream_t stream);
 
 size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed);
-int atvs_pack_conv_weights_bf16(const float* kernel, int Cin, int Cout, int transposed,
-                                void* wpacked, atvs_stream_t stream);
-int atvs_conv3d_bf16(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                     int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
-                     atvs_stream_t stream);
+int atvs_pack_conv_weights_tc(const float* kernel, int Cin, int Cout, int transposed, int dtype,
+                              void* wpacked, atvs_stream_t stream);
+int atvs_conv3d_tc(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin,
+                   int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
+                   atvs_stream_t stream);
 /* same convolution plus a depth-invariant term: raw_out[b,z,y,x,:] += plane_bias[b,c(z),y,x,:] with
  * c(z) = 0 for the first output plane, 2 for the last, 1 otherwise; plane_bias (B,3,Ho,Wo,Cout) f32.
  * Used for the first CRM layers: the cost volume of model.py:186-195 is [tile(ref, D) | warped], so the
  * reference half of the convolution is a 2-D result shared by all interior planes (computed once by
  * running this same primitive on a 3-plane (4 for stride 2) tile of the reference feature).         */
-int atvs_conv3d_bf16_bias(const void* x_bf16, const void* wpacked, int B, int D, int H, int W, int Cin,
-                          int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
-                          double* stats, atvs_stream_t stream);
-
-/* TWO convolutions of the same input in one pass over it (cnn_wrapper/atvsnet.py:104-114: every U-Net block starts
- * with conv_b*_0_1 = 8 channels, stride 1 and conv_b*_1_0 = 16 channels, stride 2 on the same tensor).  The
- * stride-2 head is evaluated densely next to the stride-1 head (its 16 columns ride in the same MMAs, whose cost
- * is the fetch of the voxel tile, not N) and only the odd positions are kept: TF SAME on even extents pads
- * (0,1), so out2[z',y',x'] is the dense result at (2z'+1, 2y'+1, 2x'+1).  wpacked32 = atvs_pack_conv_weights_dual
- * (atvs_dual_weight_bytes(Cin) bytes) of the kernel [3,3,3,Cin,32] = [head-1 (8) | head-2 (16) | zeros (8)].  raw_out1 (B,D,H,W,8), raw_out2
- * (B,D/2,H/2,W/2,16), both raw_dtype; stats1 (16 doubles) / stats2 (32 doubles) and the plane biases
- * (B,3,H,W,8) / (B,3,H/2,W/2,16) f32 as for atvs_conv3d_bf16(_bias) or NULL.                      */
-size_t atvs_dual_weight_bytes(int Cin);
-int atvs_pack_conv_weights_dual(const float* kernel32, int Cin, void* wpacked, atvs_stream_t stream);
-int atvs_conv3d_bf16_dual_supported(int B, int D, int H, int W, int Cin);
-int atvs_conv3d_bf16_dual(const void* x_bf16, const void* wpacked32, int B, int D, int H, int W, int Cin,
-                          const float* plane_bias1, const float* plane_bias2, void* raw_out1, void* raw_out2,
-                          int raw_dtype, double* stats1, double* stats2, atvs_stream_t stream);
+int atvs_conv3d_tc_bias(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin,
+                        int Cout, int stride, const float* plane_bias, void* raw_out, int raw_dtype,
+                        double* stats, atvs_stream_t stream);
 
 /* ---- batch-norm (batch statistics) + ReLU + skip adds ------ network.py:206-215, 541-550, 696
  * y = relu((raw - mean) * rsqrt(var + eps)) with mean/var from `stats` over `count` voxels

@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: a -m gpu test that also runs ~1 minute of CPU oracle at a BASELINE config size")
 
 
 @pytest.fixture(scope='session')

@@ -42,18 +42,19 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_prob2depth(p, 1, 8, 4, 4, p, p, 3, p, None, None) == -5          # up must be 1 or 4
     assert lib.atvs_build_cost_volume(p, p, p, None, 1, 8, 4, 4, 6, 0, 0, p, None) == -1  # F % 4
     assert lib.atvs_conv3d_fp32(p, p, 1, 2, 2, 2, 8, 5, 1, 0, p, None, None) == -5       # Cout
-    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 12, 8, 1, 0, p, 0, None, None) == -5      # Cin
-    assert lib.atvs_conv3d_bf16(p, p, 1, 3, 2, 2, 16, 8, 2, 0, p, 0, None, None) == -3      # odd D, stride 2
-    assert lib.atvs_conv3d_bf16(p, p, 1, 2, 2, 2, 16, 8, 1, 0, p, 1, None, None) == -2   # raw dtype must be f32 | f16
-    # entry points added in round 1: raw dtype / view table / dual head / FEM validation before any launch
+    for xd in (1, 2):                                                                      # bf16 and fp16 operands
+        assert lib.atvs_conv3d_tc(p, xd, p, 1, 2, 2, 2, 12, 8, 1, 0, p, 0, None, None) == -5      # Cin
+        assert lib.atvs_conv3d_tc(p, xd, p, 1, 3, 2, 2, 16, 8, 2, 0, p, 0, None, None) == -3      # odd D, stride 2
+        assert lib.atvs_conv3d_tc(p, xd, p, 1, 2, 2, 2, 16, 8, 1, 0, p, 1, None, None) == -2      # raw dtype must be f32 | f16
+    assert lib.atvs_conv3d_tc(p, 0, p, 1, 2, 2, 2, 16, 8, 1, 0, p, 0, None, None) == -2           # operands must be 16-bit
+    assert lib.atvs_pack_conv_weights_tc(p, 16, 8, 0, 0, p, None) == -2
+    assert lib.atvs_conv3d_tc_bias(p, 2, p, 1, 2, 2, 2, 16, 8, 1, None, p, 0, None, None) == -4   # plane bias NULL
+    # raw dtype / view table / FEM validation before any launch
     assert lib.atvs_bn_relu_add(p, 7, p, 8, 8, 1e-3, 1, None, None, p, None, 0, None) == -2              # raw dtype
     assert lib.atvs_attention_raw(p, 0, None, 2, 8, 8, 0, 0, None, p, None) == -4                        # views NULL
     assert lib.atvs_attention_raw(p, 0, p, 9, 8, 8, 0, 0, None, p, None) == -1                           # N > 8
-    assert lib.atvs_conv3d_bf16_dual_supported(1, 16, 64, 80, 8) == 1
-    assert lib.atvs_conv3d_bf16_dual_supported(1, 15, 64, 80, 8) == 0                                    # odd D
-    assert lib.atvs_conv3d_bf16_dual_supported(1, 4, 8, 8, 8) == 0                                       # below ring size
-    assert lib.atvs_conv3d_bf16_dual(p, p, 1, 15, 64, 80, 8, None, None, p, p, 0, None, None, None) == -5
-    assert lib.atvs_dual_weight_bytes(8) == 5 * 2 * 144 * 16 and lib.atvs_dual_weight_bytes(32) == 18 * 2 * 96 * 16
+    assert lib.atvs_bn_relu_add(p, 0, p, 8, 8, 1e-3, 1, None, None, p, None, 7, None) == -2              # act dtype
+    assert lib.atvs_cast(p, 2, p, 1, 8, None) == -2                                                      # fp16 -> bf16: via fp32
     assert lib.atvs_conv2d_fp32(p, p, None, 1, 8, 8, 4, 8, 5, 1, 1, 2, 2, 8, 8, 0, p, None) == -5        # kernel size 5
     assert lib.atvs_conv2d_fp32(None, p, None, 1, 8, 8, 4, 8, 3, 1, 1, 1, 1, 8, 8, 0, p, None) == -4
     assert lib.atvs_channel_moments(p, 0, 8, p, None) == -1 and lib.atvs_bn2d_apply(p, None, None, 4, 8, 1e-3, 0, p, None) == -4

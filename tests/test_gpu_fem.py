@@ -105,6 +105,6 @@ def test_images_to_depth_end_to_end(A):
         assert rel(feats.cpu().numpy(), feats_ref) < 2e-4
         out = A.pipeline.run_multiview(feats, cu(cams), D, siamese=False)
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
     rng_ = float((D - 1) * cams[0, 0, 1, 3, 1])
     assert float(np.abs(out['depth_up'].cpu().numpy() - ref['depth_agg_init_up']).mean()) / rng_ < 1e-3

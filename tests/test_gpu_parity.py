@@ -16,6 +16,11 @@ from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
+# the two 16-bit operand formats of the tensor-core path (fp16 is the default, FLAGS.precision = 'fp16')
+HALF = pytest.mark.parametrize('half', [torch.float16, torch.bfloat16], ids=['f16', 'bf16'])
+HALF_EPS = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}
+PREC = {torch.float16: 'fp16', torch.bfloat16: 'bf16'}
+
 
 @pytest.fixture(scope='module')
 def A():
@@ -182,15 +187,16 @@ def test_conv3d_fp32(A, cin, cout, stride, transposed):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-4, atol=1e-3)
 
 
+@HALF
 @pytest.mark.parametrize('cin,cout,stride,transposed', LAYER_KINDS)
-def test_conv3d_bf16_tensor_core(A, cin, cout, stride, transposed):
+def test_conv3d_bf16_tensor_core(A, cin, cout, stride, transposed, half):
     """tcgen05 implicit GEMM vs the oracle conv on bf16-rounded operands (so only the fp32
     accumulation order differs)."""
     from oracle import network as onet
     from atvsnet_b200.network import conv3d_raw
     x, w = _conv_case(cin, cout, stride, transposed, 2, shape=(1, 8, 12, 20))
-    xb = torch.from_numpy(x).to(torch.bfloat16)
-    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    xb = torch.from_numpy(x).to(half)
+    wb = torch.from_numpy(w).to(half).float()
     A.variables.packed_cache().clear()
     raw, stats = conv3d_raw(xb.cuda(), 'tc_test_%d_%d_%d_%d' % (cin, cout, stride, transposed), wb.cuda(), cout,
                             stride, bool(transposed), True)
@@ -205,7 +211,8 @@ def test_conv3d_bf16_tensor_core(A, cin, cout, stride, transposed):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=1e-2)
 
 
-def test_conv3d_bf16_ragged_and_batched(A):
+@HALF
+def test_conv3d_bf16_ragged_and_batched(A, half):
     """brick tiles hanging over every border, odd extents (stride 1 / deconv), batch > 1."""
     from oracle import network as onet
     from atvsnet_b200.network import conv3d_raw
@@ -213,8 +220,8 @@ def test_conv3d_bf16_ragged_and_batched(A):
                                            (8, 8, 1, 0, (1, 1, 9, 33)), (64, 16, 2, 0, (2, 2, 6, 10)),
                                            (8, 16, 2, 0, (1, 10, 2, 18))):
         x, w = _conv_case(cin, cout, stride, tr, 3, shape=shape)
-        xb = torch.from_numpy(x).to(torch.bfloat16)
-        wb = torch.from_numpy(w).to(torch.bfloat16).float()
+        xb = torch.from_numpy(x).to(half)
+        wb = torch.from_numpy(w).to(half).float()
         A.variables.packed_cache().clear()
         raw, _ = conv3d_raw(xb.cuda(), 'rag', wb.cuda(), cout, stride, bool(tr), True)
         xr = xb.float().numpy()
@@ -227,15 +234,16 @@ RING_CASES = [(64, 8, (1, 8, 40, 104)), (8, 8, (1, 8, 40, 104)), (8, 1, (1, 9, 3
               (64, 16, (1, 40, 32, 32))]
 
 
+@HALF
 @pytest.mark.parametrize('cin,cout,shape', RING_CASES)
-def test_conv3d_bf16_halo_ring(A, cin, cout, shape):
+def test_conv3d_bf16_halo_ring(A, cin, cout, shape, half):
     """large stride-1 volumes take the halo-ring kernel (every input plane staged once in smem)."""
     from oracle import network as onet
     from atvsnet_b200.network import conv3d_raw
     assert shape[1] * shape[2] * shape[3] >= 32768
     x, w = _conv_case(cin, cout, 1, 0, 7, shape=shape)
-    xb = torch.from_numpy(x).to(torch.bfloat16)
-    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    xb = torch.from_numpy(x).to(half)
+    wb = torch.from_numpy(w).to(half).float()
     A.variables.packed_cache().clear()
     os.environ['ATVS_RING_MINVOX'] = '32768'       # the default dispatch threshold is 65536 voxels
     try:
@@ -257,15 +265,16 @@ RAW16_CASES = [(8, 8, 1, 0, (1, 16, 64, 80)), (32, 8, 1, 0, (1, 16, 64, 80)), (8
                (8, 1, 1, 0, (1, 16, 64, 80))]
 
 
+@HALF
 @pytest.mark.parametrize('cin,cout,stride,transposed,shape', RAW16_CASES)
-def test_conv3d_bf16_raw_fp16(A, cin, cout, stride, transposed, shape):
+def test_conv3d_bf16_raw_fp16(A, cin, cout, stride, transposed, shape, half):
     """raw outputs stored as saturated fp16 (layers that only feed the BN pass): every tensor kernel (ring, stride-2
     ring, per-tap TMA, fused deconv) against its own fp32 raw output; moments unchanged (fp32 accumulators); the BN
     pass on the fp16 tensor equals the BN pass on the fp32 one to bf16 output rounding."""
     from atvsnet_b200.network import conv3d_raw, bn_relu_add
     x, w = _conv_case(cin, cout, stride, transposed, 11, shape=shape)
-    xb = torch.from_numpy(x).to(torch.bfloat16).cuda()
-    wb = torch.from_numpy(w).to(torch.bfloat16).float().cuda()
+    xb = torch.from_numpy(x).to(half).cuda()
+    wb = torch.from_numpy(w).to(half).float().cuda()
     A.variables.packed_cache().clear()
     r32, s32 = conv3d_raw(xb, 'r16_%d_%d' % (cin, cout), wb, cout, stride, bool(transposed), True)
     r16, s16 = conv3d_raw(xb, 'r16_%d_%d' % (cin, cout), wb, cout, stride, bool(transposed), True, raw_dtype=torch.float16)
@@ -276,18 +285,19 @@ def test_conv3d_bf16_raw_fp16(A, cin, cout, stride, transposed, shape):
     assert np.array_equal(a.astype(np.float16), r16.cpu().numpy())            # exactly round-to-nearest of the fp32 result
     assert np.allclose(s32.cpu().numpy(), s16.cpu().numpy(), rtol=1e-6, atol=1e-3)
     if cout % 4 == 0:
-        p32, _ = bn_relu_add(r32, s32, True, [], True, False, torch.bfloat16)
-        p16, _ = bn_relu_add(r16, s16, True, [], True, False, torch.bfloat16)
+        p32, _ = bn_relu_add(r32, s32, True, [], True, False, half)
+        p16, _ = bn_relu_add(r16, s16, True, [], True, False, half)
         d = (p32.float() - p16.float()).abs()
-        assert float(d.max()) <= 2.0 ** -7 * max(1.0, float(p32.float().abs().max()))
+        assert float(d.max()) <= 2 * HALF_EPS[half] * max(1.0, float(p32.float().abs().max()))
         assert float((d > 0).float().mean()) < 0.25
 
 
-def test_raw_fp16_saturates(A):
+@HALF
+def test_raw_fp16_saturates(A, half):
     """values beyond the fp16 range are clamped to +-65504 (never inf), NaN stays NaN."""
     from atvsnet_b200.network import conv3d_raw
-    x = torch.full((1, 8, 16, 16, 8), 300.0).to(torch.bfloat16).cuda()
-    w = torch.full((3, 3, 3, 8, 8), 2.0).cuda()
+    x = torch.full((1, 8, 16, 16, 8), 300.0).to(half).cuda()
+    w = torch.full((3, 3, 3, 8, 8), 2.0).cuda()      # 27 * 8 * 300 * 2 = 129 600 > 65 504
     w[..., 1] = -2.0
     A.variables.packed_cache().clear()
     r16, _ = conv3d_raw(x, 'sat16', w, 8, 1, False, True, raw_dtype=torch.float16)
@@ -299,15 +309,16 @@ S2_RING_CASES = [(8, 16, (1, 32, 128, 160)), (32, 16, (1, 16, 128, 192)), (16, 3
                  (32, 64, (1, 8, 256, 160)), (16, 16, (1, 68, 132, 68))]
 
 
+@HALF
 @pytest.mark.parametrize('cin,cout,shape', S2_RING_CASES)
-def test_conv3d_bf16_stride2_ring(A, cin, cout, shape):
+def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
     """large stride-2 volumes take the de-interleaving ring kernel (conv_ring_s2.cu)."""
     from oracle import network as onet
     from atvsnet_b200.network import conv3d_raw
     assert (shape[1] // 2) * (shape[2] // 2) * (shape[3] // 2) >= 32768 or True
     x, w = _conv_case(cin, cout, 2, 0, 9, shape=shape)
-    xb = torch.from_numpy(x).to(torch.bfloat16)
-    wb = torch.from_numpy(w).to(torch.bfloat16).float()
+    xb = torch.from_numpy(x).to(half)
+    wb = torch.from_numpy(w).to(half).float()
     A.variables.packed_cache().clear()
     os.environ['ATVS_RING_S2_CIN'] = str(cin)          # Cin = 32 is opt-in (see ring_s2_applicable)
     try:
@@ -324,29 +335,32 @@ def test_conv3d_bf16_stride2_ring(A, cin, cout, shape):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
+@HALF
 @pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10)),
                                           (2, (1, 8, 128, 160))])
-def test_conv3d_split_cost_volume(A, stride, shape):
+def test_conv3d_split_cost_volume(A, stride, shape, half):
     """conv over [tile(ref, D) | warped] == conv(warped) + per-plane-class bias from ref (ring and TMA kernels)."""
     from oracle import network as onet
     from atvsnet_b200.network import SplitCostVolume, conv3d_split, conv3d_raw
     rng = np.random.default_rng(11)
     B, D, H, W = shape
     F, cout = 32, 8 if stride == 1 else 16
-    ref = torch.from_numpy(rng.standard_normal((B, H, W, F)).astype(np.float32)).to(torch.bfloat16)
-    warped = torch.from_numpy(rng.standard_normal((B, D, H, W, F)).astype(np.float32)).to(torch.bfloat16)
+    ref = torch.from_numpy(rng.standard_normal((B, H, W, F)).astype(np.float32)).to(half)
+    warped = torch.from_numpy(rng.standard_normal((B, D, H, W, F)).astype(np.float32)).to(half)
     w = torch.from_numpy((rng.standard_normal((3, 3, 3, 2 * F, cout)) / np.sqrt(27 * 2 * F)).astype(np.float32))
-    w = w.to(torch.bfloat16).float()
+    w = w.to(half).float()
     A.variables.packed_cache().clear()
     stats = torch.zeros(128, dtype=torch.float64, device='cuda')
-    A.FLAGS.raw_dtype = 'f32'
+    assert A.FLAGS.first_raw_dtype == 'f32'      # default for the layers fed by the un-normalised cost volume
+    raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
+    assert raw.dtype == torch.float32
+    # optional storage as saturated fp16 = one rounding of the fp32 result
+    A.FLAGS.first_raw_dtype = 'f16'
     try:
-        raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
+        raw16, _ = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride,
+                                torch.zeros(128, dtype=torch.float64, device='cuda'))
     finally:
-        A.FLAGS.raw_dtype = 'f16'
-    # default storage of a raw output that feeds the BN pass: saturated fp16 = one rounding of the fp32 result
-    raw16, _ = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride,
-                            torch.zeros(128, dtype=torch.float64, device='cuda'))
+        A.FLAGS.first_raw_dtype = 'f32'
     assert raw16.dtype == torch.float16 and np.array_equal(npy(raw).astype(np.float16), raw16.cpu().numpy())
     full = np.concatenate([np.tile(ref.float().numpy()[:, None], (1, D, 1, 1, 1)), warped.float().numpy()], axis=-1)
     refo = onet.conv3d(full, w.numpy(), stride)
@@ -355,52 +369,8 @@ def test_conv3d_split_cost_volume(A, stride, shape):
     flat = refo.reshape(-1, cout).astype(np.float64)
     assert np.allclose(st.cpu().numpy()[:cout], flat.sum(0), rtol=1e-3, atol=5e-2)
     # and equals the plain kernel on the materialised concatenation
-    raw2, _ = conv3d_raw(torch.from_numpy(full).to(torch.bfloat16).cuda(), 'split_full', w.cuda(), cout, stride, False, True)
+    raw2, _ = conv3d_raw(torch.from_numpy(full).to(half).cuda(), 'split_full', w.cuda(), cout, stride, False, True)
     assert rel_err(npy(raw), npy(raw2)) < 1e-5
-
-
-@pytest.mark.parametrize('cin,shape,split', [(8, (1, 16, 64, 80), False), (32, (1, 16, 64, 80), False), (16, (2, 12, 96, 64), False),
-                                             (32, (1, 18, 70, 90), True), (8, (1, 128, 128, 160), False)])
-def test_conv3d_dual_head(A, cin, shape, split):
-    """the two convolutions that open a U-Net block (8 ch stride 1 + 16 ch stride 2, same input) in one launch ==
-    the two separate launches: same fp32 accumulators up to summation order, same moments; also with the split
-    cost volume (plane-class biases on both heads)."""
-    from atvsnet_b200.network import SplitCostVolume, conv3d_split, conv3d_raw, conv3d_dual, dual_supported
-    rng = np.random.default_rng(21)
-    B, D, H, W = shape
-    ctot = 2 * cin if split else cin
-    x = torch.from_numpy(rng.standard_normal((B, D, H, W, cin)).astype(np.float32)).to(torch.bfloat16).cuda()
-    w1 = torch.from_numpy((rng.standard_normal((3, 3, 3, ctot, 8)) / np.sqrt(27 * ctot)).astype(np.float32)).to(torch.bfloat16).float().cuda()
-    w2 = torch.from_numpy((rng.standard_normal((3, 3, 3, ctot, 16)) / np.sqrt(27 * ctot)).astype(np.float32)).to(torch.bfloat16).float().cuda()
-    A.variables.packed_cache().clear()
-    A.FLAGS.raw_dtype = 'f32'
-    try:
-        if split:
-            ref = torch.from_numpy(rng.standard_normal((B, H, W, cin)).astype(np.float32)).cuda()
-            xin = SplitCostVolume(ref, x)
-        else:
-            xin = x
-        assert dual_supported(xin)
-        st = torch.zeros((4, 128), dtype=torch.float64, device='cuda')
-        (r1, s1), (r2, s2) = conv3d_dual(xin, 'dh1', w1, 'dh2', w2, st[0], st[1])
-        if split:
-            q1, t1 = conv3d_split(xin, 'dh1', w1, 8, 1, st[2])
-            q2, t2 = conv3d_split(xin, 'dh2', w2, 16, 2, st[3])
-        else:
-            q1, t1 = conv3d_raw(x, 'dh1', w1, 8, 1, False, True, st[2])
-            q2, t2 = conv3d_raw(x, 'dh2', w2, 16, 2, False, True, st[3])
-        torch.cuda.synchronize()
-    finally:
-        A.FLAGS.raw_dtype = 'f16'
-    assert r1.shape == q1.shape and r2.shape == q2.shape
-    assert rel_err(npy(r1), npy(q1)) < 2e-6 and rel_err(npy(r2), npy(q2)) < 2e-6
-    assert np.allclose(s1.cpu().numpy()[:16], t1.cpu().numpy()[:16], rtol=1e-5, atol=1e-2)
-    assert np.allclose(s2.cpu().numpy()[:32], t2.cpu().numpy()[:32], rtol=1e-5, atol=1e-2)
-    # default (fp16 raw) storage: exactly the rounding of the fp32 result
-    (h1, _), (h2, _) = conv3d_dual(xin, 'dh1', w1, 'dh2', w2, torch.zeros(128, dtype=torch.float64, device='cuda'),
-                                   torch.zeros(128, dtype=torch.float64, device='cuda'))
-    assert h1.dtype == torch.float16
-    assert np.array_equal(npy(r1).astype(np.float16), h1.cpu().numpy()) and np.array_equal(npy(r2).astype(np.float16), h2.cpu().numpy())
 
 
 def test_bn_relu_add_pair(A):
@@ -426,7 +396,8 @@ def test_bn_relu_add_pair(A):
         assert rel_err(npy(sb), ref_a + ref_b) < 1e-2
 
 
-def test_build_cost_volume_bf16_source(A):
+@HALF
+def test_build_cost_volume_bf16_source(A, half):
     """bf16 volumes gather from a bf16 copy of the source features: equals the fp32-source kernel up to
     the bf16 rounding of its inputs, and exactly the oracle run on bf16-rounded source features."""
     from oracle import model as om
@@ -434,10 +405,10 @@ def test_build_cost_volume_bf16_source(A):
     cams = A.synthetic.orbit_cams(3, h, w, D)[None]
     feats = A.synthetic.smooth_features(3, h, w, F, seed=5)[None]
     ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
-    fr = torch.from_numpy(feats).to(torch.bfloat16).float().numpy()
+    fr = torch.from_numpy(feats).to(half).float().numpy()
     for mode in ('warped_only', 'concat', 'l1_masked'):
         out = A.build_cost_volume(cu(feats[:, 0]), cu(feats[:, 2]), cu(cams), D, cu(ds), cu(di), 0, 2, mode=mode,
-                                  out_dtype=torch.bfloat16)
+                                  out_dtype=half)
         full = om.build_cost_volume(feats[:, 0], fr[:, 2], cams, D, ds, di, 0, 2)
         if mode == 'warped_only':
             ref = full[..., F:]
@@ -446,7 +417,7 @@ def test_build_cost_volume_bf16_source(A):
         else:       # fp32 CUDA path of the same mode (itself checked against the oracle elsewhere)
             ref = npy(A.build_cost_volume(cu(feats[:, 0]), cu(fr[:, 2]), cu(cams), D, cu(ds), cu(di), 0, 2, mode=mode))
         got = npy(out.float())
-        assert np.abs(got - ref).max() <= 2 ** -8 * np.abs(ref).max() + 1e-6, mode
+        assert np.abs(got - ref).max() <= HALF_EPS[half] * np.abs(ref).max() + 1e-6, mode
 
 
 def test_conv3d_argument_errors(A):
@@ -493,18 +464,24 @@ def test_cost_volume_reasoning_fp32_golden(A, golden, gweights):
                    'conv_b1_5_0'):
             assert rel_err(npy(tower.get_output_by_name(nm)), golden['crm_' + nm]) < 5e-4, nm
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
 
 
-def test_cost_volume_reasoning_bf16(A, golden, gweights):
+@HALF
+def test_cost_volume_reasoning_bf16(A, golden, gweights, half):
     A.variables.load_weights(gweights)
-    A.FLAGS.precision = 'bf16'
-    prob, filt = A.cost_volume_reasoning(cu(golden['crm_in']), output_filtered_cost=True)
-    # 31 bf16 layers with batch-stat BN on tiny volumes: loose elementwise bound, tight on average
+    A.FLAGS.precision = PREC[half]
+    try:
+        prob, filt = A.cost_volume_reasoning(cu(golden['crm_in']), output_filtered_cost=True)
+    finally:
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+    # 31 16-bit layers with batch-stat BN on tiny volumes: loose elementwise bound, tight on average (8x tighter for
+    # the 11-bit format)
+    k = HALF_EPS[half] / 2.0 ** -8
     e = np.abs(npy(filt) - golden['crm_filtered'])
-    assert e.mean() < 0.03 * np.abs(golden['crm_filtered']).mean() + 0.03
+    assert e.mean() < k * (0.03 * np.abs(golden['crm_filtered']).mean() + 0.03)
     e = np.abs(npy(prob) - golden['crm_prob'])
-    assert e.mean() < 0.05 * np.abs(golden['crm_prob']).std()
+    assert e.mean() < k * 0.05 * np.abs(golden['crm_prob']).std()
 
 
 def test_attention_aggregation(A, golden, gweights):
@@ -525,7 +502,7 @@ def test_attention_aggregation(A, golden, gweights):
         one = A.cost_volume_aggregation(cu(xs[..., :1]), keepchannel=True)
         assert rel_err(npy(one), xs[..., 0]) < 1e-6
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
     keepb = A.cost_volume_aggregation(cu(xs), keepchannel=True)
     assert rel_err(npy(keepb), golden['aam1_keep']) < 2e-2
 
@@ -613,16 +590,24 @@ def test_full_size_properties_cfg2(A):
 
 
 # ------------------------------------------------------------------ end to end (stage I + II)
-def _e2e_inputs(A, D=16, h=16, w=24, nv=3, seed=3):
+# the weights bench.py times: variables.synthetic_weights() defaults (logit_gain = 4: peaked, trained-like soft-argmin)
+BENCH_GAIN = 4.0
+
+
+def _e2e_inputs(A, D=16, h=16, w=24, nv=3, seed=3, gain=BENCH_GAIN):
     cams = A.synthetic.orbit_cams(nv, h, w, D)[None]
     feats = A.synthetic.smooth_features(nv, h, w, 32, seed=seed)[None]
-    weights = A.variables.synthetic_weights(seed=11, logit_gain=2.0)
+    weights = A.variables.synthetic_weights(seed=11, logit_gain=gain)
     return cams, feats, weights
+
+
+def _mae_over_range(a, b, cams, D):
+    return float(np.abs(a - b).mean()) / ((D - 1) * float(cams[0, 0, 1, 3, 1]))
 
 
 def test_tvsnet_base_siamese_fp32(A):
     from oracle import model as om
-    cams, feats, weights = _e2e_inputs(A)
+    cams, feats, weights = _e2e_inputs(A, gain=2.0)
     A.variables.load_weights(weights)
     A.FLAGS.precision = 'fp32'
     try:
@@ -633,12 +618,12 @@ def test_tvsnet_base_siamese_fp32(A):
         rng_ = 15 * float(di[0])
         assert np.abs(npy(d) - do).max() < 1e-3 * rng_ and np.abs(npy(dv) - dvo).max() < 1e-3 * rng_
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
 
 
-def test_multiview_pipeline_fp32_and_bf16(A):
+def test_multiview_pipeline_fp32_and_16bit(A):
     from oracle import model as om
-    cams, feats, weights = _e2e_inputs(A)
+    cams, feats, weights = _e2e_inputs(A, gain=2.0)
     A.variables.load_weights(weights)
     ref = om.run_multiview_stage12(feats, cams, 16, weights, siamese=True)
     rng_ = 15 * float(cams[0, 0, 1, 3, 1])
@@ -646,41 +631,82 @@ def test_multiview_pipeline_fp32_and_bf16(A):
     try:
         out = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
     assert rel_err(npy(out['cost_volume_agg']), ref['cost_volume_agg']) < 1e-3
     assert np.abs(npy(out['depth']) - ref['depth_agg_init']).max() < 1e-3 * rng_
     assert np.abs(npy(out['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * rng_
     for a, b in zip(out['depth_views'], ref['depth_views']):
         assert np.abs(npy(a) - b).max() < 1e-3 * rng_
-    # split cost volume path (bf16) runs too at this size; its accuracy is checked at a realistic size below
-    outb = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
-    assert np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_ < 5e-3
+    # split cost volume path (16-bit) runs too at this tiny size (8-voxel deepest level: BN statistics of 8 samples);
+    # its accuracy is checked at realistic sizes below
+    for prec in ('fp16', 'bf16'):
+        A.FLAGS.precision = prec
+        try:
+            outb = A.pipeline.run_multiview(cu(feats), cu(cams), 16, siamese=True)
+        finally:
+            A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+        assert np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_ < 5e-3
 
 
-def test_multiview_pipeline_bf16_depth_mae(A):
-    """north_star tolerance: final depth map of the bf16 tensor-core path within a mean absolute error of
-    0.1 % of the depth range of the fp32 reference (CPU oracle), at a volume large enough (64x64x80) for
-    the batch-norm statistics of the deepest level (8x8x10 voxels) to be meaningful."""
+def test_multiview_pipeline_16bit_depth_mae(A):
+    """north_star tolerance: final depth map of the tensor-core path within a mean absolute error of 0.1 % of the depth
+    range of the fp32 reference (CPU oracle), with THE WEIGHTS bench.py TIMES (logit gain 4: mean peak probability
+    ~0.5), at a volume large enough (64x64x80) for the batch-norm statistics of the deepest level (8x8x10 voxels) to be
+    meaningful.  fp16 storage (the default) meets it with a 3x margin; bf16 storage (8 significant bits) does not and
+    is only bounded (tests/precision_emulation.py reproduces both numbers on the CPU: 0.025 % / 0.19 %)."""
     from oracle import model as om
     D, h, w = 64, 64, 80
     cams, feats, weights = _e2e_inputs(A, D=D, h=h, w=w, nv=3)
     A.variables.load_weights(weights)
     ref = om.run_multiview_stage12(feats, cams, D, weights, siamese=False)
-    rng_ = (D - 1) * float(cams[0, 0, 1, 3, 1])
-    A.FLAGS.precision = 'bf16'
-    outb = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
-    mae = np.abs(npy(outb['depth_up']) - ref['depth_agg_init_up']).mean() / rng_
-    assert mae < 1e-3, mae
-    # the softmax over depth must be peaked enough for that bound to mean something
+    # the softmax over depth must be peaked enough for the bound to mean something
     p = torch.softmax(-torch.from_numpy(ref['prob_volume_agg']), dim=1)
-    assert p.max(dim=1).values.mean() > 4.0 / D
+    assert p.max(dim=1).values.mean() > 0.3
+    assert A.FLAGS.precision == 'fp16'
+    out16 = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
+    mae = _mae_over_range(npy(out16['depth_up']), ref['depth_agg_init_up'], cams, D)
+    assert mae < 1e-3, mae
+    assert mae < 5e-4, mae          # measured 2.5e-4 in the CPU emulation of the storage roundings
+    A.FLAGS.precision = 'bf16'
+    try:
+        outb = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
+    finally:
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+    maeb = _mae_over_range(npy(outb['depth_up']), ref['depth_agg_init_up'], cams, D)
+    assert maeb < 4e-3, maeb
+    print("depth MAE / range at 64x64x80, gain 4: fp16 %.3e  bf16 %.3e" % (mae, maeb))
     # fp32 CUDA path at the same size, against the oracle
     A.FLAGS.precision = 'fp32'
     try:
         outf = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=False)
     finally:
-        A.FLAGS.precision = 'bf16'
-    assert np.abs(npy(outf['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * rng_
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+    assert np.abs(npy(outf['depth_up']) - ref['depth_agg_init_up']).max() < 1e-3 * (D - 1) * float(cams[0, 0, 1, 3, 1])
+
+
+@pytest.mark.slow
+def test_cfg2_full_size_against_oracle(A):
+    """BASELINE.json configs[1] at FULL size (1 ref + 4 src, 640x512 -> 128x160x32 features, D = 128, siamese stage I +
+    stage II + x4 soft-argmin), exactly bench.py's inputs and weights (make_inputs / synthetic_weights defaults): the
+    fp16 tensor-core path against the CPU oracle (~1 minute of host time) within 0.1 % of the depth range."""
+    from oracle import model as om
+    nv, h, w, D = 5, 128, 160, 128
+    cams = A.synthetic.orbit_cams(nv, h, w, D)[None]
+    feats = A.synthetic.smooth_features(nv, h, w, 32, seed=0)[None]
+    weights = A.variables.synthetic_weights()
+    A.variables.load_weights(weights)
+    assert A.FLAGS.precision == 'fp16'
+    out = A.pipeline.run_multiview(cu(feats), cu(cams), D, siamese=True)
+    torch.cuda.synchronize()
+    ref = om.run_multiview_stage12(feats, cams, D, weights, siamese=True)
+    mae = _mae_over_range(npy(out['depth_up']), ref['depth_agg_init_up'], cams, D)
+    mae_lo = _mae_over_range(npy(out['depth']), ref['depth_agg_init'], cams, D)
+    p = torch.softmax(-torch.from_numpy(ref['prob_volume_agg']), dim=1).max(dim=1).values.mean().item()
+    print("cfg2 full size: depth_up MAE / range = %.3e (low-res %.3e), mean peak probability %.3f" % (mae, mae_lo, p))
+    assert p > 0.3
+    assert mae < 1e-3 and mae_lo < 1e-3, (mae, mae_lo)
+    for a, b in zip(out['depth_views'], ref['depth_views']):
+        assert _mae_over_range(npy(a), b, cams, D) < 1e-3
 
 
 def test_frame_stream_matches_run_multiview(A):
@@ -689,7 +715,7 @@ def test_frame_stream_matches_run_multiview(A):
     D, h, w, nv = 16, 16, 24, 3
     weights = A.variables.synthetic_weights(seed=11, logit_gain=2.0)
     A.variables.load_weights(weights)
-    A.FLAGS.precision = 'bf16'
+    assert A.FLAGS.precision == A.flags.DEFAULT_PRECISION
     cams = torch.from_numpy(A.synthetic.orbit_cams(nv, h, w, D)[None])
     frames = [(torch.from_numpy(A.synthetic.smooth_features(nv, h, w, 32, seed=s)[None]).pin_memory(), cams.pin_memory())
               for s in range(5)]

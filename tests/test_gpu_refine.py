@@ -101,7 +101,7 @@ def test_four_stage_schedule_fp32_against_oracle(A):
         out = A.pipeline.run_example_schedule(cu(imgs), cu(cams), D)
         torch.cuda.synchronize()
     finally:
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
     rng_ = float((D - 1) * di[0])
     assert tuple(out['depth_refined_up'].shape) == est_up.shape
     assert float(np.abs(out['depth'].cpu().numpy() - s12['depth_agg_init']).mean()) / rng_ < 1e-3
