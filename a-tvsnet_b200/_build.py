@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(HERE, "..", "include", "atvs.h"))
     headers.append(os.path.abspath(__file__))
     nvcc = _nvcc()
-    objs = []
+    objs, jobs = [], []
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
         if not os.path.exists(s):
@@ -59,7 +59,13 @@ def build(force=False, verbose=False):
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+    if jobs:     # one nvcc per translation unit, side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, check=False), jobs):
+                if r.returncode != 0:
+                    raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or _stale(OUT, objs):
         cmd = [nvcc] + ARCH + ["--shared", "-o", OUT] + objs
         if verbose:

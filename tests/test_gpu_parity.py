@@ -336,6 +336,51 @@ def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
 
 
 @HALF
+DECONV_RING_CASES = [(16, 8, (1, 16, 40, 48)), (32, 16, (1, 10, 36, 52)), (16, 8, (2, 9, 33, 29)), (32, 16, (1, 5, 17, 9)),
+                     (16, 8, (1, 64, 64, 80)), (16, 8, (1, 3, 2, 2)), (16, 8, (1, 1, 16, 8)), (32, 16, (1, 20, 32, 40))]
+
+
+@HALF
+@pytest.mark.parametrize('cin,cout,shape', DECONV_RING_CASES)
+def test_deconv3d_plane_ring(A, cin, cout, shape, half):
+    """transposed convolution as a plane ring (conv_deconv_ring.cu: 4 shifted MMAs per input plane into [3 output
+    planes][4 parity classes][Cout] columns): against the oracle conv3d_transpose on 16-bit-rounded operands, ragged
+    tiles, batches, z segments with and without the halo plane, fp32 and fp16 raw outputs, moments."""
+    from oracle import network as onet
+    from atvsnet_b200.network import conv3d_raw
+    x, w = _conv_case(cin, cout, 2, 1, 13, shape=shape)
+    xb = torch.from_numpy(x).to(half)
+    wb = torch.from_numpy(w).to(half).float()
+    A.variables.packed_cache().clear()
+    os.environ['ATVS_DECONV_RING_MINVOX'] = '1'
+    try:
+        raw, stats = conv3d_raw(xb.cuda(), 'dring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, True, True)
+        raw16, _ = conv3d_raw(xb.cuda(), 'dring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, True, True, raw_dtype=torch.float16)
+        os.environ['ATVS_DRING_ZS'] = '3'                 # short z segments: every unit but the first starts with a halo plane
+        raw_z, _ = conv3d_raw(xb.cuda(), 'dring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, True, True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ['ATVS_DECONV_RING_MINVOX']
+        os.environ.pop('ATVS_DRING_ZS', None)
+    ref = onet.deconv3d(xb.float().numpy(), wb.numpy())
+    assert raw.shape == ref.shape
+    assert rel_err(npy(raw), ref) < 1e-4
+    assert rel_err(npy(raw_z), ref) < 1e-4
+    assert np.array_equal(npy(raw).astype(np.float16), raw16.cpu().numpy())
+    s = stats.cpu().numpy()
+    flat = ref.reshape(-1, cout).astype(np.float64)
+    assert np.allclose(s[:cout], flat.sum(0), rtol=1e-3, atol=5e-2)
+    assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
+    # and the per-(class, tap) kernel it replaces gives the same result
+    os.environ['ATVS_NO_DECONV_RING'] = '1'
+    try:
+        A.variables.packed_cache().clear()
+        old, _ = conv3d_raw(xb.cuda(), 'dold_%d_%d' % (cin, cout), wb.cuda(), cout, 2, True, True)
+    finally:
+        del os.environ['ATVS_NO_DECONV_RING']
+    assert rel_err(npy(raw), npy(old)) < 2e-5
+
+
 @pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10)),
                                           (2, (1, 8, 128, 160))])
 def test_conv3d_split_cost_volume(A, stride, shape, half):
@@ -703,7 +748,7 @@ def test_cfg2_full_size_against_oracle(A):
     mae_lo = _mae_over_range(npy(out['depth']), ref['depth_agg_init'], cams, D)
     p = torch.softmax(-torch.from_numpy(ref['prob_volume_agg']), dim=1).max(dim=1).values.mean().item()
     print("cfg2 full size: depth_up MAE / range = %.3e (low-res %.3e), mean peak probability %.3f" % (mae, mae_lo, p))
-    assert p > 0.3
+    assert p > 0.2          # peaked, trained-like soft-argmin (a uniform softmax would be 1/128)
     assert mae < 1e-3 and mae_lo < 1e-3, (mae, mae_lo)
     for a, b in zip(out['depth_views'], ref['depth_views']):
         assert _mae_over_range(npy(a), b, cams, D) < 1e-3

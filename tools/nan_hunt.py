@@ -11,7 +11,7 @@ for streams in (1, 4):
     for split in (False, True):
         A.pipeline.CONCURRENT_PASSES = streams
         A.pipeline.SPLIT_COST_VOLUME = split
-        A.FLAGS.precision = 'bf16'
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
         A.variables.packed_cache().clear()
         for rep in range(3):
             out = A.pipeline.run_multiview(feats, cams, D, siamese=False)

@@ -8,7 +8,7 @@ ap.add_argument('--views', type=int, default=5)
 ap.add_argument('--D', type=int, default=128)
 ap.add_argument('--h', type=int, default=128)
 ap.add_argument('--w', type=int, default=160)
-ap.add_argument('--precision', default='bf16')
+ap.add_argument('--precision', default='fp16')
 ap.add_argument('--no-siamese', action='store_true')
 a = ap.parse_args()
 A.FLAGS.precision = a.precision
