@@ -43,7 +43,7 @@ _SIGS = {
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
-                                "atvs_packed_weight_bytes", "atvs_launch_count"])
+                                "atvs_packed_weight_bytes", "atvs_launch_count", "atvs_saturation_count"])
 
 
 def lib_path():
@@ -68,6 +68,8 @@ def load():
         lib.atvs_packed_weight_bytes.argtypes = [_i, _i, _i]
         lib.atvs_packed_weight_bytes.restype = C.c_size_t
         lib.atvs_launch_count.restype = C.c_longlong
+        lib.atvs_saturation_count.argtypes = [_i]
+        lib.atvs_saturation_count.restype = C.c_longlong
         _lib = lib
     return _lib
 

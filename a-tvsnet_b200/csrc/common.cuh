@@ -28,6 +28,9 @@ void atvs_set_error(const char* fmt, ...);
     } while (0)
 
 void atvs_count_launch();
+// device counter (one per device, allocated on first use - never during stream capture: every path is warmed up
+// eagerly first) of fp16 raw-output rows that had to be clamped to +-65504; read with atvs_saturation_count()
+unsigned long long* atvs_sat_ptr();
 #define ATVS_LAUNCH_CHECK()              \
     do {                                 \
         atvs_count_launch();             \

@@ -25,6 +25,7 @@ struct DcParams {
     int Cout, ncols;
     int raw16;                     // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;                  // operand format bits of the instruction descriptor (tc_fmt_bits)
+    unsigned long long* sat;       // saturation counter of the fp16 raw stores (atvs_sat_ptr)
     int nstages;
     int sh_off[8][3];              // shift s reads input voxel j + sh_off[s]
     int sh_first[9];               // pairs of shift s are [sh_first[s], sh_first[s+1])
@@ -194,7 +195,7 @@ k_deconv3d_tc(const __grid_constant__ DcMaps tm, const __grid_constant__ DcParam
                 const size_t o = valid ? ((((size_t)b * Do + (2 * jz + pz)) * Ho + (2 * jy + py)) * Wo + (2 * jx + px)) * p.Cout : 0;
                 // the accumulator set is released after the LAST class has been read
                 epilogue_tile<NPAD>(taddr + (uint32_t)(cls * NPAD), cls == 7 ? &tempty[acc] : nullptr, lane, valid, out, o,
-                                    p.ncols, vec, p.raw16, stats != nullptr, run);
+                                    p.ncols, vec, p.raw16, stats != nullptr, run, nullptr, p.sat);
             }
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, 0, p.ncols);
@@ -301,6 +302,7 @@ int deconv_fused(const void* x_bf16, int dtype, const void* wimg, int B, int D, 
     p.B = B; p.Dj = D; p.Hj = H; p.Wj = W; p.Cout = Cout; p.ncols = Cout;
     p.raw16 = raw16;
     p.fmt = tc_fmt_bits(dtype);
+    p.sat = raw16 ? atvs_sat_ptr() : nullptr;
     {
         static const int opts[][3] = {{2, 8, 8}, {1, 8, 16}, {4, 4, 8}, {2, 4, 16}, {1, 4, 32}, {4, 8, 4}, {8, 4, 4},
                                       {1, 16, 8}, {2, 16, 4}, {8, 8, 2}, {16, 4, 2}, {32, 2, 2}, {8, 16, 1}, {16, 8, 1},

@@ -38,6 +38,7 @@ struct DrParams {
     int Cout;
     int raw16;              // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;           // operand format bits of the instruction descriptor (tc_fmt_bits)
+    unsigned long long* sat;   // saturation counter of the fp16 raw stores (atvs_sat_ptr)
     int nXT, nYT, nZS, ZS;
     int nring, pf;
     int wbytes;
@@ -289,7 +290,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                 for (int cls = 0; cls < 4; ++cls) {
                     const int oy = 2 * y + (cls >> 1), ox = 2 * xq + (cls & 1);
                     const size_t off = ((((size_t)un.b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
-                    store_raw_row<COUT>(out, off, v + cls * COUT, COUT, vec, p.raw16);
+                    store_raw_row<COUT>(out, off, v + cls * COUT, COUT, vec, p.raw16, p.sat);
                     if (stats != nullptr) {
 #pragma unroll
                         for (int c = 0; c < COUT; ++c) {
@@ -384,6 +385,7 @@ int deconv_ring(const void* x16, int dtype, const void* wimg, int B, int D, int 
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
     p.raw16 = raw16;
     p.fmt = tc_fmt_bits(dtype);
+    p.sat = raw16 ? atvs_sat_ptr() : nullptr;
     p.nXT = (W + DR_TX - 1) / DR_TX;
     p.nYT = (H + DR_TY - 1) / DR_TY;
     p.wbytes = (int)dr_wbytes(Cin, Cout);

@@ -63,6 +63,7 @@ struct RingParams {
     int Cout, coff, ncols;
     int raw16;          // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;       // operand format bits of the instruction descriptor (tc_fmt_bits)
+    unsigned long long* sat;   // saturation counter of the fp16 raw stores (atvs_sat_ptr)
     int nXT, nYT, nZS, ZS;
     int nring, pf;      // ring slots, planes of cp.async in flight per producer thread (pf <= nring - 1, <= 8)
     int wbytes;
@@ -422,7 +423,7 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                                 if (c < p.ncols) v[mt][c] += __ldg(brow + c);
                         }
                     }
-                    store_raw_row<CP>(out, ooff, v[mt], p.ncols, vec, p.raw16);
+                    store_raw_row<CP>(out, ooff, v[mt], p.ncols, vec, p.raw16, p.sat);
                     if (stats != nullptr) {
                         // per-THREAD running moments (rows = this thread's voxels): no cross-lane traffic per tile
 #pragma unroll
@@ -545,6 +546,7 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
     p.raw16 = raw16;
     p.fmt = tc_fmt_bits(dtype);
+    p.sat = raw16 ? atvs_sat_ptr() : nullptr;
     p.nXT = (W + RG_TX - 1) / RG_TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
     p.wbytes = (int)ring_slab_bytes(Cin, cp);

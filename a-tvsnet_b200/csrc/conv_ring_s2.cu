@@ -36,6 +36,7 @@ struct S2Params {
     int Cout, coff, ncols;
     int raw16;                  // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;               // operand format bits of the instruction descriptor (tc_fmt_bits)
+    unsigned long long* sat;    // saturation counter of the fp16 raw stores (atvs_sat_ptr)
     int nXT, nYT, nZS, ZS;
     int nring;
     int wbytes;
@@ -328,7 +329,7 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                             if (c < p.ncols) v[c] += __ldg(brow + c);
                     }
                 }
-                store_raw_row<CP>(out, ooff, v, p.ncols, vec, p.raw16);
+                store_raw_row<CP>(out, ooff, v, p.ncols, vec, p.raw16, p.sat);
                 if (stats != nullptr) {
 #pragma unroll
                     for (int c = 0; c < CP; ++c) {
@@ -437,6 +438,7 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
     p.B = B; p.D = D; p.H = H; p.W = W; p.Do = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Cout = Cout;
     p.raw16 = raw16;
     p.fmt = tc_fmt_bits(dtype);
+    p.sat = raw16 ? atvs_sat_ptr() : nullptr;
     p.nXT = (p.Wo + S2_TX - 1) / S2_TX;
     p.nYT = (p.Ho + S2_TY - 1) / S2_TY;
     p.wbytes = (int)s2_slab_bytes(Cin, cp);

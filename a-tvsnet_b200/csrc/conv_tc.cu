@@ -46,6 +46,7 @@ struct TcParams {
     int Cout, coff, ncols;     // real channel count, slab offset, real columns in this slab
     int raw16;                 // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;              // operand format bits of the instruction descriptor (tc_fmt_bits)
+    unsigned long long* sat;   // saturation counter of the fp16 raw stores (atvs_sat_ptr)
     int nstages;
     long long ntiles;
 };
@@ -224,7 +225,7 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
                 brow = bias + ((((size_t)b * 3 + zc) * p.Ho + jy) * p.Wo + jx) * p.Cout + p.coff;
             }
             epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out, o, p.ncols,
-                                raw_vec_mode(out, p.ncols, p.Cout, p.coff), p.raw16, stats != nullptr, run, brow);
+                                raw_vec_mode(out, p.ncols, p.Cout, p.coff), p.raw16, stats != nullptr, run, brow, p.sat);
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
     }
@@ -456,6 +457,7 @@ static int conv3d_tc_impl(const void* x_bf16, int x_dtype, const void* wpacked, 
         p.Cout = Cout;
         p.raw16 = raw16;
         p.fmt = tc_fmt_bits(x_dtype);
+        p.sat = raw16 ? atvs_sat_ptr() : nullptr;
         p.ncls = c1 - c0;
         // brick shape: 128 voxels, minimise padded volume, prefer a wide x extent
         {

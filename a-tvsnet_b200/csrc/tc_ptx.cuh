@@ -225,8 +225,17 @@ __device__ __forceinline__ int raw_vec_mode(const void* out, int ncols, int Cout
     if (((ncols | Cout | coff) & 3) == 0 && (((uintptr_t)out) & 15) == 0) return 4;
     return 1;
 }
+// `sat` (may be NULL): device counter of fp16 raw rows that held a value beyond +-65504 and were clamped
 template <int NC>
-__device__ __forceinline__ void store_raw_row(float* out, size_t off, const float* v, int ncols, int vec, int raw16) {
+__device__ __forceinline__ void store_raw_row(float* out, size_t off, const float* v, int ncols, int vec, int raw16,
+                                              unsigned long long* sat = nullptr) {
+    if (raw16 && sat != nullptr) {
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (c < ncols) m = fmaxf(m, fabsf(v[c]));
+        if (m > 65504.f) atomicAdd(sat, 1ULL);
+    }
     if (!raw16) {
         float* op = out + off;
         if (vec == 8) {
@@ -281,7 +290,7 @@ __device__ __forceinline__ void store_raw_row(float* out, size_t off, const floa
 template <int NPAD>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_bar, int lane, bool valid, float* out,
                                               size_t off, int ncols, int vec, int raw16, bool want_stats, float* run,
-                                              const float* bias_row = nullptr) {
+                                              const float* bias_row = nullptr, unsigned long long* sat = nullptr) {
     const bool vec4 = vec >= 4;
     float v[NPAD];
 #pragma unroll
@@ -305,7 +314,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_b
                 if (c < ncols) v[c] += __ldg(bias_row + c);
         }
     }
-    if (valid) store_raw_row<NPAD>(out, off, v, ncols, vec, raw16);
+    if (valid) store_raw_row<NPAD>(out, off, v, ncols, vec, raw16, sat);
     if (want_stats && valid) {
         // per-THREAD running moments (row = this thread's voxel): no cross-lane traffic per tile
 #pragma unroll

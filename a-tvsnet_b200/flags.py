@@ -22,9 +22,11 @@ class _Flags(object):
         self.precision = DEFAULT_PRECISION
         # tensor-core path: dtype of the raw (pre-BN) convolution outputs, 'f16' (saturated) or 'f32'
         self.raw_dtype = 'f16'
-        # ... and of the layers fed by the UN-normalised cost volume (conv_b0_0_1 / conv_b0_1_0): their magnitude
-        # follows the checkpoint's feature scale, which no normalisation bounds, so they default to fp32
-        self.first_raw_dtype = 'f32'
+        # ... and of the layers fed by the UN-normalised cost volume (conv_b0_0_1 / conv_b0_1_0), whose magnitude
+        # follows the checkpoint's feature scale: fp16 as well, guarded by the epilogues' saturation counter
+        # (atvs_saturation_count, pipeline.check_saturation): a clamped value is detected, never silent; set 'f32'
+        # for a checkpoint whose features exceed ~1e3
+        self.first_raw_dtype = 'f16'
 
 
 FLAGS = _Flags()

@@ -123,6 +123,23 @@ def aggregate(filtered_views, scope='attention_aggregate', group=None, rank=0, w
     return out.reshape(shape)
 
 
+def check_saturation(reset=True, action='raise'):
+    """fp16 raw-output rows that had to be clamped to +-65504 by the tensor-path epilogues since the last reset
+    (atvs_saturation_count; synchronises the device, so call it once per batch of frames, not per kernel).  A non-zero
+    count means the feature scale of the loaded checkpoint does not fit fp16 raw storage: ``action='raise'`` raises,
+    ``'fallback'`` switches FLAGS.raw_dtype / first_raw_dtype to 'f32' for the following frames and returns the count."""
+    n = int(L.load().atvs_saturation_count(1 if reset else 0))
+    if n < 0:
+        raise RuntimeError("atvs_saturation_count failed")
+    if n > 0:
+        if action == 'fallback':
+            N.FLAGS.raw_dtype = N.FLAGS.first_raw_dtype = 'f32'
+        elif action == 'raise':
+            raise RuntimeError("%d fp16 raw-output rows were clamped to +-65504: the feature scale of these weights does "
+                               "not fit fp16 raw storage; set FLAGS.raw_dtype = FLAGS.first_raw_dtype = 'f32'" % n)
+    return n
+
+
 def shard_views(n_views, rank, world):
     """source views 1..N-1 dealt round-robin to ranks."""
     return [v for v in range(1, n_views) if (v - 1) % world == rank]
@@ -256,6 +273,8 @@ def run_example(images, cams, depth_num=None):
         out = run_twoview(images, cams, D)
         inv = out['depth_refined_up']
     out['pred'] = inverse_to_depth(inv, twoview=n_views <= 2)
+    if N.act_dtype() in N.HALF_DTYPES:
+        check_saturation()
     return out
 
 

@@ -288,6 +288,7 @@ def run_ours(args, rank, world, local_rank):
     if not bool(torch.isfinite(dm).all()) or float(dm.min()) < dmin - 1e-4 or float(dm.max()) > dmax + 1e-4:
         raise RuntimeError("bench: depth map not finite / outside the depth sweep [%g, %g]: min %g max %g"
                            % (dmin, dmax, float(dm.min()), float(dm.max())))
+    saturated = A.pipeline.check_saturation(action='count') if args.precision != 'fp32' else 0
     h2d = feats_h.numel() * 4 + cams_h.numel() * 4
     d2h = depth_h.numel() * 4
 
@@ -402,7 +403,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clk,
-        "output_check": "depth map finite and inside the inverse-depth sweep",
+        "output_check": "depth map finite and inside the inverse-depth sweep; fp16 raw rows clamped: %d" % saturated,
     }
     if roof is not None:
         line["roofline"] = roof

@@ -45,6 +45,10 @@ int         atvs_version(void);                 /* major*10000 + minor*100 + pat
 const char* atvs_last_error(void);              /* thread-local, never NULL               */
 int         atvs_device_sm_count(void);         /* SMs of the current device (148 on B200) */
 long long   atvs_launch_count(void);            /* kernels launched by this library so far  */
+/* number of fp16 raw-output rows (8..32 channels of one voxel) that held a value beyond +-65504 and were clamped by
+ * the tensor-path epilogues on the current device since the last reset; synchronises the device; -1 on error.  A
+ * non-zero count means the checkpoint's feature scale does not fit fp16 raw storage: rerun with fp32 raw outputs. */
+long long   atvs_saturation_count(int reset);
 
 /* ---- get_homographies ------------------------------------------- homography_warping.py:179-227
  * left_cam/right_cam (B,2,4,4) f32, depth_start/depth_interval (B) f32 -> out (B,D,3,3) f32.

@@ -67,7 +67,8 @@ def test_argument_errors_without_gpu(lib):
     # per-tap TMA image + halo-ring images (stride 1, and stride 2 for Cin <= 32)
     assert lib.atvs_packed_weight_bytes(64, 64, 0) == 2 * 27 * 2 * 32 * 64 + 2 * 36 * 2 * 96 * 16
     assert lib.atvs_packed_weight_bytes(8, 8, 0) == 28 * 16 * 8 * 2 + 5 * 2 * 64 * 16 + 5 * 2 * 48 * 16
-    assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2 * 2      # per-class image + fused 8-class image
+    # per-class image + fused 8-class image + plane-ring image [4 shifts][2 chunks][3 planes x 4 classes x 8][8]
+    assert lib.atvs_packed_weight_bytes(16, 8, 1) == 27 * 16 * 16 * 2 * 2 + 4 * 2 * 96 * 16
 
 
 def test_ops_refuse_cpu_tensors():

@@ -300,9 +300,16 @@ def test_raw_fp16_saturates(A, half):
     w = torch.full((3, 3, 3, 8, 8), 2.0).cuda()      # 27 * 8 * 300 * 2 = 129 600 > 65 504
     w[..., 1] = -2.0
     A.variables.packed_cache().clear()
+    A.pipeline.check_saturation(action='count')
     r16, _ = conv3d_raw(x, 'sat16', w, 8, 1, False, True, raw_dtype=torch.float16)
     v = r16.float()
     assert bool(torch.isfinite(v).all()) and float(v.max()) == 65504.0 and float(v.min()) == -65504.0
+    # ... and is never silent: the epilogue counts every clamped row
+    with pytest.raises(RuntimeError, match='clamped'):
+        A.pipeline.check_saturation()
+    assert A.pipeline.check_saturation(action='count') == 0          # the failed check reset the counter
+    ok16, _ = conv3d_raw((x * 0.01).to(half), 'sat16', w, 8, 1, False, True, raw_dtype=torch.float16)
+    assert A.pipeline.check_saturation(action='count') == 0
 
 
 S2_RING_CASES = [(8, 16, (1, 32, 128, 160)), (32, 16, (1, 16, 128, 192)), (16, 32, (2, 20, 144, 112)), (8, 8, (1, 12, 260, 196)),
@@ -335,7 +342,6 @@ def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
     assert np.allclose(s[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
 
 
-@HALF
 DECONV_RING_CASES = [(16, 8, (1, 16, 40, 48)), (32, 16, (1, 10, 36, 52)), (16, 8, (2, 9, 33, 29)), (32, 16, (1, 5, 17, 9)),
                      (16, 8, (1, 64, 64, 80)), (16, 8, (1, 3, 2, 2)), (16, 8, (1, 1, 16, 8)), (32, 16, (1, 20, 32, 40))]
 
@@ -381,6 +387,7 @@ def test_deconv3d_plane_ring(A, cin, cout, shape, half):
     assert rel_err(npy(raw), npy(old)) < 2e-5
 
 
+@HALF
 @pytest.mark.parametrize('stride,shape', [(1, (1, 8, 40, 104)), (2, (1, 8, 40, 104)), (1, (2, 4, 10, 12)), (2, (2, 4, 12, 10)),
                                           (2, (1, 8, 128, 160))])
 def test_conv3d_split_cost_volume(A, stride, shape, half):
@@ -396,16 +403,15 @@ def test_conv3d_split_cost_volume(A, stride, shape, half):
     w = w.to(half).float()
     A.variables.packed_cache().clear()
     stats = torch.zeros(128, dtype=torch.float64, device='cuda')
-    assert A.FLAGS.first_raw_dtype == 'f32'      # default for the layers fed by the un-normalised cost volume
-    raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
-    assert raw.dtype == torch.float32
-    # optional storage as saturated fp16 = one rounding of the fp32 result
-    A.FLAGS.first_raw_dtype = 'f16'
+    A.FLAGS.first_raw_dtype = 'f32'
     try:
-        raw16, _ = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride,
-                                torch.zeros(128, dtype=torch.float64, device='cuda'))
+        raw, st = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride, stats)
     finally:
-        A.FLAGS.first_raw_dtype = 'f32'
+        A.FLAGS.first_raw_dtype = 'f16'
+    assert raw.dtype == torch.float32
+    # default storage: saturated fp16 (guarded by the saturation counter) = one rounding of the fp32 result
+    raw16, _ = conv3d_split(SplitCostVolume(ref.float().cuda(), warped.cuda()), 'split_t', w.cuda(), cout, stride,
+                            torch.zeros(128, dtype=torch.float64, device='cuda'))
     assert raw16.dtype == torch.float16 and np.array_equal(npy(raw).astype(np.float16), raw16.cpu().numpy())
     full = np.concatenate([np.tile(ref.float().numpy()[:, None], (1, D, 1, 1, 1)), warped.float().numpy()], axis=-1)
     refo = onet.conv3d(full, w.numpy(), stride)
