@@ -16,8 +16,11 @@
 //
 //   work unit : a 16(y) x 8(x) tile of input positions over an input z segment [z0, z0+zlen) (+ plane z0-1,
 //               whose kz=2 taps complete output plane 2*z0)
-//   warps 0-3 producers (cp.async, zero fill = outside the volume) | warp 4 MMA issuer | warps 5-8 epilogue
-//   accumulation is always "+=": the epilogue zeroes a group right after reading it.
+//   warps 0-3 producers (cp.async, zero fill = outside the volume) | warp 4 MMA issuer | warps 5-12 epilogue:
+//   two sets of four warps (one per TMEM lane quarter), set 0 drains the even output planes, set 1 the odd ones -
+//   the per-role timelines (tools/build_trace.sh, profiles/r02_deconv_ring_trace.txt) showed ONE set as the critical
+//   path at ~1600 cycles per input plane (convert + store + moments of 2 x 128 x 32 values on 4 warps) with the MMA
+//   warp waiting for accumulators.  Accumulation is always "+=": the epilogue zeroes a group right after reading it.
 #include "ring_common.cuh"
 #include "conv_deconv.cuh"
 #include <cstring>
@@ -29,7 +32,7 @@ constexpr int DR_TY = 16, DR_TX = 8, DR_HH = DR_TY + 1, DR_WW = DR_TX + 1;
 constexpr int DR_NVOX = DR_HH * DR_WW;              // voxels of one halo plane (153)
 constexpr int DR_KCH_PAD = DR_NVOX * 16 + 16;       // pitch of one 8-channel chunk plane (+16 B: bank skew)
 constexpr int DR_PRODUCERS = 128;
-constexpr int DR_THREADS = 288;
+constexpr int DR_THREADS = 416;                     // 4 producer + 1 MMA + 8 epilogue warps
 constexpr int DR_G = 8;                              // accumulator groups (output planes) in TMEM
 constexpr int DR_MAXR = 16;                          // ring slots (mbarrier pairs)
 
@@ -74,8 +77,18 @@ __device__ __forceinline__ DrUnit dr_decode(const DrParams& p, long long u) {
     return r;
 }
 
-template <int CIN, int COUT, int MINB>
-__global__ void __launch_bounds__(DR_THREADS, MINB)
+// 16 consecutive fp32 values -> 16 saturated halves, ONE 32-byte store (p 32-byte aligned)
+__device__ __forceinline__ void store_f16x16(__half* p, const float* v) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(DR_THREADS, 1)
 k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams p, const uint8_t* __restrict__ wimg,
                 float* __restrict__ out, double* __restrict__ stats) {
     using Cfg = DrCfg<CIN, COUT>;
@@ -118,7 +131,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 5) {
+    if (warp >= 5 && warp < 9) {
         // accumulation is always "+=": start from zero accumulators
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (uint32_t c = 0; c < Cfg::TMEM_COLS; c += 8) tc_st8_zero(taddr + c);
@@ -140,7 +153,11 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
         uint32_t slot = 0, sphase = 0, pslot = 0, pending = 0;
         const uint32_t ring_u32 = smem_u32(ring);
         auto publish = [&](int keep) {
-            if (keep >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+            if (keep >= 7) asm volatile("cp.async.wait_group 7;" ::: "memory");
+            else if (keep == 6) asm volatile("cp.async.wait_group 6;" ::: "memory");
+            else if (keep == 5) asm volatile("cp.async.wait_group 5;" ::: "memory");
+            else if (keep == 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+            else if (keep == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
             else if (keep == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
             else if (keep == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -152,6 +169,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
             }
         };
         const size_t zstride_in = (size_t)p.H * p.W * CIN;
+        TRACE_DECL
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const DrUnit un = dr_decode(p, u);
             const int ibeg = un.z0 > 0 ? -1 : 0;
@@ -168,6 +186,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
             const uint16_t* zbase = x + ((size_t)un.b * p.D + (un.z0 + ibeg)) * zstride_in;
             for (int i = ibeg; i < un.zlen; ++i, zbase += zstride_in) {
                 mbar_wait(&empty[slot], sphase ^ 1);
+                TRACE(0);
                 const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
 #pragma unroll
                 for (int k = 0; k < NITEM; ++k) {
@@ -182,11 +201,15 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
+                TRACE(1);
                 if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
                 if (++pending >= (uint32_t)PF) publish(PF - 1);
+                TRACE(2);
+                TRACE_NEXT();
             }
         }
         publish(0);
+        if (ptid == 0) TRACE_DUMP("P");
     } else if (warp == 4) {
         // ===================== MMA issuer (one elected thread) =====================
         if (elect_one()) {
@@ -209,6 +232,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
             };
             uint32_t slot = 0, sphase = 0;
             uint32_t gq = 0, gphase = 0;       // accumulator group / phase of output plane t = 0 of the unit
+            TRACE_DECL
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const DrUnit un = dr_decode(p, u);
                 const int ibeg = un.z0 > 0 ? -1 : 0;
@@ -226,7 +250,9 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                         ++twaited;
                         if (++gw == (uint32_t)G) { gw = 0; gwphase ^= 1; }
                     }
+                    TRACE(0);
                     mbar_wait(&full[slot], sphase);
+                    TRACE(1);
                     tc_fence_after();
                     const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
                     uint32_t glo = gq + (uint32_t)tlo;
@@ -247,33 +273,43 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                         tc_commit(&tfull[gdone]);
                         if (++gdone == (uint32_t)G) gdone = 0;
                     }
+                    TRACE(2);
+                    TRACE_NEXT();
                 }
                 gq = gw; gphase = gwphase;
             }
+            TRACE_DUMP("M");
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-        const int g = warp & 3;
+        // ===================== epilogue: 2 sets x 4 warps (128 TMEM lanes each) =====================
+        const int set = (warp - 5) >> 2;          // warps 5-8: even output planes, warps 9-12: odd output planes
+        const int g = warp & 3;                   // TMEM lane quarter of this warp
         const int row = g * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
         float run[2 * COUT];
 #pragma unroll
         for (int k = 0; k < 2 * COUT; ++k) run[k] = 0.f;
+        float vmax = 0.f;
         const int vec = raw_vec_mode(out, COUT, COUT, 0);
+        const bool fast16 = p.raw16 && COUT == 8 && (((uintptr_t)out) & 31) == 0;
         const int Ho = 2 * p.H, Wo = 2 * p.W, Do = 2 * p.D;
-        uint32_t grp = 0, gphase = 0;
+        // a unit starts on an even group and consumes an even number of groups: set s only ever sees groups of parity s
+        uint32_t grp = (uint32_t)set, gphase = 0;
+        TRACE_DECL
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const DrUnit un = dr_decode(p, u);
             const int y = un.y0 + ty, xq = un.x0 + tx;
             const bool ok = y < p.H && xq < p.W;
             const int nt = 2 * un.zlen;
-            for (int t = 0; t < nt; ++t) {
+            for (int t = set; t < nt; t += 2) {
                 mbar_wait(&tfull[grp], gphase);
+                TRACE(0);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + grp * (uint32_t)GC;
                 uint64_t* const tempty_bar = &tempty[grp];
-                if (++grp == (uint32_t)G) { grp = 0; gphase ^= 1; }
+                grp += 2;
+                if (grp >= (uint32_t)G) { grp -= (uint32_t)G; gphase ^= 1; }
                 float v[GC];
 #pragma unroll
                 for (int c = 0; c < GC; c += 8) tc_ld8(taddr + c, v + c);
@@ -284,24 +320,31 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
-                if (!ok) continue;
+                TRACE(1);
+                if (!ok) { TRACE_NEXT(); continue; }
                 const int oz = 2 * un.z0 + t;
 #pragma unroll
-                for (int cls = 0; cls < 4; ++cls) {
-                    const int oy = 2 * y + (cls >> 1), ox = 2 * xq + (cls & 1);
-                    const size_t off = ((((size_t)un.b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
-                    store_raw_row<COUT>(out, off, v + cls * COUT, COUT, vec, p.raw16, p.sat);
-                    if (stats != nullptr) {
+                for (int py = 0; py < 2; ++py) {
+                    // classes (py, 0) and (py, 1) are x neighbours: 2 * Cout contiguous output values
+                    const size_t off = ((((size_t)un.b * Do + oz) * Ho + (2 * y + py)) * Wo + 2 * xq) * COUT;
+                    const float* vv = v + py * 2 * COUT;
+                    if (fast16) store_f16x16(reinterpret_cast<__half*>(out) + off, vv);
+                    else store_raw_row<2 * COUT>(out, off, vv, 2 * COUT, vec, p.raw16, nullptr);
 #pragma unroll
-                        for (int c = 0; c < COUT; ++c) {
-                            const float q = v[cls * COUT + c];
-                            run[c] += q;
-                            run[COUT + c] = fmaf(q, q, run[COUT + c]);
-                        }
+                    for (int c = 0; c < 2 * COUT; ++c) {
+                        const float r = vv[c];
+                        vmax = fmaxf(vmax, fabsf(r));
+                        run[c % COUT] += r;
+                        run[COUT + c % COUT] = fmaf(r, r, run[COUT + c % COUT]);
                     }
                 }
+                TRACE(2);
+                TRACE_NEXT();
             }
         }
+        // fp16 raw output: count the threads that had to clamp a value (atvs_saturation_count)
+        if (p.raw16 && p.sat != nullptr && vmax > 65504.f) atomicAdd(p.sat, 1ULL);
+        if (warp == 5 && lane == 0) TRACE_DUMP("E");
         if (stats != nullptr) {
 #pragma unroll
             for (int k = 0; k < 2 * COUT; ++k) {
@@ -342,15 +385,15 @@ __global__ void k_pack_deconv_ring(const float* __restrict__ w, int Cin, int Cou
     }
 }
 
-template <int CIN, int COUT, int MINB>
+template <int CIN, int COUT>
 int launch_dr(const uint16_t* x, const DrParams& p, const uint8_t* wimg, float* out, double* stats, size_t smem, int grid,
               cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        ATVS_CUDA(cudaFuncSetAttribute(k_deconv3d_ring<CIN, COUT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ATVS_CUDA(cudaFuncSetAttribute(k_deconv3d_ring<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_deconv3d_ring<CIN, COUT, MINB><<<grid, DR_THREADS, smem, st>>>(x, p, wimg, out, stats);
+    k_deconv3d_ring<CIN, COUT><<<grid, DR_THREADS, smem, st>>>(x, p, wimg, out, stats);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -391,30 +434,26 @@ int deconv_ring(const void* x16, int dtype, const void* wimg, int B, int D, int 
     p.wbytes = (int)dr_wbytes(Cin, Cout);
     const size_t slot = ((size_t)(Cin / 8) * DR_KCH_PAD + 127) / 128 * 128;
     const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * DR_MAXR + 2 * DR_G + 1) * 8 + 16;
-    // Cout = 8: 256 TMEM columns -> two co-resident CTAs per SM (their handshake latencies overlap)
-    int minb = (Cout == 8 && fixed + 4 * slot <= 110 * 1024) ? 2 : 1;
-    if ((long long)B * p.nXT * p.nYT * D < (long long)sms * 2 * 4) minb = 1;
-    if (const char* e = getenv("ATVS_DRING_MINB")) minb = atoi(e) == 1 ? 1 : minb;
-    const size_t budget = (minb == 2 ? 110 : 220) * 1024;
+    // one CTA of 13 warps per SM (8 epilogue warps need the registers); at most half of the shared memory, so that a
+    // CTA of another stream's kernel can co-reside
+    const int minb = 1;
+    const size_t budget = 110 * 1024;
     int nring = (int)((budget - fixed) / slot);
-    if (nring > 8) nring = 8;
+    if (nring > 12) nring = 12;
     if (const char* e = getenv("ATVS_DRING_R")) nring = atoi(e) >= 2 && atoi(e) < nring ? atoi(e) : nring;
     if (nring < 2) {
         atvs_set_error("atvs_conv3d_tc(deconv ring): weights do not fit next to 2 ring planes (Cin=%d Cout=%d)", Cin, Cout);
         return ATVS_E_UNSUP;
     }
     p.nring = nring;
-    p.pf = (nring >= 5) ? 4 : (nring >= 3 ? 2 : 1);
+    // planes of cp.async in flight per producer thread (the loads queue behind the kernel's own 8x larger write stream:
+    // ~4000 cycles of latency in the timelines), at most nring - 1 and 8
+    p.pf = nring - 1 < 8 ? nring - 1 : 8;
+    if (const char* e = getenv("ATVS_DRING_PF")) p.pf = atoi(e) >= 1 && atoi(e) < p.pf ? atoi(e) : p.pf;
     {   // input z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
         const long long slots = (long long)sms * minb;
-        long long best = -1;
-        int bz = D;
-        for (int zs = (D < 2 ? D : 2); zs <= D; ++zs) {
-            const long long units = cols * ((D + zs - 1) / zs);
-            const long long cost = ((units + slots - 1) / slots) * (zs + 1);
-            if (best < 0 || cost < best) { best = cost; bz = zs; }
-        }
+        int bz = ring_pick_zs(cols, D, slots, 1, 1, 0.4, 10.0, 2);
         if (const char* e = getenv("ATVS_DRING_ZS")) bz = atoi(e) > 0 && atoi(e) <= D ? atoi(e) : bz;
         p.ZS = bz;
         p.nZS = (D + bz - 1) / bz;
@@ -423,10 +462,8 @@ int deconv_ring(const void* x16, int dtype, const void* wimg, int B, int D, int 
     const size_t smem = fixed + (size_t)nring * slot;
     const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
     const uint8_t* wi = (const uint8_t*)wimg;
-    if (Cin == 16 && Cout == 8)
-        return minb == 2 ? launch_dr<16, 8, 2>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st)
-                         : launch_dr<16, 8, 1>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);
-    if (Cin == 32 && Cout == 16) return launch_dr<32, 16, 1>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);
+    if (Cin == 16 && Cout == 8) return launch_dr<16, 8>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);
+    if (Cin == 32 && Cout == 16) return launch_dr<32, 16>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);
     atvs_set_error("atvs_conv3d_tc(deconv ring): no kernel for Cin=%d Cout=%d", Cin, Cout);
     return ATVS_E_UNSUP;
 }

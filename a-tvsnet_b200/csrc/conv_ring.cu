@@ -34,17 +34,6 @@
 
 namespace {
 
-#ifdef ATVS_RING_TRACE
-#define TRACE_DECL long long tr_[3][48]; int trn_ = 0; for (int q_ = 0; q_ < 48; ++q_) tr_[0][q_] = tr_[1][q_] = tr_[2][q_] = 0;
-#define TRACE(k) do { if (blockIdx.x == 0 && trn_ < 48) tr_[k][trn_] = clock64(); } while (0)
-#define TRACE_NEXT() do { ++trn_; } while (0)
-#define TRACE_DUMP(name) do { if (blockIdx.x == 0) for (int q_ = 0; q_ < 48 && q_ < trn_; ++q_) printf("%s %d %lld %lld %lld\n", name, q_, tr_[0][q_], tr_[1][q_], tr_[2][q_]); } while (0)
-#else
-#define TRACE_DECL
-#define TRACE(k)
-#define TRACE_NEXT()
-#define TRACE_DUMP(name)
-#endif
 
 // one CTA plane = RG_MT MMA tiles (16 y x 8 x each) side by side in x: every mbarrier handshake of the
 // producer / MMA / epilogue pipeline (~200 cycles each, ~4 per role and plane) then serves 256 voxels
@@ -584,14 +573,15 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     {   // z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
         const long long slots = (long long)sms * minb;
-        long long best = -1;
-        int bz = D;
-        for (int zs = (D < 4 ? D : 4); zs <= D; ++zs) {
-            const long long units = cols * ((D + zs - 1) / zs);
-            const long long cost = ((units + slots - 1) / slots) * (zs + 2);
-            if (best < 0 || cost < best) { best = cost; bz = zs; }
+        // the MMA-bound wide-input layers (Cin >= 32: ~4x longer plane steps) weigh the startup less
+        int bz = ring_pick_zs(cols, D, slots, 1, 2, Cin >= 32 ? 0.8 : 0.4, Cin >= 32 ? 2.5 : 10.0, 4);
+        {   // experiment knobs: ATVS_RING_ZS_<Cin>_<Cout> (one layer kind) beats ATVS_RING_ZS (all)
+            char name[48];
+            snprintf(name, sizeof(name), "ATVS_RING_ZS_%d_%d", Cin, Cout);
+            const char* e = getenv(name);
+            if (!e) e = getenv("ATVS_RING_ZS");
+            if (e && atoi(e) > 0) bz = atoi(e) <= D ? atoi(e) : D;
         }
-        if (const char* e = getenv("ATVS_RING_ZS")) bz = atoi(e) > 0 && atoi(e) <= D ? atoi(e) : bz;
         p.ZS = bz;
         p.nZS = (D + bz - 1) / bz;
         p.nunits = cols * p.nZS;

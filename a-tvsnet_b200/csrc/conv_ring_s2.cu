@@ -458,14 +458,14 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
     {   // output z segment length: minimise waves * (input planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
         const long long slots = (long long)sms * minb;
-        long long best = -1;
-        int bz = p.Do;
-        for (int zs = (p.Do < 2 ? p.Do : 2); zs <= p.Do; ++zs) {
-            const long long units = cols * ((p.Do + zs - 1) / zs);
-            const long long cost = ((units + slots - 1) / slots) * (2 * zs + 1);
-            if (best < 0 || cost < best) { best = cost; bz = zs; }
+        int bz = ring_pick_zs(cols, p.Do, slots, 2, 1, Cin >= 32 ? 0.8 : 0.4, Cin >= 32 ? 2.5 : 10.0, 2);
+        {   // experiment knobs: ATVS_S2_ZS_<Cin>_<Cout> (one layer kind) beats ATVS_S2_ZS (all stride-2 ring layers)
+            char name[48];
+            snprintf(name, sizeof(name), "ATVS_S2_ZS_%d_%d", Cin, Cout);
+            const char* e = getenv(name);
+            if (!e) e = getenv("ATVS_S2_ZS");
+            if (e && atoi(e) > 0) bz = atoi(e) <= p.Do ? atoi(e) : p.Do;
         }
-        if (const char* e = getenv("ATVS_RING_ZS")) bz = atoi(e) > 0 && atoi(e) <= p.Do ? atoi(e) : bz;
         p.ZS = bz;
         p.nZS = (p.Do + bz - 1) / bz;
         p.nunits = cols * p.nZS;

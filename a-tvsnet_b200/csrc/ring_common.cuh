@@ -2,6 +2,19 @@
 #pragma once
 #include "tc_ptx.cuh"
 
+// per-role clock64 timelines of CTA 0 (build with -DATVS_RING_TRACE: tools/build_trace.sh, tools/ring_trace.py)
+#ifdef ATVS_RING_TRACE
+#define TRACE_DECL long long tr_[3][48]; int trn_ = 0; for (int q_ = 0; q_ < 48; ++q_) tr_[0][q_] = tr_[1][q_] = tr_[2][q_] = 0;
+#define TRACE(k) do { if (blockIdx.x == 0 && trn_ < 48) tr_[k][trn_] = clock64(); } while (0)
+#define TRACE_NEXT() do { ++trn_; } while (0)
+#define TRACE_DUMP(name) do { if (blockIdx.x == 0) for (int q_ = 0; q_ < 48 && q_ < trn_; ++q_) printf("%s %d %lld %lld %lld\n", name, q_, tr_[0][q_], tr_[1][q_], tr_[2][q_]); } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(k)
+#define TRACE_NEXT()
+#define TRACE_DUMP(name)
+#endif
+
 namespace {
 
 // warp-converged wait: every lane polls, the vote makes the loop condition (and everything computed
@@ -63,5 +76,26 @@ __host__ __device__ constexpr uint32_t ring_idesc(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+
+// z-segment length of a plane-ring kernel's work units.  A unit costs (planes + startup) plane steps, where `startup`
+// stands for the per-CTA fixed cost (TMEM allocation, weight image, pipeline fill) in plane steps.  The kernel shares
+// the GPU with the other passes of a depth map (4-8 streams), so it is charged as if a fraction `share` of the
+// `slots` (SMs x CTAs per SM) were its own; the real wave count bounds it from below.  Measured on the whole cfg2 step
+// (tools/tune_step.py, profiles/r02_tune_step.txt): per-kernel-optimal short units (many CTAs) cost 0.8 ms of 6.7.
+//   cols: tile columns, nz: planes along z, planes(zs) = per_z * zs + halo plane steps per unit
+inline int ring_pick_zs(long long cols, int nz, long long slots, int per_z, int halo, double share, double startup,
+                        int zmin) {
+    double best = -1.0;
+    int bz = nz;
+    const double mine = share * (double)slots;
+    for (int zs = (nz < zmin ? nz : zmin); zs <= nz; ++zs) {
+        const long long units = cols * ((nz + zs - 1) / zs);
+        double waves = (double)((units + slots - 1) / slots);
+        if ((double)units / mine > waves) waves = (double)units / mine;
+        const double cost = waves * ((double)(per_z * zs + halo) + startup);
+        if (best < 0.0 || cost < best - 1e-9) { best = cost; bz = zs; }
+    }
+    return bz;
+}
 
 }  // namespace
