@@ -33,7 +33,9 @@ _SIGS = {
     "atvs_attention_raw": [_p, _i, _p, _i, _ll, _i, _i, _i, _p, _p, _p],
     "atvs_conv2d_fp32": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_channel_moments": [_p, _ll, _i, _p, _p],
-    "atvs_bn2d_apply": [_p, _p, _p, _ll, _i, _f, _i, _p, _p],
+    "atvs_bn2d_apply": [_p, _p, _p, _ll, _i, _f, _i, _p, _i, _p],
+    "atvs_pack_conv2d_weights_tc": [_p, _i, _i, _i, _i, _p, _p],
+    "atvs_conv2d_tc": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "atvs_avg_pool_same": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_resize_bilinear_align": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_transform_depth": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
@@ -43,7 +45,8 @@ _SIGS = {
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
-                                "atvs_packed_weight_bytes", "atvs_launch_count", "atvs_saturation_count"])
+                                "atvs_packed_weight_bytes", "atvs_packed_weight2d_bytes", "atvs_launch_count",
+                                "atvs_saturation_count"])
 
 
 def lib_path():
@@ -68,6 +71,8 @@ def load():
         lib.atvs_packed_weight_bytes.argtypes = [_i, _i, _i]
         lib.atvs_packed_weight_bytes.restype = C.c_size_t
         lib.atvs_launch_count.restype = C.c_longlong
+        lib.atvs_packed_weight2d_bytes.argtypes = [_i, _i, _i]
+        lib.atvs_packed_weight2d_bytes.restype = C.c_size_t
         lib.atvs_saturation_count.argtypes = [_i]
         lib.atvs_saturation_count.restype = C.c_longlong
         _lib = lib

@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int TC_MAX_TAPS = 28;
+constexpr int TC_MAX_TAPS = 48;      // 27 for a 3-D kernel; 2-D: 9 taps x up to 5 chunks of 64 input channels
 constexpr int TC_THREADS = 192;
 
 struct TcTap {
@@ -47,6 +47,8 @@ struct TcParams {
     int raw16;                 // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;              // operand format bits of the instruction descriptor (tc_fmt_bits)
     unsigned long long* sat;   // saturation counter of the fp16 raw stores (atvs_sat_ptr)
+    const float* chan_bias;    // per-channel bias (Cout) added in the epilogue, or NULL (2-D layers of the FEM)
+    int relu;                  // ReLU in the epilogue (after the bias)
     int nstages;
     long long ntiles;
 };
@@ -219,13 +221,14 @@ k_conv3d_tc(const __grid_constant__ TcMaps tm, const __grid_constant__ TcParams 
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * NPAD);
             const size_t o = valid ? ((((size_t)b * p.Do + (jz * p.os + pz)) * p.Ho + (jy * p.os + py)) * p.Wo +
                                       (jx * p.os + px)) * p.Cout + p.coff : 0;
-            const float* brow = nullptr;
+            const float* brow = p.chan_bias != nullptr ? p.chan_bias + p.coff : nullptr;
             if (bias != nullptr && valid) {      // convolutions only (os == 1): plane classes first / interior / last
                 const int zc = (jz == 0) ? 0 : (jz == p.Do - 1 ? 2 : 1);
                 brow = bias + ((((size_t)b * 3 + zc) * p.Ho + jy) * p.Wo + jx) * p.Cout + p.coff;
             }
             epilogue_tile<NPAD>(taddr, &tempty[acc], lane, valid, out, o, p.ncols,
-                                raw_vec_mode(out, p.ncols, p.Cout, p.coff), p.raw16, stats != nullptr, run, brow, p.sat);
+                                raw_vec_mode(out, p.ncols, p.Cout, p.coff), p.raw16, stats != nullptr, run, brow, p.sat,
+                                p.relu != 0);
         }
         if (stats != nullptr) flush_stats<NPAD>(stats, run, lane, p.Cout, p.coff, p.ncols);
     }
@@ -569,6 +572,186 @@ static int conv3d_tc_impl(const void* x_bf16, int x_dtype, const void* wpacked, 
             if (rc) return rc;
         }
         wofs += (size_t)nt * sp.nslabs * sp.npad * Cin;
+    }
+    return 0;
+}
+
+
+// =========================================================================== 2-D convolutions of the FEM on the same kernel
+// tf.layers.conv2d / slim.conv2d (network.py:142-215, 570-599), stride 1, k = 1 | 3, dilation `rate`, TF 'SAME' padding,
+// as the D = 1 case of k_conv3d_tc: the input (B,H,W,Cin) is read through one tensor map per chunk of <= 64 input
+// channels, a "tap" is (chunk, ky, kx) with the TMA box shifted by ((kx-1)*rate, (ky-1)*rate) (zero fill = padding), and
+// all taps' weights of one slab of output channels stay resident in shared memory.  Epilogue: + bias[c], ReLU, raw
+// fp32 | saturated fp16 store, optional per-channel moments (conv_bn layers).
+namespace {
+
+int conv2d_chunk(int Cin) { return Cin % 64 == 0 ? 64 : (Cin == 32 ? 32 : 0); }
+
+// N tile of a 2-D layer: the largest of {64, 32, 16} covering Cout whose resident weights leave room for >= 3 stages
+int conv2d_npad(int Cin, int Cout, int ksize) {
+    const int ck = conv2d_chunk(Cin);
+    const int ntaps = ksize * ksize * (Cin / ck);
+    int npad = Cout <= 16 ? 16 : Cout <= 32 ? 32 : 64;
+    while (npad > 16 && (size_t)ntaps * npad * ck * 2 > 150 * 1024) npad >>= 1;
+    return npad;
+}
+
+// packed image: [slab][tap = (chunk, ky, kx)][NPAD][ck] 16-bit, K-major, from the TF kernel [k,k,Cin,Cout]
+__global__ void k_pack_weights2d(const float* __restrict__ w, int Cin, int Cout, int ksize, int ck, int npad, int f16,
+                                 unsigned short* __restrict__ out) {
+    const int nchunk = Cin / ck, ntaps = ksize * ksize * nchunk;
+    const int slab = blockIdx.x / ntaps, tap = blockIdx.x % ntaps;
+    const int chunk = tap / (ksize * ksize), kk = tap % (ksize * ksize);
+    unsigned short* o = out + ((size_t)slab * ntaps + tap) * npad * ck;
+    for (int i = threadIdx.x; i < npad * ck; i += blockDim.x) {
+        const int n = i / ck, k = i % ck;
+        const int co = slab * npad + n;
+        const float val = co < Cout ? w[((size_t)kk * Cin + chunk * ck + k) * Cout + co] : 0.f;
+        o[i] = tc_cvt16(val, f16);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t atvs_packed_weight2d_bytes(int Cin, int Cout, int ksize) {
+    const int ck = conv2d_chunk(Cin);
+    if (ck == 0 || Cout < 1 || Cout > 256 || !(ksize == 1 || ksize == 3)) return 0;
+    const int npad = conv2d_npad(Cin, Cout, ksize);
+    const int nslabs = (Cout + npad - 1) / npad;
+    return ((size_t)nslabs * ksize * ksize * (Cin / ck) * npad * ck * 2 + 255) & ~(size_t)255;
+}
+
+extern "C" int atvs_pack_conv2d_weights_tc(const float* kernel, int Cin, int Cout, int ksize, int dtype, void* wpacked,
+                                           atvs_stream_t stream) {
+    ATVS_CHECK_ARG(kernel && wpacked, ATVS_E_NULL, "atvs_pack_conv2d_weights_tc: NULL pointer");
+    ATVS_CHECK_ARG(dtype == ATVS_BF16 || dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_pack_conv2d_weights_tc: dtype %d", dtype);
+    ATVS_CHECK_ARG(atvs_packed_weight2d_bytes(Cin, Cout, ksize) != 0, ATVS_E_UNSUP,
+                   "atvs_pack_conv2d_weights_tc: Cin=%d (32 or a multiple of 64) Cout=%d (1..256) k=%d (1 | 3)", Cin, Cout, ksize);
+    const int ck = conv2d_chunk(Cin), npad = conv2d_npad(Cin, Cout, ksize);
+    const int nslabs = (Cout + npad - 1) / npad, ntaps = ksize * ksize * (Cin / ck);
+    k_pack_weights2d<<<nslabs * ntaps, 128, 0, (cudaStream_t)stream>>>(kernel, Cin, Cout, ksize, ck, npad, dtype == ATVS_F16,
+                                                                       (unsigned short*)wpacked);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int atvs_conv2d_tc(const void* x16, int x_dtype, const void* wpacked, const float* bias, int B, int H, int W,
+                              int Cin, int Cout, int ksize, int rate, int relu, void* out, int out_dtype, double* stats,
+                              atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x16 && wpacked && out, ATVS_E_NULL, "atvs_conv2d_tc: NULL pointer");
+    ATVS_CHECK_ARG(x_dtype == ATVS_BF16 || x_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_conv2d_tc: x_dtype %d", x_dtype);
+    ATVS_CHECK_ARG(out_dtype == ATVS_F32 || out_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_conv2d_tc: out_dtype %d (ATVS_F32 | ATVS_F16)", out_dtype);
+    ATVS_CHECK_ARG(B > 0 && H > 0 && W > 0 && rate >= 1, ATVS_E_SHAPE, "atvs_conv2d_tc: bad shape");
+    ATVS_CHECK_ARG(atvs_packed_weight2d_bytes(Cin, Cout, ksize) != 0, ATVS_E_UNSUP,
+                   "atvs_conv2d_tc: Cin=%d (32 or a multiple of 64) Cout=%d (1..256) k=%d (1 | 3)", Cin, Cout, ksize);
+    ATVS_CHECK_ARG((((uintptr_t)x16 | (uintptr_t)wpacked | (uintptr_t)out | (uintptr_t)bias) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_conv2d_tc: buffers must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode();
+    if (!encode) {
+        atvs_set_error("atvs_conv2d_tc: cuTensorMapEncodeTiled entry point not available");
+        return ATVS_E_UNSUP;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ck = conv2d_chunk(Cin), nchunk = Cin / ck;
+    const int npad = conv2d_npad(Cin, Cout, ksize);
+    const int nslabs = (Cout + npad - 1) / npad;
+    const int nt = ksize * ksize * nchunk;
+    ATVS_CHECK_ARG(nt <= TC_MAX_TAPS && nchunk <= 8, ATVS_E_UNSUP, "atvs_conv2d_tc: %d taps (Cin=%d k=%d) exceed %d", nt, Cin,
+                   ksize, TC_MAX_TAPS);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Dj = 1; p.Hj = H; p.Wj = W;
+    p.Do = 1; p.Ho = H; p.Wo = W;
+    p.os = 1;
+    p.Cout = Cout;
+    p.raw16 = out_dtype == ATVS_F16;
+    p.fmt = tc_fmt_bits(x_dtype);
+    p.sat = p.raw16 ? atvs_sat_ptr() : nullptr;
+    p.chan_bias = bias;
+    p.relu = relu;
+    p.ncls = 1;
+    {   // 128-pixel brick: minimise the padded area, prefer wide rows
+        static const int opts[][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}, {32, 4}};
+        long long best = -1;
+        int bi = 0;
+        for (int i = 0; i < (int)(sizeof(opts) / sizeof(opts[0])); ++i) {
+            const long long n = (long long)((H + opts[i][0] - 1) / opts[i][0]) * ((W + opts[i][1] - 1) / opts[i][1]);
+            if (best < 0 || n < best) { best = n; bi = i; }
+        }
+        auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+        p.ltd = 0; p.lth = lg(opts[bi][0]); p.ltw = lg(opts[bi][1]);
+        p.nTD = 1; p.nTH = (H + opts[bi][0] - 1) / opts[bi][0]; p.nTW = (W + opts[bi][1] - 1) / opts[bi][1];
+        p.ntiles = (long long)B * p.nTH * p.nTW;
+    }
+    const int TH = 1 << p.lth, TW = 1 << p.ltw;
+    int n = 0;
+    for (int c = 0; c < nchunk; ++c)
+        for (int ky = 0; ky < ksize; ++ky)
+            for (int kx = 0; kx < ksize; ++kx) {
+                TcTap& t = p.taps[n++];
+                t.map = c; t.oz = 0;
+                t.oy = (ky - ksize / 2) * rate;
+                t.ox = (kx - ksize / 2) * rate;
+            }
+    p.cls_tap0[0] = 0; p.cls_tap0[1] = nt;
+    p.ntaps = nt;
+    const CUtensorMapSwizzle swz = swizzle_for(ck);
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int c = 0; c < nchunk; ++c) {
+        cuuint64_t dims[5] = {(cuuint64_t)ck, (cuuint64_t)W, (cuuint64_t)H, 1, (cuuint64_t)B};
+        cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                                 (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        void* base = (void*)((const char*)x16 + (size_t)c * ck * 2);
+        CUresult r = encode(&maps.a[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            atvs_set_error("atvs_conv2d_tc: cuTensorMapEncodeTiled(input, chunk %d) failed: %d", c, (int)r);
+            return (int)r;
+        }
+    }
+    for (int slab = 0; slab < nslabs; ++slab) {
+        p.coff = slab * npad;
+        p.ncols = (Cout - p.coff < npad) ? Cout - p.coff : npad;
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)ck, (cuuint64_t)nt * npad};
+            cuuint64_t strides[1] = {(cuuint64_t)ck * 2};
+            cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)npad};
+            cuuint32_t es[2] = {1, 1};
+            void* base = (void*)((const char*)wpacked + (size_t)slab * nt * npad * ck * 2);
+            CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                atvs_set_error("atvs_conv2d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+                return (int)r;
+            }
+        }
+        const size_t wbytes = ((size_t)nt * npad * ck * 2 + 1023) & ~(size_t)1023;
+        const size_t stage_bytes = (size_t)128 * ck * 2;
+        const size_t budget = 216 * 1024;
+        if (wbytes + 2 * stage_bytes > budget) {
+            atvs_set_error("atvs_conv2d_tc: weights do not fit in shared memory (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
+            return ATVS_E_UNSUP;
+        }
+        int nst = (int)((budget - wbytes) / stage_bytes);
+        if (nst > 8) nst = 8;
+        if (nst > nt) nst = nt > 2 ? nt : 2;
+        p.nstages = nst;
+        const size_t smem = 1024 + wbytes + (size_t)nst * stage_bytes + (2 * nst + 5) * 8 + 16;
+        const int sms = atvs_num_sms();
+        const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+        int rc = 0;
+        if (ck == 32 && npad == 16) rc = launch_tc<32, 16>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        else if (ck == 32 && npad == 32) rc = launch_tc<32, 32>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        else if (ck == 32 && npad == 64) rc = launch_tc<32, 64>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        else if (ck == 64 && npad == 16) rc = launch_tc<64, 16>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        else if (ck == 64 && npad == 32) rc = launch_tc<64, 32>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        else rc = launch_tc<64, 64>(maps, p, (float*)out, stats, nullptr, smem, grid, st);
+        if (rc) return rc;
     }
     return 0;
 }

@@ -162,9 +162,10 @@ k_channel_moments(const float* __restrict__ x, long long count, int C, double* _
     }
 }
 
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_bn2d_apply(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ beta, long long count,
-             int C, float eps, int relu, float* __restrict__ out) {
+             int C, float eps, int relu, OutT* __restrict__ out) {
     const long long n = count * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -175,7 +176,8 @@ k_bn2d_apply(const float* __restrict__ x, const double* __restrict__ stats, cons
         float y = x[i] * inv - (float)mean * inv;
         if (beta) y += beta[c];
         if (relu) y = fmaxf(y, 0.f);
-        out[i] = y;
+        if (sizeof(OutT) == 2) y = fminf(fmaxf(y, -65504.f), 65504.f);      // fp16 output saturates
+        out[i] = (OutT)y;
     }
 }
 
@@ -302,10 +304,14 @@ extern "C" int atvs_channel_moments(const float* x, long long count, int C, doub
 }
 
 extern "C" int atvs_bn2d_apply(const float* x, const double* stats, const float* beta, long long count, int C, float eps,
-                               int relu, float* out, atvs_stream_t stream) {
+                               int relu, void* out, int out_dtype, atvs_stream_t stream) {
     ATVS_CHECK_ARG(x && stats && out, ATVS_E_NULL, "atvs_bn2d_apply: NULL pointer");
     ATVS_CHECK_ARG(count > 0 && C > 0, ATVS_E_SHAPE, "atvs_bn2d_apply: count=%lld C=%d", count, C);
-    k_bn2d_apply<<<ew_grid(count * C), 256, 0, (cudaStream_t)stream>>>(x, stats, beta, count, C, eps, relu, out);
+    ATVS_CHECK_ARG(out_dtype == ATVS_F32 || out_dtype == ATVS_F16, ATVS_E_DTYPE, "atvs_bn2d_apply: out_dtype %d (ATVS_F32 | ATVS_F16)", out_dtype);
+    if (out_dtype == ATVS_F16)
+        k_bn2d_apply<__half><<<ew_grid(count * C), 256, 0, (cudaStream_t)stream>>>(x, stats, beta, count, C, eps, relu, (__half*)out);
+    else
+        k_bn2d_apply<float><<<ew_grid(count * C), 256, 0, (cudaStream_t)stream>>>(x, stats, beta, count, C, eps, relu, (float*)out);
     ATVS_LAUNCH_CHECK();
     return 0;
 }

@@ -290,7 +290,8 @@ __device__ __forceinline__ void store_raw_row(float* out, size_t off, const floa
 template <int NPAD>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_bar, int lane, bool valid, float* out,
                                               size_t off, int ncols, int vec, int raw16, bool want_stats, float* run,
-                                              const float* bias_row = nullptr, unsigned long long* sat = nullptr) {
+                                              const float* bias_row = nullptr, unsigned long long* sat = nullptr,
+                                              bool relu = false) {
     const bool vec4 = vec >= 4;
     float v[NPAD];
 #pragma unroll
@@ -313,6 +314,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t* tempty_b
             for (int c = 0; c < NPAD; ++c)
                 if (c < ncols) v[c] += __ldg(bias_row + c);
         }
+    }
+    if (relu) {
+#pragma unroll
+        for (int c = 0; c < NPAD; ++c) v[c] = fmaxf(v[c], 0.f);
     }
     if (valid) store_raw_row<NPAD>(out, off, v, ncols, vec, raw16, sat);
     if (want_stats && valid) {

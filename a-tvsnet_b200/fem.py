@@ -9,8 +9,51 @@ import torch
 
 from . import _lib as L
 from . import variables as V
+from .flags import FLAGS
 
 BN_EPS = 1e-3
+
+
+def tensor_path():
+    """the stride-1 convolutions run on the tcgen05 kernel (fp16 operands, fp32 accumulation) when asked to
+    (FLAGS.fem_tensor, opt-in: see flags.py for the accuracy it costs) and the hot path is in fp16."""
+    return FLAGS.precision == 'fp16' and getattr(FLAGS, 'fem_tensor', False)
+
+
+def _packed2d(kernel):
+    cache = V.packed_cache()
+    key = ('fem2d', kernel.data_ptr(), tuple(kernel.shape))
+    if key not in cache:
+        k, _, cin, cout = kernel.shape
+        buf = torch.empty(L.load().atvs_packed_weight2d_bytes(cin, cout, k), dtype=torch.uint8, device=kernel.device)
+        L.call("atvs_pack_conv2d_weights_tc", L.ptr(kernel), cin, cout, k, L.F16, L.ptr(buf), L.stream())
+        cache[key] = buf
+    return cache[key]
+
+
+def tc_supported(x, kernel, stride, explicit_pad):
+    cin, cout = kernel.shape[2], kernel.shape[3]
+    return (stride == 1 and explicit_pad is None and kernel.shape[0] in (1, 3) and (cin == 32 or cin % 64 == 0)
+            and cin <= 320 and cout <= 256 and x.shape[1] * x.shape[2] >= 128)
+
+
+def conv2d_tc(x, kernel, rate=1, bias=None, relu=False, out_dtype=torch.float32, stats=None):
+    """stride-1 'SAME' convolution on the tensor cores: x (B,H,W,Cin) fp16 -> (B,H,W,Cout) fp32 | fp16
+    = [relu](conv + bias); ``stats`` (2*Cout fp64, zeroed) receives the per-channel moments (conv_bn layers)."""
+    B, H, W, cin = x.shape
+    k, cout = kernel.shape[0], kernel.shape[-1]
+    out = torch.empty((B, H, W, cout), dtype=out_dtype, device=x.device)
+    L.call("atvs_conv2d_tc", L.ptr(x), L.F16, L.ptr(_packed2d(kernel)), L.ptr(bias), B, H, W, cin, cout, k, rate, int(relu),
+           L.ptr(out), L.F16 if out_dtype == torch.float16 else L.F32, L.ptr(stats), L.stream())
+    return out
+
+
+def to_half(x):
+    if x.dtype == torch.float16:
+        return x
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    L.call("atvs_cast", L.ptr(x), L.F32, L.ptr(out), L.F16, x.numel(), L.stream())
+    return out
 
 
 def _same_pad(n, k_eff, s):
@@ -23,6 +66,8 @@ def conv2d(x, kernel, stride=1, rate=1, bias=None, relu=False, padding='SAME', e
     """x (B,H,W,Cin) fp32 cuda, kernel [k,k,Cin,Cout].  padding 'SAME' (TF) or 'VALID' after ``explicit_pad`` =
     (begin, end) zero rows/cols on both axes (the bottleneck's tf.pad + VALID, network.py:589-595)."""
     L.require_cuda(x, kernel)
+    if tensor_path() and tc_supported(x, kernel, stride, explicit_pad) and padding == 'SAME':
+        return conv2d_tc(to_half(x.contiguous()), kernel, rate, bias, relu)
     x = L.f32c(x)
     B, H, W, cin = x.shape
     k, cout = kernel.shape[0], kernel.shape[-1]
@@ -44,20 +89,29 @@ def conv2d(x, kernel, stride=1, rate=1, bias=None, relu=False, padding='SAME', e
     return out
 
 
-def batch_norm(x, beta=None, relu=False):
-    """batch statistics over (B,H,W), biased variance, eps 1e-3, optional ``+ beta``, optional ReLU."""
+def batch_norm(x, beta=None, relu=False, stats=None, out_dtype=torch.float32):
+    """batch statistics over (B,H,W), biased variance, eps 1e-3, optional ``+ beta``, optional ReLU.  ``stats``: moments
+    already accumulated by the producing convolution's epilogue; ``out_dtype`` fp16 feeds a tensor-core convolution."""
+    x = L.f32c(x)
     C = x.shape[-1]
     count = x.numel() // C
-    stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
-    L.call("atvs_channel_moments", L.ptr(x), count, C, L.ptr(stats), L.stream())
-    out = torch.empty_like(x)
-    L.call("atvs_bn2d_apply", L.ptr(x), L.ptr(stats), L.ptr(beta), count, C, BN_EPS, int(relu), L.ptr(out), L.stream())
+    if stats is None:
+        stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        L.call("atvs_channel_moments", L.ptr(x), count, C, L.ptr(stats), L.stream())
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    L.call("atvs_bn2d_apply", L.ptr(x), L.ptr(stats), L.ptr(beta), count, C, BN_EPS, int(relu), L.ptr(out),
+           L.F16 if out_dtype == torch.float16 else L.F32, L.stream())
     return out
 
 
-def conv_bn(x, name, stride=1, rate=1):
+def conv_bn(x, name, stride=1, rate=1, out_dtype=torch.float32):
     """network.py:173-215 on a 4-D tensor: name/conv2d/kernel, BN without affine, ReLU."""
-    return batch_norm(conv2d(x, V.get_variable(name + '/conv2d/kernel'), stride, rate), None, True)
+    kernel = V.get_variable(name + '/conv2d/kernel')
+    if tensor_path() and tc_supported(x, kernel, stride, None):
+        stats = torch.zeros(2 * kernel.shape[-1], dtype=torch.float64, device=x.device)
+        raw = conv2d_tc(to_half(x.contiguous()), kernel, rate, stats=stats)        # moments from the fp32 accumulators
+        return batch_norm(raw, None, True, stats=stats, out_dtype=out_dtype)
+    return batch_norm(conv2d(x, kernel, stride, rate), None, True, out_dtype=out_dtype)
 
 
 def add(a, b):
@@ -74,6 +128,15 @@ def bottleneck(x, scope, depth, stride=1, rate=1):
     """network.py:552-603."""
     g = V.get_variable
     depth_in = x.shape[-1]
+    if tensor_path() and stride == 1 and (depth_in == 32 or depth_in % 64 == 0) and x.shape[1] * x.shape[2] >= 128:
+        # tensor-core bottleneck: the residual stream x stays fp32, everything a convolution reads is fp16
+        preact = batch_norm(x, g(scope + '/preact/beta'), True, out_dtype=torch.float16)
+        shortcut = x if depth == depth_in else conv2d_tc(preact, g(scope + '/shortcut/weights'), 1,
+                                                         g(scope + '/shortcut/biases'))
+        r = conv2d_tc(preact, g(scope + '/conv1/weights'), 1, g(scope + '/conv1/biases'), True, torch.float16)
+        r = conv2d_tc(r, g(scope + '/conv2/weights'), rate, g(scope + '/conv2/biases'), True, torch.float16)
+        r = conv2d_tc(r, g(scope + '/conv3/weights'), 1, g(scope + '/conv3/biases'))
+        return add(shortcut, r)
     preact = batch_norm(x, g(scope + '/preact/beta'), True)
     if depth == depth_in:
         shortcut = x if stride == 1 else x[:, ::stride, ::stride, :].contiguous()

@@ -22,6 +22,11 @@ class _Flags(object):
         self.precision = DEFAULT_PRECISION
         # tensor-core path: dtype of the raw (pre-BN) convolution outputs, 'f16' (saturated) or 'f32'
         self.raw_dtype = 'f16'
+        # 2-D feature extractor: run its stride-1 convolutions on the tensor cores (fp16 operands, fp32 residual stream
+        # and statistics; needs precision == 'fp16').  OFF by default: 5 x faster FEM (7.0 -> 2.1 ms per 640x512 image)
+        # but ~50 layers of 11-bit operand rounding put 0.6 % of error on the features, which moves the depth map by
+        # 0.09 - 0.24 % of the range (tools/fem_accuracy.py) - outside the 0.1 % bound the fp32 FEM keeps (0.015 - 0.03 %)
+        self.fem_tensor = False
         # ... and of the layers fed by the UN-normalised cost volume (conv_b0_0_1 / conv_b0_1_0), whose magnitude
         # follows the checkpoint's feature scale: fp16 as well, guarded by the epilogues' saturation counter
         # (atvs_saturation_count, pipeline.check_saturation): a clamped value is detected, never silent; set 'f32'

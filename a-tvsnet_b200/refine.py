@@ -1,11 +1,12 @@
-"""Refinement stage (stage III of /root/reference/atvsnet/example.py:160-172) on torch CUDA tensors, fp32 first path:
+"""Refinement stage (stage III of /root/reference/atvsnet/example.py:160-172) on torch CUDA tensors:
 /root/reference/atvsnet/homography_warping.py:275-326 (transform_depth), :329-387 (get_visual_hull),
 /root/reference/atvsnet/model.py:143-154 (extract_feature_shallow), :227-339 (refinement), :428-441 (TVSNet_refine),
 /root/reference/cnn_wrapper/atvsnet.py:245-251 (ResNetDS2SPP_shallow_f16), :295-336 (CostVolRefineNet).
 
 Geometry through the C ABI (csrc/geom.cu: atvs_transform_depth, atvs_refine_geo_group, atvs_refine_photo_group,
-atvs_visual_hull, plus the existing by-depth warps and the L1_MASKED mode of K1); the refinement U-Net runs on the fp32
-convolution / BN primitives (the bf16 tensor kernels do not cover its 48 / 19 / 1 input channels yet).  Checked against
+atvs_visual_hull, plus the existing by-depth warps and the L1_MASKED mode of K1); the refinement U-Net
+(CostVolRefineNet) runs on the tensor-core kernels when FLAGS.precision is 16-bit (its 48 / 19 / 1 / 1-channel input
+groups zero-padded to 64 / 32 / 8 / 8) and on the fp32 CUDA-core primitives otherwise.  Checked against
 oracle/refine.py and the reference-function golden vectors (tests/test_gpu_refine.py)."""
 import torch
 
@@ -62,23 +63,63 @@ def extract_feature_shallow(images, ref_id=0, view_id=1):
     return shallow_features(images[:, ref_id]), shallow_features(images[:, view_id])
 
 
-def _conv_bn(x, name, stride=1, transposed=False):
-    key = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
-    w = V.get_variable(key)
-    cout = w.shape[-2] if transposed else w.shape[-1]
-    raw, stats = N.conv3d_raw(x, key, w, cout, stride, transposed, True)
-    out, _ = N.bn_relu_add(raw, stats, True, [], True, False, torch.float32)
+def _pad_channels(x, cpad, dt):
+    """(B,D,h,w,C) fp32 -> (B,D,h,w,cpad) in the activation dtype, extra channels zero: the tensor-core kernels take
+    8 / 16 / 32 / 64 input channels, the refinement groups have 48 / 19 / 1 / 1 (model.py:328-333)."""
+    B, D, h, w, C = x.shape
+    if C == cpad:
+        return N.to_dtype(x.contiguous(), dt)
+    out = torch.zeros((B, D, h, w, cpad), dtype=dt, device=x.device)
+    out[..., :C] = x
     return out
 
 
+def _padded_kernel(key, cpad):
+    """kernel [3,3,3,Cin,Cout] zero-padded on Cin to ``cpad`` (cached next to the packed weight images)."""
+    w = V.get_variable(key)
+    if w.shape[-2] == cpad:
+        return key, w
+    cache = V.packed_cache()
+    k = key + '/cin%d' % cpad
+    if k not in cache:
+        wp = torch.zeros(tuple(w.shape[:3]) + (cpad, w.shape[-1]), dtype=w.dtype, device=w.device)
+        wp[..., :w.shape[-2], :] = w
+        cache[k] = wp
+    return k, cache[k]
+
+
+def _cin_pad(c):
+    return 8 if c <= 8 else 16 if c <= 16 else 32 if c <= 32 else 64
+
+
+def _conv_bn(x, name, stride=1, transposed=False, skips=()):
+    """conv_bn / deconv_bn (network.py:173-215, 511-550) + the following `add` of ``skips`` (network.py:696), in the
+    dtype of ``x``: fp32 -> CUDA-core parity path, fp16 / bf16 -> tcgen05 path (fp16 raw output, fused BN + ReLU + add)."""
+    key = name + ('/conv3d_transpose/kernel' if transposed else '/conv3d/kernel')
+    w = V.get_variable(key)
+    cout = w.shape[-2] if transposed else w.shape[-1]
+    if x.dtype in N.HALF_DTYPES and not transposed:
+        key, w = _padded_kernel(key, x.shape[-1])
+    raw, stats = N.conv3d_raw(x, key, w, cout, stride, transposed, True, raw_dtype=N.raw_dtype_for_bn(x))
+    plain, summ = N.bn_relu_add(raw, stats, True, list(skips), not skips, bool(skips), x.dtype)
+    return summ if skips else plain
+
+
 def CostVolRefineNet(photo_group, geo_group, prob_vol, vis_hull):
-    """cnn_wrapper/atvsnet.py:295-336 -> (global_refine_3dconv6_1 (B,D,H,W,8), global_refined_cost_vol (B,D,H,W,1))."""
+    """cnn_wrapper/atvsnet.py:295-336 -> (global_refine_3dconv6_1 (B,D,H,W,8), global_refined_cost_vol (B,D,H,W,1)), fp32
+    at the interface.  With FLAGS.precision = 'fp16' | 'bf16' the U-Net runs on the tensor-core kernels (input groups
+    zero-padded to 64 / 32 / 8 / 8 channels), with 'fp32' on the CUDA-core parity path."""
     p = 'global_refine_'
     if any(int(n) % 8 for n in photo_group.shape[1:4]):
         raise ValueError("CostVolRefineNet: D, h, w must be multiples of 8 (three stride-2 levels joined by `add`), got %s"
                          % (tuple(photo_group.shape[1:4]),))
-    cat = torch.cat([_conv_bn(photo_group, p + 'photo_3dconv'), _conv_bn(geo_group, p + 'geo_3dconv'),
-                     _conv_bn(prob_vol, p + 'prob_3dconv'), _conv_bn(vis_hull, p + 'vishull_3dconv')], dim=-1).contiguous()
+    dt = N.act_dtype()
+    if dt in N.HALF_DTYPES:
+        groups = [_pad_channels(g, _cin_pad(g.shape[-1]), dt) for g in (photo_group, geo_group, prob_vol, vis_hull)]
+    else:
+        groups = [photo_group, geo_group, prob_vol, vis_hull]
+    heads = [_conv_bn(g, p + n) for g, n in zip(groups, ('photo_3dconv', 'geo_3dconv', 'prob_3dconv', 'vishull_3dconv'))]
+    cat = torch.cat(heads, dim=-1).contiguous()
     c10 = _conv_bn(cat, p + '3dconv1_0', 2)
     c20 = _conv_bn(c10, p + '3dconv2_0', 2)
     c30 = _conv_bn(c20, p + '3dconv3_0', 2)
@@ -86,12 +127,12 @@ def CostVolRefineNet(photo_group, geo_group, prob_vol, vis_hull):
     c11 = _conv_bn(c10, p + '3dconv1_1')
     c21 = _conv_bn(c20, p + '3dconv2_1')
     c31 = _conv_bn(c30, p + '3dconv3_1')
-    c41 = fem.add(_conv_bn(c31, p + '3dconv4_0', 2, True), c21)
-    c51 = fem.add(_conv_bn(c41, p + '3dconv5_0', 2, True), c11)
-    c61 = fem.add(_conv_bn(c51, p + '3dconv6_0', 2, True), c01)
+    c41 = _conv_bn(c31, p + '3dconv4_0', 2, True, skips=(c21,))
+    c51 = _conv_bn(c41, p + '3dconv5_0', 2, True, skips=(c11,))
+    c61 = _conv_bn(c51, p + '3dconv6_0', 2, True, skips=(c01,))
     wk = V.get_variable('global_refined_cost_vol/kernel')
     res, _ = N.conv3d_raw(c61, 'global_refined_cost_vol/kernel', wk, 1, 1, False, False)
-    return c61, res
+    return N.to_dtype(c61, torch.float32), res
 
 
 def refinement(init_depth_images, cams, depth_num, depth_start, depth_interval, images, prob_vol, ref_id, view_id,

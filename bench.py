@@ -334,14 +334,17 @@ def run_ours(args, rank, world, local_rank):
         def step_four():
             return A.pipeline.run_example_schedule(imgs_d, cams_d, D)['depth_refined_up']
 
-        for name, fn, what in (("from_images", step_images, "IMAGES in: 2-D feature extractor (ResNetDS2SPP) on the 5 views + stages I + II + x4 soft-argmin"),
-                               ("four_stage", step_four, "IMAGES in: the whole example.py:144-181 schedule (FEM, stages I-IV with refinement)")):
+        for name, fn, what in (("from_images", step_images, "IMAGES in: 2-D feature extractor (ResNetDS2SPP, fp32 CUDA-core path: the parity default) on the 5 views + stages I + II + x4 soft-argmin"),
+                               ("four_stage", step_four, "IMAGES in: the whole example.py:144-181 schedule (FEM, stages I-IV with refinement)"),
+                               ("from_images_tensor_fem", step_images, "as from_images with FLAGS.fem_tensor = True: the FEM's stride-1 convolutions on tcgen05 (fp16 operands); opt-in, costs 0.09-0.24 % of the depth range in accuracy (tools/fem_accuracy.py)"),
+                               ("four_stage_tensor_fem", step_four, "as four_stage with FLAGS.fem_tensor = True")):
+            A.FLAGS.fem_tensor = name.endswith("tensor_fem")
             try:
                 for _ in range(2):
                     o = fn()
                 torch.cuda.synchronize()
                 k = max(3, min(args.steps, 10))
-                graphed = name == "from_images" and not args.no_graph
+                graphed = name.startswith("from_images") and not args.no_graph
                 if graphed:
                     g, o = capture(fn, torch)
                     ms, _ = timed_steps(lambda: g.replay(), k, torch, barrier)
@@ -351,7 +354,9 @@ def run_ours(args, rank, world, local_rank):
                 extras[name] = {"what": what, "ms_per_step": ms / k, "value": k / (ms * 1e-3), "unit": "depth maps/s",
                                 "steps": k, "cuda_graph": graphed, "finite": bool(torch.isfinite(o).all())}
                 del o
+                A.FLAGS.fem_tensor = False
             except Exception as e:       # an extra must never take the headline line down with it
+                A.FLAGS.fem_tensor = False
                 extras[name] = {"what": what, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
                 torch.cuda.synchronize()
         del imgs_d

@@ -163,7 +163,8 @@ int atvs_attention_raw(const void* act_raw, int act_dtype /* ATVS_F32 | ATVS_F16
                        atvs_stream_t stream);
 
 /* ---- 2-D feature extraction module (FEM, ResNetDS2SPP) --- cnn_wrapper/atvsnet.py:254-292, network.py:142-215, 552-671
- * fp32 NHWC CUDA-core parity path of SURVEY.md 8(f) row N1 (the tensor-core version is not built yet).
+ * fp32 NHWC CUDA-core parity path of SURVEY.md 8(f) row N1; atvs_conv2d_tc below is the tensor-core path of its
+ * stride-1 convolutions.
  * atvs_conv2d_fp32: kernel [k,k,Cin,Cout] (TF layout), k = 1 | 3, stride, dilation `rate`, explicit zero padding
  *   pad_top / pad_left (bottom / right follow from Ho, Wo): TF 'SAME' and the bottleneck's pad + 'VALID'
  *   (network.py:589-595) are both expressed this way; out (B,Ho,Wo,Cout) = [relu](conv + bias), bias may be NULL.
@@ -177,11 +178,25 @@ int atvs_conv2d_fp32(const float* x, const float* kernel, const float* bias, int
                      int relu, float* out, atvs_stream_t stream);
 int atvs_channel_moments(const float* x, long long count, int C, double* stats, atvs_stream_t stream);
 int atvs_bn2d_apply(const float* x, const double* stats, const float* beta, long long count, int C, float eps,
-                    int relu, float* out, atvs_stream_t stream);
+                    int relu, void* out, int out_dtype /* ATVS_F32 | ATVS_F16 (saturated) */, atvs_stream_t stream);
 int atvs_avg_pool_same(const float* x, int B, int H, int W, int C, int ksize, int stride, float* out,
                        atvs_stream_t stream);
 int atvs_resize_bilinear_align(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out,
                                atvs_stream_t stream);
+
+/* ---- 2-D convolutions of the FEM on tcgen05 -------------- network.py:142-215 (conv, conv_bn), 570-599 (slim.conv2d)
+ * stride 1, k = 1 | 3, dilation `rate`, TF 'SAME' padding, as the D = 1 case of the 3-D implicit-GEMM kernel: x16
+ * (B,H,W,Cin) ATVS_F16 | ATVS_BF16 with Cin = 32 or a multiple of 64 (read through one TMA map per 64-channel chunk);
+ * wpacked from atvs_pack_conv2d_weights_tc (kernel [k,k,Cin,Cout] f32, atvs_packed_weight2d_bytes bytes, Cout <= 256);
+ * out (B,H,W,Cout) = [relu](conv + bias[c]) stored as out_dtype = ATVS_F32 | ATVS_F16 (saturated); bias may be NULL;
+ * stats (2*Cout doubles, caller zeroes) receives the per-channel moments of the stored value's fp32 source when not
+ * NULL (the conv_bn layers).  Stride-2 / 3-channel layers stay on atvs_conv2d_fp32.                              */
+size_t atvs_packed_weight2d_bytes(int Cin, int Cout, int ksize);
+int atvs_pack_conv2d_weights_tc(const float* kernel, int Cin, int Cout, int ksize, int dtype, void* wpacked,
+                                atvs_stream_t stream);
+int atvs_conv2d_tc(const void* x16, int x_dtype, const void* wpacked, const float* bias, int B, int H, int W, int Cin,
+                   int Cout, int ksize, int rate, int relu, void* out, int out_dtype, double* stats,
+                   atvs_stream_t stream);
 
 /* ---- refinement-stage geometry (stage III) ----- homography_warping.py:275-387, model.py:269-337
  * fp32 first path.  atvs_transform_depth: depth (B,H,W) of the left view re-expressed in the right camera, on the left

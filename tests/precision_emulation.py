@@ -108,7 +108,41 @@ class EmuUNet(onet.StackedUNet_prob):
         return self._done(name, out)
 
 
-def emu_stage12(features, cams, depth_num, weights, emu, split_first_layer=True):
+def warp_half_arith(src16, H):
+    """bilinear warp of a (1,h,w,C) feature map (values already on the fp16 grid) with the BLEND evaluated in fp16
+    arithmetic, as a packed-half (HFMA2) K1 would: weights rounded to fp16, out = fma(wd, d, fma(wc, c, fma(wb, b, wa*a)))
+    with every step rounded to fp16 (numpy float16 rounds after the multiply AND after the add: an upper bound on the
+    single rounding of a hardware fma).  Coordinates / validity exactly as oracle.homography_warping (fp32)."""
+    f = np.float32
+    _, h, w, C = src16.shape
+    Hm = np.asarray(H, dtype=f)[0]
+    xs, ys = np.meshgrid(np.arange(w, dtype=f) + f(0.5), np.arange(h, dtype=f) + f(0.5))
+    xa = (Hm[0, 0] * xs + Hm[0, 1] * ys) + Hm[0, 2]
+    ya = (Hm[1, 0] * xs + Hm[1, 1] * ys) + Hm[1, 2]
+    z = (Hm[2, 0] * xs + Hm[2, 1] * ys) + Hm[2, 2]
+    z = z + f(1e-7) * (z == 0)
+    with np.errstate(all='ignore'):
+        u = xa / z - f(0.5)
+        v = ya / z - f(0.5)
+        valid = (u >= 0) & (v >= 0) & (u < f(w - 1)) & (v < f(h - 1)) & ~np.isnan(u) & ~np.isnan(v)
+    u = np.where(valid, u, 0).astype(f)
+    v = np.where(valid, v, 0).astype(f)
+    x0 = np.floor(u).astype(np.int64)
+    y0 = np.floor(v).astype(np.int64)
+    x1, y1 = np.minimum(x0 + 1, w - 1), np.minimum(y0 + 1, h - 1)
+    fx1, fy1 = (x0 + 1).astype(f), (y0 + 1).astype(f)
+    wa = ((fy1 - v) * (fx1 - u)).astype(np.float16)[..., None]
+    wb = ((fy1 - v) * (u - x0.astype(f))).astype(np.float16)[..., None]
+    wc = ((v - y0.astype(f)) * (fx1 - u)).astype(np.float16)[..., None]
+    wd = ((v - y0.astype(f)) * (u - x0.astype(f))).astype(np.float16)[..., None]
+    img = src16[0].astype(np.float16)
+    a, b, c, d = img[y0, x0], img[y0, x1], img[y1, x0], img[y1, x1]
+    out = wd * d + (wc * c + (wb * b + wa * a))
+    out = np.where(valid[..., None], out, np.float16(0))
+    return out.astype(f)[None]
+
+
+def emu_stage12(features, cams, depth_num, weights, emu, split_first_layer=True, k1_half_arith=False):
     """oracle.model.run_multiview_stage12 (siamese=False) with the storage roundings of ``emu``."""
     cams = np.asarray(cams, dtype=F32)
     features = np.asarray(features, dtype=F32)
@@ -118,7 +152,10 @@ def emu_stage12(features, cams, depth_num, weights, emu, split_first_layer=True)
     for v in range(1, N):
         hs = get_homographies(cams[:, 0], cams[:, v], depth_num, ds, di, True)
         src = emu.qa(features[:, v])
-        warped = np.stack([homography_warping(src, hs[:, d]) for d in range(depth_num)], axis=1)
+        if k1_half_arith:
+            warped = np.stack([warp_half_arith(src, hs[:, d])[0] for d in range(depth_num)], axis=0)[None]
+        else:
+            warped = np.stack([homography_warping(src, hs[:, d]) for d in range(depth_num)], axis=1)
         warped = emu.qa(warped)
         ref = emu.qa(features[:, 0])
         cv = np.concatenate([np.tile(ref[:, None], (1, depth_num, 1, 1, 1)), warped], axis=-1)
@@ -169,6 +206,9 @@ def main(argv):
         out = emu_stage12(feats, cams, D, weights, Emu(act, raw))
         print("  act=%-4s raw=%-3s  depth_up MAE/range = %.4e" % (
             act, raw, depth_mae_over_range(out['depth_up'], ref['depth_agg_init_up'], cams, D)), flush=True)
+    out = emu_stage12(feats, cams, D, weights, Emu('f16', 'f16'), k1_half_arith=True)
+    print("  act=f16  raw=f16 + K1 blend in fp16 arithmetic  depth_up MAE/range = %.4e" % (
+        depth_mae_over_range(out['depth_up'], ref['depth_agg_init_up'], cams, D)), flush=True)
 
 
 if __name__ == '__main__':

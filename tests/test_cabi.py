@@ -57,7 +57,11 @@ def test_argument_errors_without_gpu(lib):
     assert lib.atvs_cast(p, 2, p, 1, 8, None) == -2                                                      # fp16 -> bf16: via fp32
     assert lib.atvs_conv2d_fp32(p, p, None, 1, 8, 8, 4, 8, 5, 1, 1, 2, 2, 8, 8, 0, p, None) == -5        # kernel size 5
     assert lib.atvs_conv2d_fp32(None, p, None, 1, 8, 8, 4, 8, 3, 1, 1, 1, 1, 8, 8, 0, p, None) == -4
-    assert lib.atvs_channel_moments(p, 0, 8, p, None) == -1 and lib.atvs_bn2d_apply(p, None, None, 4, 8, 1e-3, 0, p, None) == -4
+    assert lib.atvs_channel_moments(p, 0, 8, p, None) == -1 and lib.atvs_bn2d_apply(p, None, None, 4, 8, 1e-3, 0, p, 0, None) == -4
+    assert lib.atvs_bn2d_apply(p, p, None, 4, 8, 1e-3, 0, p, 1, None) == -2                              # fp32 | fp16 output
+    assert lib.atvs_conv2d_tc(p, 2, p, None, 1, 8, 8, 48, 32, 3, 1, 0, p, 0, None, None) == -5           # Cin 32 | 64k
+    assert lib.atvs_conv2d_tc(p, 0, p, None, 1, 8, 8, 64, 32, 3, 1, 0, p, 0, None, None) == -2           # 16-bit operands
+    assert lib.atvs_packed_weight2d_bytes(128, 128, 3) == 4 * 18 * 32 * 64 * 2 and lib.atvs_packed_weight2d_bytes(48, 8, 3) == 0
     assert lib.atvs_avg_pool_same(p, 1, 8, 8, 4, 0, 1, p, None) == -1
     assert lib.atvs_resize_bilinear_align(p, 1, 8, 8, 4, 0, 4, p, None) == -1
     assert lib.atvs_transform_depth(p, p, None, 1, 4, 4, 1, p, None) == -4

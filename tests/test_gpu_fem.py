@@ -28,6 +28,22 @@ def A():
     return A_
 
 
+@pytest.fixture
+def fp32_path(A):
+    """the fp32 CUDA-core parity path of the FEM (the default precision 'fp16' routes the stride-1 convolutions to the
+    tensor cores)."""
+    A.FLAGS.precision = 'fp32'
+    yield
+    A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+
+
+@pytest.fixture
+def tensor_fem(A):
+    A.FLAGS.fem_tensor = True
+    yield
+    A.FLAGS.fem_tensor = False
+
+
 CONV_CASES = [  # cin, cout, k, stride, rate, mode, shape(H, W)
     (3, 32, 3, 2, 1, 'same', (30, 44)), (32, 32, 3, 1, 1, 'same', (17, 23)), (32, 64, 1, 2, 1, 'same', (16, 24)),
     (64, 64, 3, 2, 1, 'explicit', (16, 24)), (128, 128, 3, 1, 2, 'same', (12, 20)), (128, 128, 3, 1, 4, 'same', (9, 33)),
@@ -36,7 +52,7 @@ CONV_CASES = [  # cin, cout, k, stride, rate, mode, shape(H, W)
 
 
 @pytest.mark.parametrize('cin,cout,k,stride,rate,mode,hw', CONV_CASES)
-def test_conv2d_fp32(A, cin, cout, k, stride, rate, mode, hw):
+def test_conv2d_fp32(A, fp32_path, cin, cout, k, stride, rate, mode, hw):
     from oracle import fem as ofem
     rng = np.random.default_rng(cin * 7 + cout)
     x = rng.standard_normal((2,) + hw + (cin,)).astype(np.float32)
@@ -55,7 +71,7 @@ def test_conv2d_fp32(A, cin, cout, k, stride, rate, mode, hw):
     assert rel(got_r.cpu().numpy(), ref_r) < 2e-5
 
 
-def test_bn_pool_resize(A):
+def test_bn_pool_resize(A, fp32_path):
     from oracle import fem as ofem
     rng = np.random.default_rng(5)
     for C in (32, 64, 128, 20):
@@ -71,7 +87,60 @@ def test_bn_pool_resize(A):
         assert rel(A.fem.image_resize(cu(s), ho, wo).cpu().numpy(), ofem.resize_bilinear_align(s, ho, wo)) < 1e-6
 
 
-def test_resnet_ds2_spp_matches_reference_graph_golden(A):
+TC2D_CASES = [  # cin, cout, k, rate, (H, W)
+    (32, 32, 3, 1, (40, 56)), (32, 32, 1, 1, (17, 23)), (32, 64, 1, 1, (16, 24)), (64, 64, 3, 1, (24, 40)),
+    (64, 128, 1, 1, (12, 20)), (128, 128, 3, 2, (12, 20)), (128, 128, 3, 4, (9, 33)), (128, 128, 1, 1, (32, 40)),
+    (320, 128, 3, 1, (16, 24)), (128, 32, 1, 1, (8, 40)), (64, 64, 3, 1, (128, 160))]
+
+
+@pytest.mark.parametrize('cin,cout,k,rate,hw', TC2D_CASES)
+def test_conv2d_tensor_core(A, tensor_fem, cin, cout, k, rate, hw):
+    """the FEM's stride-1 convolutions on tcgen05 (atvs_conv2d_tc: channel-chunked taps, dilation, bias / ReLU epilogue,
+    fp32 | fp16 output, moments) against the oracle conv2d on fp16-rounded operands."""
+    from oracle import fem as ofem
+    rng = np.random.default_rng(cin * 5 + cout + k + rate)
+    x = rng.standard_normal((2,) + hw + (cin,)).astype(np.float32)
+    w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    xh = torch.from_numpy(x).half()
+    wh = torch.from_numpy(w).half().float()
+    ref = ofem.conv2d(xh.float().numpy(), wh.numpy(), 1, rate, 'SAME', b)
+    A.variables.packed_cache().clear()
+    assert A.fem.tc_supported(xh, wh, 1, None)
+    got = A.fem.conv2d_tc(xh.cuda(), wh.cuda(), rate, cu(b))
+    assert tuple(got.shape) == ref.shape and got.dtype == torch.float32
+    assert rel(got.cpu().numpy(), ref) < 1e-4
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
+    got_r = A.fem.conv2d_tc(xh.cuda(), wh.cuda(), rate, cu(b), relu=True, out_dtype=torch.float16, stats=stats)
+    ref_r = np.maximum(ref, 0)
+    assert got_r.dtype == torch.float16
+    assert np.abs(got_r.float().cpu().numpy() - ref_r).max() <= 2.0 ** -10 * np.abs(ref_r).max()
+    flat = ref_r.reshape(-1, cout).astype(np.float64)
+    st = stats.cpu().numpy()
+    assert np.allclose(st[:cout], flat.sum(0), rtol=1e-3, atol=5e-2) and np.allclose(st[cout:], (flat ** 2).sum(0), rtol=1e-3, atol=5e-2)
+    nob = A.fem.conv2d_tc(xh.cuda(), wh.cuda(), rate)
+    assert rel(nob.cpu().numpy(), ref - b) < 1e-4
+
+
+def test_resnet_ds2_spp_tensor_path_vs_golden(A, tensor_fem):
+    """whole FEM with the stride-1 convolutions on the tensor cores (fp16 operands, fp32 residual stream and batch
+    statistics) against the reference-graph golden vectors: ~40 layers of 11-bit operand rounding."""
+    from gen_common import fem_weights
+    gold = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_golden_fem.npz')))
+    A.variables.load_weights(fem_weights(7))
+    assert A.fem.tensor_path()
+    out, layers = A.fem.ResNetDS2SPP(cu(gold['image']), return_layers=True)
+    torch.cuda.synchronize()
+    errs = {nm: rel(layers[nm].cpu().numpy(), gold[nm]) for nm in ('conv0_2', 'conv0_x', 'conv1_x', 'conv2_x', 'conv3_x', 'fusion0')}
+    errs['feature'] = rel(out.cpu().numpy(), gold['feature'])
+    print("FEM tensor path, max rel err per layer:", {k: "%.2e" % v for k, v in errs.items()})
+    assert max(errs.values()) < 1e-2, errs
+    mean_rel = float(np.abs(out.cpu().numpy() - gold['feature']).mean() / np.abs(gold['feature']).mean())
+    print("FEM tensor path: mean |err| / mean |feature| = %.2e" % mean_rel)
+    assert mean_rel < 1.5e-2
+
+
+def test_resnet_ds2_spp_matches_reference_graph_golden(A, fp32_path):
     from gen_common import fem_weights
     gold = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_golden_fem.npz')))
     A.variables.load_weights(fem_weights(7))

@@ -468,7 +468,10 @@ def test_build_cost_volume_bf16_source(A, half):
         else:       # fp32 CUDA path of the same mode (itself checked against the oracle elsewhere)
             ref = npy(A.build_cost_volume(cu(feats[:, 0]), cu(fr[:, 2]), cu(cams), D, cu(ds), cu(di), 0, 2, mode=mode))
         got = npy(out.float())
-        assert np.abs(got - ref).max() <= HALF_EPS[half] * np.abs(ref).max() + 1e-6, mode
+        # bf16: fp32 blend, one rounding.  fp16: the blend itself runs in packed-half arithmetic (4 products + 3 fused
+        # adds on fp16-rounded weights), a few fp16 roundings of the largest term
+        k = 1.0 if half == torch.bfloat16 or mode == 'l1_masked' else 4.0
+        assert np.abs(got - ref).max() <= k * HALF_EPS[half] * np.abs(ref).max() + 1e-6, mode
 
 
 def test_conv3d_argument_errors(A):
