@@ -12,4 +12,4 @@ from .atvsnet import (AttAggregation, AttAggregation_keepchannel, AttAggregation
                       AttAggregation_refine_keepchannel, OutputConv, OutputConv_refine, StackedUNet,
                       StackedUNet_prob)
 from .network import Network  # noqa: F401
-from . import ckpt, eval_errors, fem, pipeline, preprocess, refine, synthetic  # noqa: F401
+from . import ckpt, eval_errors, fem, fusion, pipeline, preprocess, refine, synthetic  # noqa: F401

@@ -24,6 +24,7 @@ SOURCES = {
     "conv_deconv.cu": [],
     "conv_deconv_ring.cu": [],
     "fem2d.cu": [],
+    "fusion.cu": ["--fmad=false"],
 }
 
 

@@ -43,9 +43,11 @@ _SIGS = {
     "atvs_refine_photo_group": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "atvs_visual_hull": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_prob2depth": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
+    "atvs_fuse_depth_maps": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _ll, _p, _p, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
                                 "atvs_packed_weight_bytes", "atvs_packed_weight2d_bytes", "atvs_launch_count",
+                                "atvs_fuse_workspace_bytes",
                                 "atvs_saturation_count"])
 
 
@@ -73,6 +75,8 @@ def load():
         lib.atvs_launch_count.restype = C.c_longlong
         lib.atvs_packed_weight2d_bytes.argtypes = [_i, _i, _i]
         lib.atvs_packed_weight2d_bytes.restype = C.c_size_t
+        lib.atvs_fuse_workspace_bytes.argtypes = [_i, _i, _i]
+        lib.atvs_fuse_workspace_bytes.restype = C.c_size_t
         lib.atvs_saturation_count.argtypes = [_i]
         lib.atvs_saturation_count.restype = C.c_longlong
         _lib = lib

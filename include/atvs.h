@@ -220,6 +220,22 @@ int atvs_visual_hull(const float* ref_depth, const float* trans_depth, const flo
                      const float* depth_start, const float* depth_interval, int B, int D, int H, int W, int view_num,
                      int inverse_depth, float* out, atvs_stream_t stream);
 
+/* ---- depth-map fusion (post-processing) ------ fusibile/fusibile.cu:138-277 (kernel), :279-325 (scan)
+ * normals_depths (N,H,W,4) f32 = (nx, ny, nz, depth) per view (depth_fusion.py:93-112 writes normals (1,1,1)/sqrt(3) where
+ * depth > 0), images (N,H,W,4) f32 colour or NULL; cameras as the reference's Camera_cu holds them: cam_P (N,3,4) =
+ * (K E)[0:3], cam_Minv (N,3,3) = P[:, :3]^-1, cam_C (N,3) centre, cam_f (N) = K[0,0].  A reference pixel becomes a point
+ * when at least num_consistent other views agree: |disp - disp'| / disp < depth_thresh on the projected depth and the
+ * angle between the normals < normal_thresh (radians).  All reference cameras in one call; the points are compacted on the
+ * device in the reference's order (camera-major, row-major; zero coordinates dropped): out_coord / out_normal
+ * (capacity,3), out_texture (capacity,4) or NULL, *out_count (device) = number of points found (may exceed capacity:
+ * only the first `capacity` are written).  workspace: atvs_fuse_workspace_bytes(N,H,W) device bytes, 256-byte aligned. */
+size_t atvs_fuse_workspace_bytes(int N, int H, int W);
+int atvs_fuse_depth_maps(const float* normals_depths, const float* images, const float* cam_P, const float* cam_Minv,
+                         const float* cam_C, const float* cam_f, int N, int H, int W, float depth_thresh,
+                         float normal_thresh, int num_consistent, int save_texture, void* workspace, long long capacity,
+                         float* out_coord, float* out_normal, float* out_texture, long long* out_count,
+                         atvs_stream_t stream);
+
 /* ---- prob2depth / get_propability_map / prob2depth_upsample -------- model.py:80-129, 13-76
  * prob_volume (B,D,H,W) f32 logits; softmax over D of -logit, expectation against
  * linspace(start, start+(D-1)*interval, D) -> depth (B,H*up,W*up) f32; prob_map (same shape,
