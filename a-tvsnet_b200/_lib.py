@@ -47,7 +47,7 @@ _SIGS = {
 }
 EXPORTS = sorted(list(_SIGS) + ["atvs_version", "atvs_last_error", "atvs_device_sm_count",
                                 "atvs_packed_weight_bytes", "atvs_packed_weight2d_bytes", "atvs_launch_count",
-                                "atvs_fuse_workspace_bytes",
+                                "atvs_fuse_workspace_bytes", "atvs_crc32c",
                                 "atvs_saturation_count"])
 
 
@@ -77,6 +77,8 @@ def load():
         lib.atvs_packed_weight2d_bytes.restype = C.c_size_t
         lib.atvs_fuse_workspace_bytes.argtypes = [_i, _i, _i]
         lib.atvs_fuse_workspace_bytes.restype = C.c_size_t
+        lib.atvs_crc32c.argtypes = [_p, C.c_size_t, C.c_uint]
+        lib.atvs_crc32c.restype = C.c_uint
         lib.atvs_saturation_count.argtypes = [_i]
         lib.atvs_saturation_count.restype = C.c_longlong
         _lib = lib

@@ -177,13 +177,29 @@ def read_index(prefix, verify=True):
     return header, entries
 
 
-def read_checkpoint(prefix, names=None, verify_crc_below=1 << 16):
-    """{variable name: np.ndarray} from a V2 checkpoint.  ``names``: optional filter (iterable or predicate).  Tensor
-    CRC-32C is checked for tensors smaller than ``verify_crc_below`` bytes (pure-Python CRC)."""
+def _fast_crc():
+    """CRC-32C over whole tensors through libatvs.so's host helper (slice-by-8); None when the library is not built."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+        return lambda raw: int(lib.atvs_crc32c(raw, len(raw), 0))
+    except Exception:
+        return None
+
+
+def read_checkpoint(prefix, names=None, verify_crc_below=1 << 16, required=()):
+    """{variable name: np.ndarray} from a V2 checkpoint.  ``names``: optional filter (iterable or predicate).  Every
+    tensor's CRC-32C is verified (libatvs.so's host helper; without the library only tensors smaller than
+    ``verify_crc_below`` bytes, in pure Python).  Partitioned (sliced) variables are not assembled: one that is listed in
+    ``required`` raises, others are skipped."""
     header, entries = read_index(prefix)
     want = (lambda n: True) if names is None else (names if callable(names) else set(names).__contains__)
     files, out = {}, {}
+    fast = _fast_crc()
+    required = set(required)
     for name, e in entries.items():
+        if e['sliced'] and name in required:
+            raise ValueError("checkpoint variable %r is stored as partitioned slices, which this reader does not assemble" % name)
         if not want(name) or e['sliced']:
             continue
         if e['dtype'] not in DTYPES:
@@ -198,8 +214,10 @@ def read_checkpoint(prefix, names=None, verify_crc_below=1 << 16):
         n = int(np.prod(e['shape'])) if e['shape'] else 1
         if len(raw) != e['size'] or e['size'] != n * dt.itemsize:
             raise ValueError("checkpoint tensor %r: %d bytes for shape %s %s" % (name, len(raw), e['shape'], dt))
-        if e['crc32c'] is not None and e['size'] < verify_crc_below and mask_crc(crc32c(raw)) != e['crc32c']:
-            raise ValueError("checkpoint tensor %r: CRC mismatch" % name)
+        if e['crc32c'] is not None and (fast is not None or e['size'] < verify_crc_below):
+            got = fast(raw) if fast is not None else crc32c(raw)
+            if mask_crc(got) != e['crc32c']:
+                raise ValueError("checkpoint tensor %r: CRC mismatch" % name)
         out[name] = np.frombuffer(raw, dtype=dt).reshape(e['shape']).copy()
     for f in files.values():
         f.close()

@@ -170,13 +170,51 @@ def synthetic_refine_weights(seed=2468):
     return w
 
 
-def load_checkpoint(prefix, device='cuda'):
+def expected_variable_shapes(parts=('crm', 'fem', 'refine')):
+    """name -> shape of every variable the inference graphs read: 'crm' = StackedUNet_prob, both
+    attention modules and both output convolutions (the hot path), 'fem' = ResNetDS2SPP, 'refine' = the refinement stage."""
+    s = {}
+    if 'crm' in parts:
+        for name, kind, cin, cout, _ in crm_layer_table():
+            if kind == 'conv_bn':
+                s[name + '/conv3d/kernel'] = (3, 3, 3, cin, cout)
+            elif kind == 'deconv_bn':
+                s[name + '/conv3d_transpose/kernel'] = (3, 3, 3, cout, cin)
+            else:
+                s[name + '/kernel'] = (3, 3, 3, cin, cout)
+        for scope, outc in (('attention_aggregate', 'attention_prob_vol'), ('attention_aggregate_refine', 'attention_prob_vol_refine')):
+            s[scope + '/attention_activation/weight_unique'] = (3, 3, 3, 8, 8)
+            s[scope + '/attention_activation/weight_shared'] = (3, 3, 3, 8, 8)
+            s[outc + '/kernel'] = (3, 3, 3, 8, 1)
+    if 'fem' in parts:
+        s.update(fem_variable_shapes())
+    if 'refine' in parts:
+        s.update(refine_variable_shapes())
+    return s
+
+
+def check_variables(weights, parts=('crm', 'fem', 'refine')):
+    """raise a ValueError that lists every missing or mis-shaped variable of ``parts`` (a wrong or partial checkpoint
+    would otherwise surface as a KeyError mid-pipeline or a mis-shaped kernel handed to a CUDA launch)."""
+    exp = expected_variable_shapes(parts)
+    missing = sorted(n for n in exp if n not in weights)
+    wrong = sorted("%s: %s, expected %s" % (n, tuple(np.shape(weights[n])), exp[n]) for n in exp
+                   if n in weights and tuple(np.shape(weights[n])) != tuple(exp[n]))
+    if missing or wrong:
+        raise ValueError("checkpoint does not hold the variables of %s: %d missing %s%s; %d mis-shaped %s"
+                         % ('+'.join(parts), len(missing), missing[:8], ' ...' if len(missing) > 8 else '', len(wrong), wrong[:8]))
+
+
+def load_checkpoint(prefix, device='cuda', parts=('crm', 'fem', 'refine')):
     """restore every variable of a TensorFlow V2 checkpoint (``prefix.index`` / ``prefix.data-*``, example.py:121-125)
-    by name, without TensorFlow (ckpt.read_checkpoint): optimizer slots and non-float entries are ignored."""
+    by name, without TensorFlow (ckpt.read_checkpoint): optimizer slots and non-float entries are ignored; the variables
+    of ``parts`` must all be present with the right shapes (check_variables), every tensor's CRC-32C is verified."""
     from . import ckpt
-    w = {k: v for k, v in ckpt.read_checkpoint(prefix).items()
+    exp = expected_variable_shapes(parts)
+    w = {k: v for k, v in ckpt.read_checkpoint(prefix, required=exp).items()
          if v.dtype == np.float32 and not k.endswith(('/Adam', '/Adam_1', '/Momentum', '/RMSProp', '/RMSProp_1'))}
     if not w:
         raise RuntimeError("no float variables found in checkpoint %r" % prefix)
+    check_variables(w, parts)
     load_weights(w, device=device)
     return sorted(w)

@@ -45,6 +45,9 @@ int         atvs_version(void);                 /* major*10000 + minor*100 + pat
 const char* atvs_last_error(void);              /* thread-local, never NULL               */
 int         atvs_device_sm_count(void);         /* SMs of the current device (148 on B200) */
 long long   atvs_launch_count(void);            /* kernels launched by this library so far  */
+/* host helper: CRC-32C (Castagnoli) of n HOST bytes continuing from `crc` (0 to start); the tensor checksums of a
+ * TensorFlow V2 checkpoint, example.py:121-125 (ckpt.py verifies every tensor with it)                          */
+unsigned    atvs_crc32c(const void* data_host, size_t n, unsigned crc);
 /* number of fp16 raw-output rows (8..32 channels of one voxel) that held a value beyond +-65504 and were clamped by
  * the tensor-path epilogues on the current device since the last reset; synchronises the device; -1 on error.  A
  * non-zero count means the checkpoint's feature scale does not fit fp16 raw storage: rerun with fp32 raw outputs. */

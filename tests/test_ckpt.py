@@ -49,7 +49,7 @@ def test_round_trip_with_checkpoint_variable_names(tmp_path):
     w2 = dict(w)
     w2['conv_b0_1_0/conv3d/kernel/Adam'] = np.zeros((3, 3, 3, 64, 16), np.float32)
     K.write_checkpoint(prefix + '2', w2)
-    names = A.variables.load_checkpoint(prefix + '2', device='cpu')
+    names = A.variables.load_checkpoint(prefix + '2', device='cpu', parts=('crm',))
     assert 'global_step' not in names and 'flag' not in names and 'conv_b0_1_0/conv3d/kernel/Adam' not in names
     assert np.array_equal(A.variables.get_variable('conv_b2_6_2/kernel').numpy(), w['conv_b2_6_2/kernel'])
     only = K.read_checkpoint(prefix, names=lambda n: n.startswith('attention_aggregate/'))
@@ -73,3 +73,35 @@ def test_corruption_is_detected(tmp_path):
     open(prefix + '.index', 'wb').write(b'not a table' * 10)
     with pytest.raises(ValueError, match='magic'):
         K.read_index(prefix)
+
+
+def test_load_checkpoint_validates_the_variable_set_and_large_tensor_crc(tmp_path):
+    """a partial / mis-shaped checkpoint is refused with the list of offending names, and a flipped bit in a LARGE
+    tensor (beyond what the pure-Python CRC covers) is caught through libatvs.so's host CRC-32C."""
+    import __graft_entry__ as ge
+    ge.build()
+    import atvsnet_b200 as A
+    w = A.variables.synthetic_weights(seed=3)
+    prefix = str(tmp_path / 'm.ckpt')
+    K.write_checkpoint(prefix, w)
+    with pytest.raises(ValueError, match='missing'):
+        A.variables.load_checkpoint(prefix, device='cpu')                       # FEM / refinement variables absent
+    assert 'conv_b2_6_2/kernel' in A.variables.load_checkpoint(prefix, device='cpu', parts=('crm',))
+    bad = dict(w)
+    bad['conv_b1_2_1/conv3d/kernel'] = np.zeros((3, 3, 3, 32, 16), np.float32)
+    del bad['attention_prob_vol/kernel']
+    K.write_checkpoint(prefix + 'b', bad)
+    with pytest.raises(ValueError) as ei:
+        A.variables.load_checkpoint(prefix + 'b', device='cpu', parts=('crm',))
+    assert 'attention_prob_vol/kernel' in str(ei.value) and 'conv_b1_2_1/conv3d/kernel' in str(ei.value)
+    # corruption inside a 442 KB kernel
+    header, entries = K.read_index(prefix)
+    e = entries['conv_b0_3_1/conv3d/kernel']
+    assert e['size'] > (1 << 16)
+    raw = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    raw[e['offset'] + e['size'] // 2] ^= 0x10
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(raw))
+    with pytest.raises(ValueError, match='CRC'):
+        A.ckpt.read_checkpoint(prefix)           # the packaged module reaches libatvs.so's host CRC
+    lib = A._lib.load()
+    assert lib.atvs_crc32c(b'123456789', 9, 0) == 0xE3069283                     # the published CRC-32C check value
