@@ -406,7 +406,8 @@ bool deconv_ring_supported(int Cin, int Cout) { return (Cin == 16 && Cout == 8) 
 
 bool deconv_ring_applicable(int B, int D, int H, int W) {
     if (getenv("ATVS_NO_DECONV_RING") != nullptr) return false;
-    const long long minvox = getenv("ATVS_DECONV_RING_MINVOX") ? atoll(getenv("ATVS_DECONV_RING_MINVOX")) : 16384;
+    // below ~100k input voxels the per-(class, tap) kernel is faster (18.6 vs 30 us for 32 -> 16 on 32x32x40)
+    const long long minvox = getenv("ATVS_DECONV_RING_MINVOX") ? atoll(getenv("ATVS_DECONV_RING_MINVOX")) : 100000;
     return (long long)B * D * H * W >= minvox && H >= 2 && W >= 2;
 }
 

@@ -35,13 +35,13 @@
 namespace {
 
 
-// one CTA plane = RG_MT MMA tiles (16 y x 8 x each) side by side in x: every mbarrier handshake of the
-// producer / MMA / epilogue pipeline (~200 cycles each, ~4 per role and plane) then serves 256 voxels
-constexpr int RG_MT = 2;
-constexpr int RG_TY = 16, RG_TX = 8 * RG_MT, RG_HH = RG_TY + 2, RG_WW = RG_TX + 2;
-constexpr int RG_NVOX = RG_HH * RG_WW;              // voxels of one halo plane (324)
-constexpr int RG_KCH_PAD = RG_NVOX * 16 + 16;       // pitch of one 8-channel chunk plane; +16 B keeps the
-                                                    // 8 chunk stores of a voxel on distinct banks
+// one CTA plane = MT MMA tiles (16 y x 8 x each) side by side in x: MT = 2 (256 voxels per plane step) by default.
+// The skeleton of the three roles (no loads / MMAs / stores) runs at ~760 cycles per 256-voxel plane
+// (profiles/r02_ring_8_8_trace.txt), which is what bounds the 8-channel layers; MT = 4 (512 voxels, 7-group accumulator
+// ring so that two CTAs still share the 512 TMEM columns) and grouped publishing of planes (PG) were built to amortise
+// it and measured: neither changes the 45 us of an 8 -> 8 layer at cfg2 (profiles/r02_ring_probe.txt), so the cost
+// scales with the plane, not with the handshake count.
+constexpr int RG_TY = 16, RG_HH = RG_TY + 2;
 constexpr int RG_PRODUCERS = 128;
 constexpr int RG_THREADS = 288;
 constexpr int RG_MAXG = 15;
@@ -53,24 +53,28 @@ struct RingParams {
     int raw16;          // raw output dtype: 0 fp32, 1 saturated fp16
     uint32_t fmt;       // operand format bits of the instruction descriptor (tc_fmt_bits)
     unsigned long long* sat;   // saturation counter of the fp16 raw stores (atvs_sat_ptr)
-    int nXT, nYT, nZS, ZS;
-    int nring, pf;      // ring slots, planes of cp.async in flight per producer thread (pf <= nring - 1, <= 8)
+    int nXT, nYT, nZS, ZS, TX;   // TX = tile width in voxels (8 * MT)
+    int nring, pf, pg;  // ring slots; cp.async GROUPS in flight per producer thread; planes per group (pf * pg < nring)
     int wbytes;
     int dbg;            // ATVS_RING_DEBUG bit mask (tools/conv_probe.py): 1 no loads, 2 no MMAs, 4 no stores, 8 no zeroing
     long long nunits;
 };
 
-template <int CIN, int CP>
+template <int CIN, int CP, int MT>
 struct RingCfg {
+    static constexpr int TX = 8 * MT, WW = TX + 2;
+    static constexpr int NVOX = RG_HH * WW;               // voxels of one halo plane (324 for MT = 2)
+    static constexpr int KCH_PAD = NVOX * 16 + 16;        // pitch of one 8-channel chunk plane; +16 B keeps the
+                                                          // 8 chunk stores of a voxel on distinct banks
     static constexpr int NKC = CIN / 8;
-    static constexpr int SLOT_BYTES = (NKC * RG_KCH_PAD + 127) / 128 * 128;
+    static constexpr int SLOT_BYTES = (NKC * KCH_PAD + 127) / 128 * 128;
     static constexpr int NSTEPS = (CIN >= 16) ? 9 * (CIN / 16) : 5;     // K=16 MMA steps per input plane
     static constexpr bool PAD = (CP == 8);                              // runs are padded to N % 16 == 0 with zero weights
-    static constexpr int G = (CP == 8) ? 15 : 8;                        // accumulator groups in the ring
+    static constexpr int G = (CP == 8) ? (MT == 4 ? 7 : 15) : 8;        // accumulator groups in the ring
     static constexpr int NROWS = (CP == 8) ? 64 : 3 * CP;               // rows of one weight step image
     static constexpr int STEP_BYTES = 2 * NROWS * 16;
-    static constexpr uint32_t TILE_COLS = (CP == 32) ? 256u : 128u;     // CP=8: 15 groups + 1 dummy
-    static constexpr uint32_t TMEM_COLS = RG_MT * TILE_COLS;
+    static constexpr uint32_t TILE_COLS = (CP == 32) ? 256u : ((CP == 8 && MT == 4) ? 64u : 128u);   // CP=8: G groups + 1 dummy
+    static constexpr uint32_t TMEM_COLS = MT * TILE_COLS;
 };
 
 struct Unit {
@@ -81,7 +85,7 @@ __device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
     Unit r;
     const int zs = (int)(u % p.nZS);
     long long t = u / p.nZS;
-    r.x0 = (int)(t % p.nXT) * RG_TX;
+    r.x0 = (int)(t % p.nXT) * p.TX;
     t /= p.nXT;
     r.y0 = (int)(t % p.nYT) * RG_TY;
     r.b = (int)(t / p.nYT);
@@ -115,13 +119,14 @@ __device__ __forceinline__ void ring_window(int f, int len, uint32_t& row_off_by
     }
 }
 
-template <int CIN, int CP, int MINB>
+template <int CIN, int CP, int MT, int MINB>
 __global__ void __launch_bounds__(RG_THREADS, MINB)
 k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
               const float* __restrict__ bias) {
-    using Cfg = RingCfg<CIN, CP>;
+    using Cfg = RingCfg<CIN, CP, MT>;
     constexpr int G = Cfg::G;
+    constexpr int RG_WW = Cfg::WW, RG_NVOX = Cfg::NVOX, RG_KCH_PAD = Cfg::KCH_PAD, RG_MT = MT;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -182,8 +187,11 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         constexpr int NITEM = (Cfg::NKC * RG_NVOX + RG_PRODUCERS - 1) / RG_PRODUCERS;
         // up to PF planes of cp.async in flight per thread; plane q is published (fence.proxy.async +
         // mbarrier arrive) once plane q+PF-1 has been issued.  PF <= R-1 keeps the ring deadlock-free.
-        const int PF = p.pf;
-        uint32_t slot = 0, sphase = 0, pslot = 0, pending = 0;
+        // Publishing a plane (cp.async.wait_group + fence.proxy.async + __syncwarp + mbarrier arrive) costs ~400 cycles of
+        // the producer's per-plane loop whatever the plane holds (profiles/r02_ring_8_8_trace.txt: 770 cycles per plane
+        // with nothing to load): planes are committed and published in groups of PG, up to PF groups in flight.
+        const int PF = p.pf, PG = p.pg;
+        uint32_t slot = 0, sphase = 0, pslot = 0, pending = 0, pplanes = 0, gopen = 0;
         const uint32_t ring_u32 = smem_u32(ring);
         auto publish = [&](int keep) {
             // wait until at most `keep` groups are pending, then publish every older plane
@@ -199,10 +207,12 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
             // every lane's copies have landed and are visible to the async proxy; one release-arrive per warp
             // (128 per-thread arrivals on one mbarrier cost more than the plane's cp.async issue)
             __syncwarp();
-            for (; pending > (uint32_t)keep; --pending) {
+            // the groups that stay pending are full ones (a partial group only exists at the very end, flushed with keep 0)
+            for (; pplanes > (uint32_t)(keep * PG); --pplanes) {
                 if ((threadIdx.x & 31) == 0) mbar_arrive(&full[pslot]);
                 if (++pslot == (uint32_t)R) pslot = 0;
             }
+            if (pending > (uint32_t)keep) pending = (uint32_t)keep;
         };
         const size_t zstride_in = (size_t)p.H * p.W * CIN;
         TRACE_DECL
@@ -236,13 +246,22 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                                      : "memory");
                     }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
                 TRACE(1);
                 if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
-                if (++pending >= (uint32_t)PF) publish(PF - 1);
+                if (++gopen == (uint32_t)PG) {
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    gopen = 0;
+                    pplanes += (uint32_t)PG;
+                    if (++pending >= (uint32_t)PF) publish(PF - 1);
+                }
                 TRACE(2);
                 TRACE_NEXT();
             }
+        }
+        if (gopen > 0) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            pplanes += gopen;
+            ++pending;
         }
         publish(0);
         if (ptid == 0) TRACE_DUMP("P");
@@ -480,15 +499,15 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
     }
 }
 
-template <int CIN, int CP, int MINB>
+template <int CIN, int CP, int MT, int MINB>
 int launch_ring(const uint16_t* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
                 const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, CP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, CP, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_ring<CIN, CP, MINB><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
+    k_conv3d_ring<CIN, CP, MT, MINB><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -536,14 +555,19 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     p.raw16 = raw16;
     p.fmt = tc_fmt_bits(dtype);
     p.sat = raw16 ? atvs_sat_ptr() : nullptr;
-    p.nXT = (W + RG_TX - 1) / RG_TX;
+    // 4-tile planes for the 8-channel layers exist (ATVS_RING_MT=4) but measured no faster than 2-tile planes
+    // (profiles/r02_ring_probe.txt: 45 us either way at cfg2): the default stays 2
+    int mt = 2;
+    if (const char* e = getenv("ATVS_RING_MT")) mt = (atoi(e) == 4 && Cin == 8 && cp == 8 && W >= 32) ? 4 : 2;
+    p.TX = 8 * mt;
+    p.nXT = (W + p.TX - 1) / p.TX;
     p.nYT = (H + RG_TY - 1) / RG_TY;
     p.wbytes = (int)ring_slab_bytes(Cin, cp);
     {
         const char* e = getenv("ATVS_RING_DEBUG");
         p.dbg = e ? atoi(e) : 0;
     }
-    const size_t slot = ((size_t)(Cin / 8) * RG_KCH_PAD + 127) / 128 * 128;
+    const size_t slot = ((size_t)(Cin / 8) * ((size_t)RG_HH * (p.TX + 2) * 16 + 16) + 127) / 128 * 128;
     const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * RG_MAXR + 2 * RG_MAXG + 1) * 8 + 16;
     // two co-resident CTAs per SM when 2 x (weights + 4 planes) fit: their producer / MMA / epilogue
     // handshake latencies overlap
@@ -555,7 +579,7 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     const size_t budget = (minb == 2 ? 110 : 220) * 1024;
     int nring = (int)((budget - fixed) / slot);
     {
-        int cap = 8;
+        int cap = Cin <= 16 ? 12 : 8;
         if (const char* e = getenv("ATVS_RING_R")) cap = atoi(e) < RG_MAXR ? (atoi(e) > 1 ? atoi(e) : 2) : RG_MAXR;
         if (nring > cap) nring = cap;
     }
@@ -564,12 +588,17 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
         return ATVS_E_UNSUP;
     }
     p.nring = nring;
-    p.pf = (nring >= 5) ? 4 : (nring >= 3 ? 2 : 1);
+    // planes per published group: 2 where a plane is small (Cin <= 16: the per-plane publish cost dominates), else 1
+    p.pg = (Cin <= 16 && nring >= 6) ? 2 : 1;
+    if (const char* e = getenv("ATVS_RING_PG")) p.pg = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : p.pg;
+    while (p.pg > 1 && 2 * p.pg + 1 > nring) --p.pg;
+    p.pf = (nring - 1) / p.pg;                      // groups in flight: pf * pg < nring keeps the ring deadlock-free
+    if (p.pf > 4) p.pf = 4;
     if (const char* e = getenv("ATVS_RING_PF")) {
         const int v = atoi(e);
-        if (v >= 1) p.pf = v < nring - 1 ? (v < 8 ? v : 8) : (nring - 1 < 8 ? nring - 1 : 8);
-        if (p.pf < 1) p.pf = 1;
+        if (v >= 1 && v * p.pg < nring) p.pf = v < 8 ? v : 8;
     }
+    if (p.pf < 1) p.pf = 1;
     {   // z segment length: minimise waves * (planes per unit)
         const long long cols = (long long)B * p.nXT * p.nYT;
         const long long slots = (long long)sms * minb;
@@ -595,9 +624,13 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
         int rc = 0;
 #define RG_CASE(CI, CPV)                                                                                              \
     if (Cin == CI && cp == CPV) {                                                                                     \
-        rc = (minb == 2) ? launch_ring<CI, CPV, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st) \
-                         : launch_ring<CI, CPV, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st); \
+        rc = (minb == 2) ? launch_ring<CI, CPV, 2, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st) \
+                         : launch_ring<CI, CPV, 2, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st); \
     } else
+        if (Cin == 8 && cp == 8 && mt == 4) {
+            rc = (minb == 2) ? launch_ring<8, 8, 4, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st)
+                             : launch_ring<8, 8, 4, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st);
+        } else
         RG_CASE(8, 8) RG_CASE(8, 16) RG_CASE(8, 32) RG_CASE(16, 8) RG_CASE(16, 16) RG_CASE(16, 32)
         RG_CASE(32, 8) RG_CASE(32, 16) RG_CASE(32, 32) RG_CASE(64, 8) RG_CASE(64, 16) RG_CASE(64, 32)
         {
