@@ -406,8 +406,10 @@ bool deconv_ring_supported(int Cin, int Cout) { return (Cin == 16 && Cout == 8) 
 
 bool deconv_ring_applicable(int B, int D, int H, int W) {
     if (getenv("ATVS_NO_DECONV_RING") != nullptr) return false;
-    // below ~100k input voxels the per-(class, tap) kernel is faster (18.6 vs 30 us for 32 -> 16 on 32x32x40)
-    const long long minvox = getenv("ATVS_DECONV_RING_MINVOX") ? atoll(getenv("ATVS_DECONV_RING_MINVOX")) : 100000;
+    // alone, the per-(class, tap) kernel is faster below ~100k input voxels (18.6 vs 30 us for 32 -> 16 on 32x32x40), but
+    // inside the step the plane ring wins there too (5.93 vs 6.08 ms per cfg2 depth map: 110 KB of shared memory and 8
+    // staged TMA tiles per 128 voxels less pressure on the co-running passes)
+    const long long minvox = getenv("ATVS_DECONV_RING_MINVOX") ? atoll(getenv("ATVS_DECONV_RING_MINVOX")) : 16384;
     return (long long)B * D * H * W >= minvox && H >= 2 && W >= 2;
 }
 

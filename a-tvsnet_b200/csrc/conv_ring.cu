@@ -579,7 +579,7 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     const size_t budget = (minb == 2 ? 110 : 220) * 1024;
     int nring = (int)((budget - fixed) / slot);
     {
-        int cap = Cin <= 16 ? 12 : 8;
+        int cap = 8;
         if (const char* e = getenv("ATVS_RING_R")) cap = atoi(e) < RG_MAXR ? (atoi(e) > 1 ? atoi(e) : 2) : RG_MAXR;
         if (nring > cap) nring = cap;
     }
@@ -589,7 +589,7 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     }
     p.nring = nring;
     // planes per published group: 2 where a plane is small (Cin <= 16: the per-plane publish cost dominates), else 1
-    p.pg = (Cin <= 16 && nring >= 6) ? 2 : 1;
+    p.pg = 1;          // grouped publishing (ATVS_RING_PG=2..4) measured no faster: profiles/r02_ring_probe.txt
     if (const char* e = getenv("ATVS_RING_PG")) p.pg = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : p.pg;
     while (p.pg > 1 && 2 * p.pg + 1 > nring) --p.pg;
     p.pf = (nring - 1) / p.pg;                      // groups in flight: pf * pg < nring keeps the ring deadlock-free

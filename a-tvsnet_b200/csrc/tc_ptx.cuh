@@ -31,10 +31,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// ATVS_MBAR_HINT_NS: suspend-time hint of mbarrier.try_wait in ns; 0 = no hint (the hardware's default time limit, what
-// CUTLASS's ClusterBarrier::wait uses).  Measured (tools/sweep2.sh, profiles/r02_mbar_hint.txt): see DESIGN.md.
+// ATVS_MBAR_HINT_NS: suspend-time hint of mbarrier.try_wait in ns; 0 = no hint (the hardware's default time limit).
+// Measured both ways (profiles/r02_ring_probe.txt): the kernels alone do not care, the whole cfg2 step is 0.08 ms faster
+// with the long hint (waiting warps sleep instead of polling while 8 streams share the SMs).
 #ifndef ATVS_MBAR_HINT_NS
-#define ATVS_MBAR_HINT_NS 0
+#define ATVS_MBAR_HINT_NS 10000000
 #endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

@@ -344,12 +344,17 @@ def run_ours(args, rank, world, local_rank):
                     o = fn()
                 torch.cuda.synchronize()
                 k = max(3, min(args.steps, 10))
-                graphed = name.startswith("from_images") and not args.no_graph
+                graphed = not args.no_graph
                 if graphed:
-                    g, o = capture(fn, torch)
+                    try:
+                        g, o = capture(fn, torch)
+                    except Exception:          # a step that cannot be captured is timed as eager launches
+                        torch.cuda.synchronize()
+                        graphed = False
+                if graphed:
                     ms, _ = timed_steps(lambda: g.replay(), k, torch, barrier)
                     del g
-                else:           # stages III / IV go through torch glue that is not captured: eager launches
+                else:
                     ms, o = timed_steps(fn, k, torch, barrier)
                 extras[name] = {"what": what, "ms_per_step": ms / k, "value": k / (ms * 1e-3), "unit": "depth maps/s",
                                 "steps": k, "cuda_graph": graphed, "finite": bool(torch.isfinite(o).all())}
