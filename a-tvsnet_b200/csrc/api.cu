@@ -54,11 +54,9 @@ unsigned long long* atvs_sat_ptr() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (g_sat[dev] == nullptr) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         unsigned long long* p = nullptr;
         if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         cudaMemset(p, 0, sizeof(unsigned long long));
-        (void)cs;
         g_sat[dev] = p;
     }
     return g_sat[dev];

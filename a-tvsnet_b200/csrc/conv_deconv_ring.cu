@@ -46,6 +46,8 @@ struct DrParams {
     int nring, pf;
     int wbytes;
     long long nunits;
+    int balanced;           // ring_common.cuh RingSpan: 1 = balanced ranges of input planes
+    long long total;        // tile columns * D
 };
 
 template <int CIN, int COUT>
@@ -64,18 +66,20 @@ struct DrUnit {
     int b, x0, y0, z0, zlen;
 };
 
-__device__ __forceinline__ DrUnit dr_decode(const DrParams& p, long long u) {
-    DrUnit r;
-    const int zs = (int)(u % p.nZS);
-    long long t = u / p.nZS;
-    r.x0 = (int)(t % p.nXT) * DR_TX;
-    t /= p.nXT;
-    r.y0 = (int)(t % p.nYT) * DR_TY;
-    r.b = (int)(t / p.nYT);
-    r.z0 = zs * p.ZS;
-    r.zlen = min(p.ZS, p.D - r.z0);
-    return r;
-}
+
+struct DrIter {
+    RingSpan span;
+    __device__ __forceinline__ explicit DrIter(const DrParams& p) : span(p.balanced, p.total, p.nunits) {}
+    __device__ __forceinline__ bool next(const DrParams& p, DrUnit& r) {
+        long long t;
+        if (!span.next(p.balanced, p.D, p.nZS, p.ZS, t, r.z0, r.zlen)) return false;
+        r.x0 = (int)(t % p.nXT) * DR_TX;
+        t /= p.nXT;
+        r.y0 = (int)(t % p.nYT) * DR_TY;
+        r.b = (int)(t / p.nYT);
+        return true;
+    }
+};
 
 // 16 consecutive fp32 values -> 16 saturated halves, ONE 32-byte store (p 32-byte aligned)
 __device__ __forceinline__ void store_f16x16(__half* p, const float* v) {
@@ -170,8 +174,9 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
         };
         const size_t zstride_in = (size_t)p.H * p.W * CIN;
         TRACE_DECL
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const DrUnit un = dr_decode(p, u);
+        DrIter units(p);
+        DrUnit un;
+        while (units.next(p, un)) {
             const int ibeg = un.z0 > 0 ? -1 : 0;
             int goff[NITEM];       // element offset inside a z plane, -1 = zero fill, -2 = no item
 #pragma unroll
@@ -233,8 +238,9 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
             uint32_t slot = 0, sphase = 0;
             uint32_t gq = 0, gphase = 0;       // accumulator group / phase of output plane t = 0 of the unit
             TRACE_DECL
-            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-                const DrUnit un = dr_decode(p, u);
+            DrIter units(p);
+            DrUnit un;
+            while (units.next(p, un)) {
                 const int ibeg = un.z0 > 0 ? -1 : 0;
                 const int nt = 2 * un.zlen;
                 uint32_t gw = gq, gwphase = gphase;   // group / phase of the next output plane to acquire
@@ -297,8 +303,9 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
         // a unit starts on an even group and consumes an even number of groups: set s only ever sees groups of parity s
         uint32_t grp = (uint32_t)set, gphase = 0;
         TRACE_DECL
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const DrUnit un = dr_decode(p, u);
+        DrIter units(p);
+        DrUnit un;
+        while (units.next(p, un)) {
             const int y = un.y0 + ty, xq = un.x0 + tx;
             const bool ok = y < p.H && xq < p.W;
             const int nt = 2 * un.zlen;
@@ -463,7 +470,13 @@ int deconv_ring(const void* x16, int dtype, const void* wimg, int B, int D, int 
         p.nunits = cols * p.nZS;
     }
     const size_t smem = fixed + (size_t)nring * slot;
-    const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    {   // balanced ranges of input planes (default, ring_common.cuh); ATVS_DRING_BALANCED=0: fixed z segments
+        p.total = (long long)B * p.nXT * p.nYT * D;
+        p.balanced = 1;
+        if (const char* e = getenv("ATVS_DRING_BALANCED")) p.balanced = atoi(e) != 0;
+        if (p.balanced) grid = ring_balanced_grid(p.total, (long long)sms * minb, 160, "ATVS_DRING_CTAS", nullptr);
+    }
     const uint8_t* wi = (const uint8_t*)wimg;
     if (Cin == 16 && Cout == 8) return launch_dr<16, 8>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);
     if (Cin == 32 && Cout == 16) return launch_dr<32, 16>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);

@@ -26,7 +26,13 @@
 //               8-channel chunk = LBO), filled by 4 producer warps with 16-byte cp.async (zero fill =
 //               'SAME' padding) and published to the async proxy with fence.proxy.async
 //   Cin = 8   : one K=16 step covers two taps of the plane (LBO = distance of the taps)
-//   warps 0-3 producers | warp 4 MMA issuer (converged, elected lane) | warps 5-8 epilogue
+//   warps 0-3 producers | warp 4 MMA issuer (one elected lane) | warps 5-8 epilogue
+//
+// The issuing thread's stream is ~10 SASS instructions per MMA (descriptor arithmetic in vector registers + R2UR moves
+// to the uniform registers UTCHMMA reads) and sustains one MMA per ~47 cycles against the pipe's 40
+// (profiles/r02_ring32_issue_trace.txt).  Splitting the two MMA tiles of a plane over two issuing warps (4 and 9, each
+// committing its own MMAs) was built and measured: 93.7 us against 93.9 for 32 -> 8, 51.2 against 48.7 for 8 -> 8 at
+// cfg2 - the pipe, not the issue stream, is what the plane step waits for; one issuer stays.
 #include "ring_common.cuh"
 #include "conv_ring.cuh"
 #include <cstring>
@@ -58,6 +64,8 @@ struct RingParams {
     int wbytes;
     int dbg;            // ATVS_RING_DEBUG bit mask (tools/conv_probe.py): 1 no loads, 2 no MMAs, 4 no stores, 8 no zeroing
     long long nunits;
+    int balanced;       // 1: every CTA owns one contiguous range of the linear (tile column, z) plane sequence
+    long long total;    // balanced: tile columns * D
 };
 
 template <int CIN, int CP, int MT>
@@ -81,18 +89,21 @@ struct Unit {
     int b, x0, y0, z0, zlen;
 };
 
-__device__ __forceinline__ Unit decode_unit(const RingParams& p, long long u) {
-    Unit r;
-    const int zs = (int)(u % p.nZS);
-    long long t = u / p.nZS;
-    r.x0 = (int)(t % p.nXT) * p.TX;
-    t /= p.nXT;
-    r.y0 = (int)(t % p.nYT) * RG_TY;
-    r.b = (int)(t / p.nYT);
-    r.z0 = zs * p.ZS;
-    r.zlen = min(p.ZS, p.D - r.z0);
-    return r;
-}
+
+// units of this CTA (ring_common.cuh RingSpan: balanced plane ranges by default, fixed z segments on request)
+struct UnitIter {
+    RingSpan span;
+    __device__ __forceinline__ explicit UnitIter(const RingParams& p) : span(p.balanced, p.total, p.nunits) {}
+    __device__ __forceinline__ bool next(const RingParams& p, Unit& r) {
+        long long t;
+        if (!span.next(p.balanced, p.D, p.nZS, p.ZS, t, r.z0, r.zlen)) return false;
+        r.x0 = (int)(t % p.nXT) * p.TX;
+        t /= p.nXT;
+        r.y0 = (int)(t % p.nYT) * RG_TY;
+        r.b = (int)(t / p.nYT);
+        return true;
+    }
+};
 
 // input planes of a unit: i in [ibeg, iend], plane i = volume plane z0 - 1 + i; planes outside the volume
 // contribute nothing ('SAME' zero padding) and are skipped by all three roles
@@ -216,8 +227,9 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         };
         const size_t zstride_in = (size_t)p.H * p.W * CIN;
         TRACE_DECL
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const Unit un = decode_unit(p, u);
+        UnitIter units(p);
+        Unit un;
+        while (units.next(p, un)) {
             const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
             int goff[NITEM];       // element offset inside a z plane, -1 = zero fill, -2 = no item
 #pragma unroll
@@ -266,10 +278,9 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         publish(0);
         if (ptid == 0) TRACE_DUMP("P");
     } else if (warp == 4) {
-        // ===================== MMA issuer (converged warp, elected lane issues) =====================
-        // One warp issues every MMA of the CTA, so its instruction stream per plane is what bounds the
-        // small-channel layers: counters are incremental (no divisions), and the steady state (three
-        // live output planes, no ring wrap) is a straight-line block.
+        // ===================== MMA issuer (elected lane) =====================
+        // The instruction stream per plane matters for the small-channel layers: counters are incremental (no
+        // divisions), and the steady state (three live output planes, no ring wrap) is a straight-line block.
         if (elect_one()) {
         mbar_wait(wbar, 0);
         tc_fence_after();
@@ -285,7 +296,8 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
             for (int s = 0; s < Cfg::NSTEPS; ++s) {
                 uint32_t aoff;
                 if (CIN >= 16) {
-                    const int tp = s / (CIN / 16), ks = s % (CIN / 16);
+                    constexpr int KS = (CIN >= 16) ? CIN / 16 : 1;
+                    const int tp = s / KS, ks = s % KS;
                     aoff = (uint32_t)((2 * ks * RG_KCH_PAD + ((tp / 3) * RG_WW + (tp % 3)) * 16) >> 4);
                 } else {
                     // tap pairs (0,1) (2,3) (4,5) (6,7) (7*,8): the 9th tap is paired with a second,
@@ -304,8 +316,9 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         TRACE_DECL
         uint32_t slot = 0, sphase = 0;     // ring position of the next input plane
         uint32_t gq = 0, gphase = 0;       // accumulator group / phase of output plane t = 0 of the unit
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const Unit un = decode_unit(p, u);
+        UnitIter units(p);
+        Unit un;
+        while (units.next(p, un)) {
             const int ibeg = unit_ibeg(un), iend = unit_iend(p, un);
             uint32_t gw = gq, gwphase = gphase;   // group / phase of the next output plane to wait for
             int twaited = -1;
@@ -375,8 +388,9 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         const int vec = raw_vec_mode(out, p.ncols, p.Cout, p.coff);
         uint32_t grp = 0, gphase = 0;
         TRACE_DECL
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const Unit un = decode_unit(p, u);
+        UnitIter units(p);
+        Unit un;
+        while (units.next(p, un)) {
             const int y = un.y0 + ty, xq = un.x0 + tx;          // tile mt covers x = xq + 8 * mt
             const bool yok = y < p.H;
             const size_t obase = ((((size_t)un.b * p.D + un.z0) * p.H + (yok ? y : 0)) * p.W) * p.Cout + p.coff;
@@ -616,7 +630,19 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
         p.nunits = cols * p.nZS;
     }
     const size_t smem = fixed + (size_t)nring * slot;
-    const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    {   // balanced plane ranges (default, ring_common.cuh); ATVS_RING_BALANCED=0: fixed z segments
+        p.total = (long long)B * p.nXT * p.nYT * D;
+        p.balanced = 1;
+        char name[48];
+        snprintf(name, sizeof(name), "ATVS_RING_BALANCED_%d_%d", Cin, Cout);
+        if (const char* e = getenv(name)) p.balanced = atoi(e) != 0;
+        else if (const char* e2 = getenv("ATVS_RING_BALANCED")) p.balanced = atoi(e2) != 0;
+        if (p.balanced) {
+            snprintf(name, sizeof(name), "ATVS_RING_CTAS_%d_%d", Cin, Cout);
+            grid = ring_balanced_grid(p.total, (long long)sms * minb, 40, name, "ATVS_RING_CTAS");
+        }
+    }
     for (int slab = 0; slab < nslabs; ++slab) {
         p.coff = slab * cp;
         p.ncols = (Cout - p.coff < cp) ? Cout - p.coff : cp;

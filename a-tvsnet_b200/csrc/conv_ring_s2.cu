@@ -41,6 +41,8 @@ struct S2Params {
     int nring;
     int wbytes;
     long long nunits;
+    int balanced;               // ring_common.cuh RingSpan: 1 = balanced ranges of output planes
+    long long total;            // tile columns * Do
 };
 
 template <int CIN, int CP>
@@ -57,18 +59,19 @@ struct S2Unit {
     int b, x0, y0, z0, zlen;
 };
 
-__device__ __forceinline__ S2Unit s2_decode(const S2Params& p, long long u) {
-    S2Unit r;
-    const int zs = (int)(u % p.nZS);
-    long long t = u / p.nZS;
-    r.x0 = (int)(t % p.nXT) * S2_TX;
-    t /= p.nXT;
-    r.y0 = (int)(t % p.nYT) * S2_TY;
-    r.b = (int)(t / p.nYT);
-    r.z0 = zs * p.ZS;
-    r.zlen = min(p.ZS, p.Do - r.z0);
-    return r;
-}
+struct S2Iter {
+    RingSpan span;
+    __device__ __forceinline__ explicit S2Iter(const S2Params& p) : span(p.balanced, p.total, p.nunits) {}
+    __device__ __forceinline__ bool next(const S2Params& p, S2Unit& r) {
+        long long t;
+        if (!span.next(p.balanced, p.Do, p.nZS, p.ZS, t, r.z0, r.zlen)) return false;
+        r.x0 = (int)(t % p.nXT) * S2_TX;
+        t /= p.nXT;
+        r.y0 = (int)(t % p.nYT) * S2_TY;
+        r.b = (int)(t / p.nYT);
+        return true;
+    }
+};
 // input planes of a unit: i in [0, iend], plane i = input plane 2*z0 + i; the plane behind the volume
 // ('SAME' padding) is skipped
 __device__ __forceinline__ int s2_iend(const S2Params& p, const S2Unit& u) {
@@ -165,8 +168,9 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
             }
         };
         const size_t zstride_in = (size_t)p.H * p.W * CIN;
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const S2Unit un = s2_decode(p, u);
+        S2Iter units(p);
+        S2Unit un;
+        while (units.next(p, un)) {
             const int iend = s2_iend(p, un);
             int goff[NITEM];       // element offset inside an input z plane, -1 = zero fill, -2 = no item
 #pragma unroll
@@ -218,7 +222,8 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                 for (int s = 0; s < Cfg::NSTEPS; ++s) {
                     uint32_t aoff;
                     if (CIN >= 16) {
-                        const int tp = s / (CIN / 16), ks = s % (CIN / 16);
+                        constexpr int KS = (CIN >= 16) ? CIN / 16 : 1;
+                        const int tp = s / KS, ks = s % KS;
                         aoff = (uint32_t)((2 * ks * S2_PITCH) >> 4) + (s2_tap_off(tp) >> 4);
                     } else {
                         const uint32_t offa = s2_tap_off(s2_pair_a(s)), offb = s2_tap_off(s2_pair_b(s));
@@ -231,8 +236,9 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
             constexpr uint32_t W_W2W0 = 0u, W_W0 = (uint32_t)CP, W_W1 = 2u * (uint32_t)CP;
             uint32_t slot = 0, sphase = 0;
             uint32_t gq = 0, gphase = 0;       // accumulator group / phase of output plane t = 0 of the unit
-            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-                const S2Unit un = s2_decode(p, u);
+            S2Iter units(p);
+            S2Unit un;
+            while (units.next(p, un)) {
                 const int iend = s2_iend(p, un);
                 uint32_t gw = gq, gwphase = gphase;    // next output plane to wait for (fresh accumulator)
                 uint32_t gcur = gq;                    // group of output plane j = i >> 1
@@ -287,8 +293,9 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
         const int vec = raw_vec_mode(out, p.ncols, p.Cout, p.coff);
         uint32_t grp = 0, gphase = 0;
-        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const S2Unit un = s2_decode(p, u);
+        S2Iter units(p);
+        S2Unit un;
+        while (units.next(p, un)) {
             const int y = un.y0 + ty, xq = un.x0 + tx;
             const bool valid = y < p.Ho && xq < p.Wo;
             const size_t obase = valid ? ((((size_t)un.b * p.Do + un.z0) * p.Ho + y) * p.Wo + xq) * p.Cout + p.coff : 0;
@@ -471,7 +478,17 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
         p.nunits = cols * p.nZS;
     }
     const size_t smem = fixed + (size_t)nring * slot;
-    const int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    int grid = (int)(p.nunits < (long long)sms * minb ? p.nunits : (long long)sms * minb);
+    {   // balanced ranges of output planes (default, ring_common.cuh); ATVS_S2_BALANCED=0: fixed z segments
+        p.total = (long long)B * p.nXT * p.nYT * p.Do;
+        p.balanced = 1;
+        if (const char* e = getenv("ATVS_S2_BALANCED")) p.balanced = atoi(e) != 0;
+        if (p.balanced) {
+            char name[48];
+            snprintf(name, sizeof(name), "ATVS_S2_CTAS_%d_%d", Cin, Cout);
+            grid = ring_balanced_grid(p.total, (long long)sms * minb, 80, name, "ATVS_S2_CTAS");
+        }
+    }
     for (int slab = 0; slab < nslabs; ++slab) {
         p.coff = slab * cp;
         p.ncols = (Cout - p.coff < cp) ? Cout - p.coff : cp;

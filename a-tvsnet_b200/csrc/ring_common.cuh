@@ -1,6 +1,7 @@
 // ring_common.cuh - helpers shared by the halo-ring convolution kernels (conv_ring.cu, conv_ring_s2.cu)
 #pragma once
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 // per-role clock64 timelines of CTA 0 (build with -DATVS_RING_TRACE: tools/build_trace.sh, tools/ring_trace.py)
 #ifdef ATVS_RING_TRACE
@@ -76,6 +77,64 @@ __host__ __device__ constexpr uint32_t ring_idesc(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+
+// Work of one CTA of a plane-ring kernel as a sequence of units (tile column, z0, zlen).
+//   fixed z segments (balanced = 0): units u = blockIdx.x, blockIdx.x + gridDim.x, ... of length ZS.  The tile columns
+//     of a volume rarely divide by the resident CTAs (cfg2: 80 columns x 5 segments = 400 units on 296 CTAs = 1.35
+//     waves: the launch lasts 2 x 28 plane steps where 37 would do).
+//   balanced = 1 (default): the planes of all columns form ONE sequence (column-major, z fastest) that is cut into
+//     gridDim.x equal ranges; a range that crosses a column end becomes two units.  Every CTA runs total/grid planes
+//     (+ the halo planes of its 1-2 units), whatever the volume.
+struct RingSpan {
+    long long pos, end;
+    __device__ __forceinline__ RingSpan(int balanced, long long total, long long nunits) {
+        if (balanced) {
+            pos = total * (long long)blockIdx.x / (long long)gridDim.x;
+            end = total * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+        } else {
+            pos = blockIdx.x;
+            end = nunits;
+        }
+    }
+    // next unit: balanced -> (col, z0, zlen) of the piece; fixed segments -> (col, z0, zlen) of unit `pos`
+    __device__ __forceinline__ bool next(int balanced, int nz, int nZS, int ZS, long long& col, int& z0, int& zlen) {
+        if (pos >= end) return false;
+        if (balanced) {
+            col = pos / nz;
+            z0 = (int)(pos - col * nz);
+            zlen = (int)min((long long)(nz - z0), end - pos);
+            pos += zlen;
+        } else {
+            col = pos / nZS;
+            z0 = (int)(pos - col * nZS) * ZS;
+            zlen = min(ZS, nz - z0);
+            pos += gridDim.x;
+        }
+        return true;
+    }
+};
+
+// grid of a balanced launch: all resident slots, but at least `minplanes` planes per CTA.  A CTA's fixed cost (TMEM
+// allocation, weight image, pipeline fill, cold first loads) is worth ~10 plane steps, and a tensor CTA holds half an
+// SM's shared memory and TMEM columns while it lives, so in the whole step (8 passes on 8 streams) FEWER, LONGER CTAs
+// win: tools/tune_step.py on cfg2, profiles/r02_tune_step_balanced.txt - 5.95 ms with fixed z segments, 6.46 with
+// 12 planes per CTA, 5.77 with 40, 5.60 with 40 (stride 1) / 80 (stride 2) / 160 (transposed).  `knob` (environment,
+// optional) sets the CTA count; ATVS_RING_MINPLANES overrides `minplanes` for every ring kernel (experiments)
+inline int ring_balanced_grid(long long total, long long slots, int minplanes, const char* knob1, const char* knob2) {
+    long long g = slots;
+    if (const char* e = getenv("ATVS_RING_MINPLANES")) minplanes = atoi(e) > 0 ? atoi(e) : minplanes;
+    if (total / g < minplanes) g = total / minplanes;
+    {   // small volumes: never fewer than 16 CTAs (of >= 6 planes) - a layer of 320 planes on 2 CTAs would serialise its pass
+        long long floor_g = total / 6 < 16 ? total / 6 : 16;
+        if (g < floor_g) g = floor_g;
+    }
+    const char* e = knob1 ? getenv(knob1) : nullptr;
+    if (!e && knob2) e = getenv(knob2);
+    if (e && atoi(e) > 0) g = atoi(e) < slots ? atoi(e) : slots;
+    if (g > total) g = total;
+    if (g < 1) g = 1;
+    return (int)g;
+}
 
 // z-segment length of a plane-ring kernel's work units.  A unit costs (planes + startup) plane steps, where `startup`
 // stands for the per-CTA fixed cost (TMEM allocation, weight image, pipeline fill) in plane steps.  The kernel shares

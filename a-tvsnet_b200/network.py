@@ -188,7 +188,10 @@ def conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=None,
                    L.ptr(raw), _raw_code(raw), L.ptr(stats), L.stream())
     if prof:
         e1.record()
-        PROFILE[1].append((wkey, e0, e1, raw.numel() // cout, cin, cout))
+        # last field: re-issues exactly this launch (same tensors), for back-to-back replays of one layer
+        again = lambda: conv3d_raw(x, wkey, w, cout, stride, transposed, want_stats, stats_buf=stats, bias=bias, out=raw,
+                                   raw_dtype=raw_dtype)
+        PROFILE[1].append((wkey, e0, e1, raw.numel() // cout, cin, cout, again))
     return raw, stats
 
 

@@ -12,18 +12,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import atvsnet_b200 as A
 
+# round 2, balanced plane ranges (ring_common.cuh RingSpan): CTAs per launch instead of z-segment lengths
 KNOBS = [
-    ("ATVS_RING_ZS_32_8", [None, 16, 22, 26, 32, 43, 64]),
-    ("ATVS_RING_ZS_8_8", [None, 16, 22, 26, 32, 43, 64]),
-    ("ATVS_RING_ZS_8_16", [None, 16, 26, 32, 43, 64]),
-    ("ATVS_RING_ZS_8_1", [None, 16, 26, 32, 43, 64]),
-    ("ATVS_RING_ZS_16_16", [None, 8, 16, 22, 32, 64]),
-    ("ATVS_S2_ZS_8_16", [None, 8, 13, 16, 22, 32, 64]),
-    ("ATVS_DRING_ZS", [None, 8, 11, 16, 22, 32]),
-    ("ATVS_PASSES", [None, 3, 4, 5, 6, 8]),
+    ("ATVS_DRING_CTAS", [None, 4, 8, 12, 16, 24]),
+    ("ATVS_S2_CTAS_8_16", [None, 12, 16, 24, 32, 48]),
+    ("ATVS_RING_CTAS_16_16", [None, 6, 8, 12, 16, 24]),
+    ("ATVS_RING_CTAS_8_8", [None, 32, 48, 64, 80, 100, 148]),
+    ("ATVS_RING_CTAS_32_8", [None, 64, 100, 148, 200]),
+    ("ATVS_RING_CTAS_8_16", [None, 64, 100, 148, 296]),
+    ("ATVS_RING_CTAS_8_1", [None, 64, 100, 148, 200]),
+    ("ATVS_RING_MINPLANES", [28, 40, 56]),
 ]
-START = {"ATVS_DRING_ZS": 16, "ATVS_RING_ZS_32_8": 26, "ATVS_RING_ZS_8_8": 26, "ATVS_RING_ZS_8_16": 26,
-         "ATVS_RING_ZS_16_16": 26, "ATVS_RING_ZS_8_1": 26, "ATVS_S2_ZS_8_16": 13}
+START = {"ATVS_RING_MINPLANES": 40, "ATVS_RING_CTAS_8_8": 100, "ATVS_RING_CTAS_8_1": 200, "ATVS_DRING_CTAS": 16}
 
 nv, h, w, D = 5, 128, 160, 128
 A.variables.load_weights(A.variables.synthetic_weights())
@@ -37,7 +37,7 @@ def apply(cfg):
     for k, v in cfg.items():
         if v is not None:
             os.environ[k] = str(v)
-    A.pipeline.CONCURRENT_PASSES = int(cfg.get("ATVS_PASSES") or 4)
+    A.pipeline.CONCURRENT_PASSES = int(cfg.get("ATVS_PASSES") or 8)
 
 
 def measure(cfg, steps=12):
