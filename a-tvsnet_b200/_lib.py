@@ -18,6 +18,7 @@ _SIGS = {
     "atvs_homography_warping": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_homography_warping_by_depth": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_build_cost_volume": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "atvs_build_cost_volume_src16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_conv3d_fp32": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "atvs_pack_conv_weights_tc": [_p, _i, _i, _i, _i, _p, _p],
     "atvs_conv3d_tc": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p],

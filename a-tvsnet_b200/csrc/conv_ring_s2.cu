@@ -428,9 +428,9 @@ int ring_s2_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, 
 bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout) {
     // Cin = 32 needs ~200 KB of ring planes per CTA: standalone it beats the per-tap TMA kernel (73 vs 88 us
     // at cfg2), but it monopolises the SM while the other streams of a step want to co-run (measured
-    // +0.25 ms per depth map), so it is opt-in (ATVS_RING_S2_CIN=32)
-    const char* e = getenv("ATVS_RING_S2_CIN");
-    if (e ? atoi(e) != Cin : Cin > 16) return false;
+    // +0.25 ms per depth map), so it is opt-in (ATVS_RING_S2_MAXCIN=32)
+    const char* e = getenv("ATVS_RING_S2_MAXCIN");
+    if (Cin > (e ? atoi(e) : 16)) return false;
     return ring_s2_supported(Cin, Cout) && ((D | H | W) & 1) == 0 && (long long)(D / 2) * (H / 2) * (W / 2) >= 131072 &&
            getenv("ATVS_NO_RING_S2") == nullptr;
 }

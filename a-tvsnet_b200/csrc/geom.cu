@@ -1196,6 +1196,26 @@ static int launch_k1(const float* ref, const float* view, const float* hv, const
     return 0;
 }
 
+// 16-bit K1 (k_build_cost_volume_h): the source feature map is 16-bit in the volume's own format
+static bool k1_h_supported(int F) { return F == 8 || F == 16 || F == 32 || F == 64 || F == 128; }
+static int launch_k1_h(const float* ref_feature, const uint16_t* vb, const float* homographies, int B, int D, int h, int w,
+                       int F, int mode, int out_dtype, uint16_t* o, cudaStream_t st) {
+    const int G8 = F / 8;
+    const int ppb = 256 / G8, ph = ppb >= 8 ? ppb / 8 : 1, pw = ppb / ph;
+    dim3 grid((unsigned)(((w + pw - 1) / pw) * ((h + ph - 1) / ph)), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
+#define K1H(M, G) do { if (out_dtype == ATVS_F16) k_build_cost_volume_h<M, G, true><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); \
+                       else k_build_cost_volume_h<M, G, false><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); } while (0)
+#define K1H_G(M) do { switch (G8) { case 1: K1H(M, 1); break; case 2: K1H(M, 2); break; case 4: K1H(M, 4); break; \
+                                     case 8: K1H(M, 8); break; default: K1H(M, 16); break; } } while (0)
+    if (mode == 0) K1H_G(0);
+    else if (mode == 1) K1H_G(1);
+    else K1H_G(2);
+#undef K1H_G
+#undef K1H
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* view_feature, const float* homographies,
                                       const float* ref_homographies, int B, int D, int h, int w, int F, int mode,
                                       int out_dtype, void* out, atvs_stream_t stream) {
@@ -1213,8 +1233,7 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
         return launch_k1<float>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
                                 (float*)out, st);
     const bool half_out = out_dtype == ATVS_BF16 || out_dtype == ATVS_F16;
-    if (half_out && !ref_homographies && F % 8 == 0 && (F == 8 || F == 16 || F == 32 || F == 64 || F == 128) &&
-        getenv("ATVS_K1_F32SRC") == nullptr) {
+    if (half_out && !ref_homographies && k1_h_supported(F) && getenv("ATVS_K1_F32SRC") == nullptr) {
         // 16-bit volume: gather from a 16-bit copy of the source feature map (stream-ordered scratch)
         uint16_t* vb = nullptr;
         const long long n = (long long)B * h * w * F;
@@ -1223,22 +1242,9 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
         if (out_dtype == ATVS_F16) k_f32_to_16<true><<<cgrid, 256, 0, st>>>(view_feature, vb, n / 4);
         else k_f32_to_16<false><<<cgrid, 256, 0, st>>>(view_feature, vb, n / 4);
         ATVS_LAUNCH_CHECK();
-        const int G8 = F / 8;
-        const int ppb = 256 / G8, ph = ppb >= 8 ? ppb / 8 : 1, pw = ppb / ph;
-        dim3 grid((unsigned)(((w + pw - 1) / pw) * ((h + ph - 1) / ph)), (unsigned)((D + K1_DCHUNK - 1) / K1_DCHUNK), (unsigned)B);
-        uint16_t* o = (uint16_t*)out;
-#define K1H(M, G) do { if (out_dtype == ATVS_F16) k_build_cost_volume_h<M, G, true><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); \
-                       else k_build_cost_volume_h<M, G, false><<<grid, 256, 0, st>>>(ref_feature, vb, homographies, D, h, w, o); } while (0)
-#define K1H_G(M) do { switch (G8) { case 1: K1H(M, 1); break; case 2: K1H(M, 2); break; case 4: K1H(M, 4); break; \
-                                     case 8: K1H(M, 8); break; default: K1H(M, 16); break; } } while (0)
-        if (mode == 0) K1H_G(0);
-        else if (mode == 1) K1H_G(1);
-        else K1H_G(2);
-#undef K1H_G
-#undef K1H
-        ATVS_LAUNCH_CHECK();
+        const int rc = launch_k1_h(ref_feature, vb, homographies, B, D, h, w, F, mode, out_dtype, (uint16_t*)out, st);
         ATVS_CUDA(cudaFreeAsync(vb, st));
-        return 0;
+        return rc;
     }
     if (out_dtype == ATVS_BF16)
         return launch_k1<__nv_bfloat16>(ref_feature, view_feature, homographies, ref_homographies, B, D, h, w, F, mode,
@@ -1248,6 +1254,22 @@ extern "C" int atvs_build_cost_volume(const float* ref_feature, const float* vie
                                  (__half*)out, st);
     atvs_set_error("atvs_build_cost_volume: out_dtype %d", out_dtype);
     return ATVS_E_DTYPE;
+}
+
+extern "C" int atvs_build_cost_volume_src16(const float* ref_feature, const void* view_feature16, const float* homographies,
+                                            int B, int D, int h, int w, int F, int mode, int dtype, void* out,
+                                            atvs_stream_t stream) {
+    ATVS_CHECK_ARG(view_feature16 && homographies && out && (mode == 1 || ref_feature), ATVS_E_NULL,
+                   "atvs_build_cost_volume_src16: NULL pointer");
+    ATVS_CHECK_ARG(B > 0 && B < 65536 && D > 0 && h > 1 && w > 1, ATVS_E_SHAPE,
+                   "atvs_build_cost_volume_src16: bad shape B=%d D=%d h=%d w=%d F=%d", B, D, h, w, F);
+    ATVS_CHECK_ARG(mode >= 0 && mode <= 2, ATVS_E_UNSUP, "atvs_build_cost_volume_src16: mode %d", mode);
+    ATVS_CHECK_ARG(dtype == ATVS_F16 || dtype == ATVS_BF16, ATVS_E_DTYPE, "atvs_build_cost_volume_src16: dtype %d", dtype);
+    ATVS_CHECK_ARG(k1_h_supported(F), ATVS_E_SHAPE, "atvs_build_cost_volume_src16: F=%d (8, 16, 32, 64 or 128)", F);
+    ATVS_CHECK_ARG((((uintptr_t)ref_feature | (uintptr_t)view_feature16 | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_build_cost_volume_src16: buffers must be 16-byte aligned");
+    return launch_k1_h(ref_feature, (const uint16_t*)view_feature16, homographies, B, D, h, w, F, mode, dtype, (uint16_t*)out,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int atvs_prob2depth(const float* prob_volume, int B, int D, int H, int W, const float* depth_start,

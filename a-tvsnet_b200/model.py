@@ -79,7 +79,13 @@ def build_cost_volume(ref_feature, view_feature, cams, depth_num, depth_start, d
     reference feature, streamed straight to the output volume (no warped stack/tile/concat
     intermediates).  ``mode``/``out_dtype`` are extensions (defaults = reference behaviour)."""
     L.require_cuda(ref_feature, view_feature, cams)
-    ref, view, cams = L.f32c(ref_feature), L.f32c(view_feature), L.f32c(cams)
+    # a 16-bit view feature map in the volume's own dtype (e.g. converted once per frame, pipeline.run_multiview) is
+    # gathered from directly: one launch, no per-call conversion
+    src16 = view_feature.dtype in (torch.float16, torch.bfloat16)
+    if src16 and (view_feature.dtype != out_dtype or warp_ref):
+        raise ValueError("build_cost_volume: a 16-bit view feature map needs out_dtype == its dtype and warp_ref=False")
+    ref, cams = L.f32c(ref_feature), L.f32c(cams)
+    view = view_feature.contiguous() if src16 else L.f32c(view_feature)
     B, h, w, F = ref.shape
     D = int(depth_num)
     ref_cam = cams[:, ref_id].contiguous()
@@ -90,8 +96,12 @@ def build_cost_volume(ref_feature, view_feature, cams, depth_num, depth_start, d
     m = _MODES[mode]
     cout = 2 * F if m == 0 else F
     out = torch.empty((B, D, h, w, cout), dtype=out_dtype, device=ref.device)
-    L.call("atvs_build_cost_volume", L.ptr(ref), L.ptr(view), L.ptr(hv), L.ptr(hr), B, D, h, w, F, m,
-           L.dtype_code(out), L.ptr(out), L.stream())
+    if src16:
+        L.call("atvs_build_cost_volume_src16", L.ptr(ref), L.ptr(view), L.ptr(hv), B, D, h, w, F, m, L.dtype_code(out),
+               L.ptr(out), L.stream())
+    else:
+        L.call("atvs_build_cost_volume", L.ptr(ref), L.ptr(view), L.ptr(hv), L.ptr(hr), B, D, h, w, F, m,
+               L.dtype_code(out), L.ptr(out), L.stream())
     return (out, hv) if output_homo else out
 
 

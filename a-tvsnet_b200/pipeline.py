@@ -18,8 +18,11 @@ SPLIT_COST_VOLUME = True
 CONCURRENT_PASSES = int(__import__('os').environ.get('ATVS_PASSES', '8'))
 
 
-def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid):
+def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid, v16=None):
+    """``v16``: the view's feature map already in the activation dtype (features_act): K1 gathers from it directly."""
     dt = N.act_dtype()
+    if dt in N.HALF_DTYPES and v16 is not None and v16.dtype == dt and v.shape[-1] in (8, 16, 32, 64, 128):
+        v = v16
     if dt in N.HALF_DTYPES and SPLIT_COST_VOLUME:
         # [tile(ref) | warped] kept as its halves: K1 writes only the warped 32 channels
         warped = build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid,
@@ -28,17 +31,25 @@ def _cost_volume(r, v, cams, depth_num, depth_start, depth_interval, rid, vid):
     return build_cost_volume(r, v, cams, depth_num, depth_start, depth_interval, ref_id=rid, view_id=vid, out_dtype=dt)
 
 
-def stage1_forward(features, cams, depth_num, depth_start, depth_interval, view_i):
+def features_act(features):
+    """(B,N,h,w,F) fp32 feature maps -> the same in the 16-bit activation dtype, ONE conversion per frame for all the
+    passes that warp a view (forward passes warp the sources, reverse passes the reference); None on the fp32 path."""
+    return N.to_act(features) if N.act_dtype() in N.HALF_DTYPES else None
+
+
+def stage1_forward(features, cams, depth_num, depth_start, depth_interval, view_i, features16=None):
     """forward half of TVSNet_base_siamese (model.py:409-411): ref <- view_i.  Returns the 8-ch
     filtered volume (activation dtype) and the prob logits (fp32)."""
-    cv = _cost_volume(features[:, 0], features[:, view_i], cams, depth_num, depth_start, depth_interval, 0, view_i)
+    cv = _cost_volume(features[:, 0], features[:, view_i], cams, depth_num, depth_start, depth_interval, 0, view_i,
+                      None if features16 is None else features16[:, view_i])
     tower = StackedUNet_prob({'data': cv}, outputs=('conv_b2_6_1', 'conv_b2_6_2'))
     return tower.get_output_by_name('conv_b2_6_1'), tower.get_output().squeeze(-1)
 
 
-def stage1_reverse(features, cams, depth_num, depth_start, depth_interval, view_i):
+def stage1_reverse(features, cams, depth_num, depth_start, depth_interval, view_i, features16=None):
     """reverse half (model.py:413-415): view_i as reference -> depth_view (B,h,w,1)."""
-    cvv = _cost_volume(features[:, view_i], features[:, 0], cams, depth_num, depth_start, depth_interval, view_i, 0)
+    cvv = _cost_volume(features[:, view_i], features[:, 0], cams, depth_num, depth_start, depth_interval, view_i, 0,
+                       None if features16 is None else features16[:, 0])
     pv = StackedUNet_prob({'data': cvv}, outputs=('conv_b2_6_2',)).get_output().squeeze(-1)
     return _prob2depth(pv, depth_start, depth_interval, 1, False)[0]
 
@@ -166,10 +177,12 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     att_raw = N.attention_raw_alloc(len(mine), torch.empty((B_, int(depth_num), h_, w_, 8), dtype=N.act_dtype(),
                                                            device='meta'), device=features.device)
 
+    feats16 = features_act(features)     # on the calling stream, before the passes fan out
+
     def run_task(v, kind):
         if kind == 'r':
-            return stage1_reverse(features, cams, depth_num, ds, di, v)
-        out = stage1_forward(features, cams, depth_num, ds, di, v)
+            return stage1_reverse(features, cams, depth_num, ds, di, v, feats16)
+        out = stage1_forward(features, cams, depth_num, ds, di, v, feats16)
         N.attention_raw_view(att_raw, mine.index(v), N.to_act(out[0]), 'attention_aggregate')
         return out
 

@@ -551,9 +551,16 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, act_dtype):
     V = D * h * w
     logits = torch.randn(1, D, h, w, device=feats_d.device)
 
-    def k1():
-        return A.build_cost_volume(feats_d[:, 0], feats_d[:, 1], cams_d, D, ds, di, 0, 1, mode='warped_only',
-                                   out_dtype=act_dtype)
+    feats16 = A.pipeline.features_act(feats_d)      # once per frame in the step (pipeline.run_multiview)
+    hv = A.get_homographies(cams_d[:, 0].contiguous(), cams_d[:, 1].contiguous(), depth_num=D, depth_start=ds,
+                            depth_interval=di)
+    cv_out = torch.empty((1, D, h, w, F), dtype=act_dtype, device=feats_d.device)
+    ref0, v16 = feats_d[:, 0].contiguous(), feats16[:, 1].contiguous()
+
+    def k1():       # the K1 kernel itself, through its C-ABI entry (homographies: a 4.7 us helper launch per pass)
+        A._lib.call("atvs_build_cost_volume_src16", A._lib.ptr(ref0), A._lib.ptr(v16), A._lib.ptr(hv), 1, D, h, w, F, 1,
+                    A._lib.dtype_code(cv_out), A._lib.ptr(cv_out), A._lib.stream())
+        return cv_out
 
     def k4up():
         return A.model._prob2depth(logits, ds, di, 4, False)
@@ -589,9 +596,9 @@ def hbm_kernel_lines(A, feats_d, cams_d, D, h, w, act_dtype):
 
     out = {}
     for name, fn, nbytes, note in (
-            ("K1 k_build_cost_volume_h (16-bit, warped-only)", k1, 4 * h * w * F + 2 * V * F,
-             "reads the fp32 source feature map once, writes the (D,h,w,32) 16-bit slice; the time includes K1's two "
-             "helper launches (homographies, fp32->16-bit source copy)"),
+            ("K1 k_build_cost_volume_h (16-bit, warped-only)", k1, 2 * h * w * F + 2 * V * F,
+             "reads the 16-bit source feature map (converted once per frame for all passes), writes the (D,h,w,32) 16-bit "
+             "slice; one launch of atvs_build_cost_volume_src16"),
             ("K4 k_prob2depth_up_sliced<4> (x4 upsample fused)", k4up, 4 * V + 4 * 16 * h * w,
              "reads the low-res logits once, writes the 4h x 4w depth map; instruction bound by construction (16*V "
              "interpolations + exponentials per 4*V bytes), see equivalent_unfused_gbs"),

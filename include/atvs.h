@@ -86,6 +86,12 @@ int atvs_build_cost_volume(const float* ref_feature, const float* view_feature,
                            const float* homographies, const float* ref_homographies, int B,
                            int D, int h, int w, int F, int mode, int out_dtype, void* out,
                            atvs_stream_t stream);
+/* The same with the source (view) feature map already 16-bit in the volume's own format `dtype` (ATVS_F16 | ATVS_BF16),
+ * e.g. converted once per frame for all the passes that warp it: one launch, no scratch (atvs_build_cost_volume makes
+ * that copy itself on every call).  ref_feature stays f32 (unused in mode 1).  F in {8, 16, 32, 64, 128}.        */
+int atvs_build_cost_volume_src16(const float* ref_feature, const void* view_feature16,
+                                 const float* homographies, int B, int D, int h, int w, int F,
+                                 int mode, int dtype, void* out, atvs_stream_t stream);
 
 /* ---- 3-D convolution primitives ------------------ network.py:142-215 (conv, conv_bn), 511-550
  * x (B,D,H,W,Cin) dtype `dtype`; kernel in TF layout: conv [3,3,3,Cin,Cout] f32, transposed

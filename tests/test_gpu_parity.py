@@ -327,12 +327,12 @@ def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
     xb = torch.from_numpy(x).to(half)
     wb = torch.from_numpy(w).to(half).float()
     A.variables.packed_cache().clear()
-    os.environ['ATVS_RING_S2_CIN'] = str(cin)          # Cin = 32 is opt-in (see ring_s2_applicable)
+    os.environ['ATVS_RING_S2_MAXCIN'] = '32'           # Cin = 32 is opt-in (see ring_s2_applicable)
     try:
         raw, stats = conv3d_raw(xb.cuda(), 's2ring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, False, True)
         torch.cuda.synchronize()
     finally:
-        del os.environ['ATVS_RING_S2_CIN']
+        del os.environ['ATVS_RING_S2_MAXCIN']
     ref = onet.conv3d(xb.float().numpy(), wb.numpy(), 2)
     assert raw.shape == ref.shape
     assert rel_err(npy(raw), ref) < 1e-4
@@ -472,6 +472,30 @@ def test_build_cost_volume_bf16_source(A, half):
         # adds on fp16-rounded weights), a few fp16 roundings of the largest term
         k = 1.0 if half == torch.bfloat16 or mode == 'l1_masked' else 4.0
         assert np.abs(got - ref).max() <= k * HALF_EPS[half] * np.abs(ref).max() + 1e-6, mode
+
+
+@HALF
+def test_build_cost_volume_src16_entry(A, half):
+    """atvs_build_cost_volume_src16 (16-bit view feature map handed in, as pipeline.run_multiview does once per frame)
+    is bit-identical to atvs_build_cost_volume converting the fp32 map itself, in all three modes; argument errors."""
+    h, w, D, F = 24, 40, 20, 32
+    cams = A.synthetic.orbit_cams(3, h, w, D)[None]
+    feats = A.synthetic.smooth_features(3, h, w, F, seed=6)[None]
+    ds, di = cams[:, 0, 1, 3, 0], cams[:, 0, 1, 3, 1]
+    v16 = cu(feats[:, 2]).to(half)
+    for mode in ('warped_only', 'concat', 'l1_masked'):
+        a = A.build_cost_volume(cu(feats[:, 0]), cu(feats[:, 2]), cu(cams), D, cu(ds), cu(di), 0, 2, mode=mode, out_dtype=half)
+        b = A.build_cost_volume(cu(feats[:, 0]), v16, cu(cams), D, cu(ds), cu(di), 0, 2, mode=mode, out_dtype=half)
+        assert torch.equal(a, b), mode
+    with pytest.raises(ValueError):
+        A.build_cost_volume(cu(feats[:, 0]), v16, cu(cams), D, cu(ds), cu(di), 0, 2)      # fp32 volume from a 16-bit map
+    other = torch.float16 if half == torch.bfloat16 else torch.bfloat16
+    with pytest.raises(ValueError):
+        A.build_cost_volume(cu(feats[:, 0]), v16, cu(cams), D, cu(ds), cu(di), 0, 2, out_dtype=other)
+    f12 = cu(feats[:, 2, :, :, :12]).contiguous().to(half)
+    with pytest.raises(RuntimeError):
+        A.build_cost_volume(cu(feats[:, 0, :, :, :12]).contiguous(), f12, cu(cams), D, cu(ds), cu(di), 0, 2,
+                            mode='warped_only', out_dtype=half)
 
 
 def test_conv3d_argument_errors(A):
