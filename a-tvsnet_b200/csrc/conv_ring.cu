@@ -395,6 +395,20 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
             const bool yok = y < p.H;
             const size_t obase = ((((size_t)un.b * p.D + un.z0) * p.H + (yok ? y : 0)) * p.W) * p.Cout + p.coff;
             const size_t zstride = (size_t)p.H * p.W * p.Cout;
+            // depth-invariant part of the layer (the tiled reference-feature half of the cost volume): the interior-plane
+            // class is the same for all but the first and last plane of the volume - fetched once per unit
+            // (8-channel layers only: wider accumulator rows would spill)
+            constexpr bool HOIST = (CP == 8);
+            float bint[HOIST ? RG_MT : 1][HOIST ? CP : 1];
+            if (HOIST && bias != nullptr && yok) {
+#pragma unroll
+                for (int mt = 0; mt < RG_MT; ++mt) {
+                    const int xm = xq + 8 * mt;
+                    const float* brow = bias + ((((size_t)un.b * 3 + 1) * p.H + y) * p.W + (xm < p.W ? xm : 0)) * p.Cout + p.coff;
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) bint[mt][c] = (c < p.ncols) ? __ldg(brow + c) : 0.f;
+                }
+            }
             for (int t = 0; t < un.zlen; ++t) {
                 mbar_wait(&tfull[grp], gphase);
                 TRACE(0);
@@ -429,8 +443,10 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                     const int xm = xq + 8 * mt;
                     if (xm >= p.W) continue;
                     const size_t ooff = obase + (size_t)t * zstride + (size_t)xm * p.Cout;
-                    if (bias != nullptr) {
-                        // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
+                    if (HOIST && bias != nullptr && zc == 1) {
+#pragma unroll
+                        for (int c = 0; c < CP; ++c) v[mt][c] += bint[HOIST ? mt : 0][HOIST ? c : 0];
+                    } else if (bias != nullptr) {
                         const float* brow = bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xm) * p.Cout + p.coff;
                         if (vec4) {
 #pragma unroll
