@@ -25,6 +25,7 @@ _SIGS = {
     "atvs_conv3d_tc_bias": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
     "atvs_bn_relu_add": [_p, _i, _p, _ll, _i, _f, _i, _p, _p, _p, _p, _i, _p],
     "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
+    "atvs_set_concurrency": [_i],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
     "atvs_add": [_p, _p, _p, _i, _ll, _p],
     "atvs_attention_combine": [_p, _p, _i, _ll, _i, _i, _p, _p],

@@ -49,6 +49,15 @@ static std::atomic<long long> g_launches{0};
 void atvs_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long atvs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// how many independent passes the caller runs side by side on its streams (pipeline.run_multiview): the plane-ring
+// kernels size their grids with it (ring_common.cuh ring_balanced_grid)
+static std::atomic<int> g_concurrency{1};
+int atvs_concurrency() { return g_concurrency.load(std::memory_order_relaxed); }
+extern "C" int atvs_set_concurrency(int n) {
+    g_concurrency.store(n < 1 ? 1 : (n > 64 ? 64 : n), std::memory_order_relaxed);
+    return 0;
+}
+
 static unsigned long long* g_sat[64] = {nullptr};
 unsigned long long* atvs_sat_ptr() {
     int dev = 0;

@@ -31,6 +31,7 @@ void atvs_count_launch();
 // device counter (one per device, allocated on first use - never during stream capture: every path is warmed up
 // eagerly first) of fp16 raw-output rows that had to be clamped to +-65504; read with atvs_saturation_count()
 unsigned long long* atvs_sat_ptr();
+int atvs_concurrency();          // api.cu: passes the caller runs side by side (atvs_set_concurrency)
 #define ATVS_LAUNCH_CHECK()              \
     do {                                 \
         atvs_count_launch();             \

@@ -475,7 +475,7 @@ int deconv_ring(const void* x16, int dtype, const void* wimg, int B, int D, int 
         p.total = (long long)B * p.nXT * p.nYT * D;
         p.balanced = 1;
         if (const char* e = getenv("ATVS_DRING_BALANCED")) p.balanced = atoi(e) != 0;
-        if (p.balanced) grid = ring_balanced_grid(p.total, (long long)sms * minb, 160, "ATVS_DRING_CTAS", nullptr);
+        if (p.balanced) grid = ring_balanced_grid(p.total, (long long)sms * minb, 20, 160, "ATVS_DRING_CTAS", nullptr);
     }
     const uint8_t* wi = (const uint8_t*)wimg;
     if (Cin == 16 && Cout == 8) return launch_dr<16, 8>((const uint16_t*)x16, p, wi, raw_out, stats, smem, grid, st);

@@ -656,7 +656,7 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
         else if (const char* e2 = getenv("ATVS_RING_BALANCED")) p.balanced = atoi(e2) != 0;
         if (p.balanced) {
             snprintf(name, sizeof(name), "ATVS_RING_CTAS_%d_%d", Cin, Cout);
-            grid = ring_balanced_grid(p.total, (long long)sms * minb, 40, name, "ATVS_RING_CTAS");
+            grid = ring_balanced_grid(p.total, (long long)sms * minb, 12, 40, name, "ATVS_RING_CTAS");
         }
     }
     for (int slab = 0; slab < nslabs; ++slab) {

@@ -486,7 +486,7 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
         if (p.balanced) {
             char name[48];
             snprintf(name, sizeof(name), "ATVS_S2_CTAS_%d_%d", Cin, Cout);
-            grid = ring_balanced_grid(p.total, (long long)sms * minb, 80, name, "ATVS_S2_CTAS");
+            grid = ring_balanced_grid(p.total, (long long)sms * minb, 20, 80, name, "ATVS_S2_CTAS");
         }
     }
     for (int slab = 0; slab < nslabs; ++slab) {

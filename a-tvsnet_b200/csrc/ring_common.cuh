@@ -116,12 +116,17 @@ struct RingSpan {
 
 // grid of a balanced launch: all resident slots, but at least `minplanes` planes per CTA.  A CTA's fixed cost (TMEM
 // allocation, weight image, pipeline fill, cold first loads) is worth ~10 plane steps, and a tensor CTA holds half an
-// SM's shared memory and TMEM columns while it lives, so in the whole step (8 passes on 8 streams) FEWER, LONGER CTAs
-// win: tools/tune_step.py on cfg2, profiles/r02_tune_step_balanced.txt - 5.95 ms with fixed z segments, 6.46 with
-// 12 planes per CTA, 5.77 with 40, 5.60 with 40 (stride 1) / 80 (stride 2) / 160 (transposed).  `knob` (environment,
-// optional) sets the CTA count; ATVS_RING_MINPLANES overrides `minplanes` for every ring kernel (experiments)
-inline int ring_balanced_grid(long long total, long long slots, int minplanes, const char* knob1, const char* knob2) {
+// SM's shared memory and TMEM columns while it lives.  A launch that has the GPU to itself wants many CTAs
+// (`alone` planes per CTA); in a step of 8 passes on 8 streams FEWER, LONGER CTAs win (`shared` planes per CTA:
+// tools/tune_step.py on cfg2, profiles/r02_tune_step_balanced.txt - 5.95 ms with fixed z segments, 6.46 with 12 planes
+// per CTA everywhere, 5.60 with 40 (stride 1) / 80 (stride 2) / 160 (transposed)), at the price of the launch's own
+// latency (a 16-CTA transposed convolution lasts 95 us instead of 33).  The caller says how many passes it runs side
+// by side (atvs_set_concurrency, 1 by default); in between the two settings are interpolated.
+// `knob1/knob2` (environment, optional) set the CTA count; ATVS_RING_MINPLANES overrides the planes per CTA.
+inline int ring_balanced_grid(long long total, long long slots, int alone, int shared, const char* knob1, const char* knob2) {
     long long g = slots;
+    const int conc = atvs_concurrency() < 8 ? atvs_concurrency() : 8;
+    int minplanes = alone + (shared - alone) * (conc - 1) / 7;
     if (const char* e = getenv("ATVS_RING_MINPLANES")) minplanes = atoi(e) > 0 ? atoi(e) : minplanes;
     if (total / g < minplanes) g = total / minplanes;
     {   // small volumes: never fewer than 16 CTAs (of >= 6 planes) - a layer of 320 planes on 2 CTAs would serialise its pass

@@ -178,6 +178,8 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
                                                            device='meta'), device=features.device)
 
     feats16 = features_act(features)     # on the calling stream, before the passes fan out
+    # scheduling hint for the persistent tensor kernels: `nstreams` passes share the SMs (fewer, longer CTAs per launch)
+    L.call("atvs_set_concurrency", nstreams)
 
     def run_task(v, kind):
         if kind == 'r':
@@ -210,6 +212,7 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
                 results[(v, kind)] = out
         for st in streams:
             main.wait_stream(st)
+    L.call("atvs_set_concurrency", 1)      # stage II runs alone on the calling stream
     filtered = [results[(v, 'f')][0] for v in mine]
     depth_views = [results[(v, 'r')] for v in mine] if siamese else [None for _ in mine]
     cost_agg = aggregate(filtered, 'attention_aggregate', group, rank, world, raw=att_raw)

@@ -166,6 +166,8 @@ def run_reference(args, rank, world):
 # ============================================================================ our arm
 def capture(step_fn, torch):
     """CUDA-graph capture of one step (after eager warm-up by the caller) -> (graph, output tensor)."""
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()        # the eager warm-up's cached blocks would sit beside the graph's private pool (cfg3: 2 x 80 GB)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -246,6 +248,8 @@ def run_ours(args, rank, world, local_rank):
     if use_graph:
         graph, out = capture(step, torch)
 
+    value_graphed = graph is not None
+
     def run_step():
         if graph is not None:
             graph.replay()
@@ -263,6 +267,11 @@ def run_ours(args, rank, world, local_rank):
     # inputs H2D and its depth map D2H; the copies of neighbouring frames overlap the step on their own streams
     fstream = None
     if graph is not None:
+        # the device-resident graph is done: release its private pool before FrameStream captures its own (cfg3 holds
+        # ~100 GB of intermediate volumes per captured step)
+        graph, res, out = None, None, None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         fstream = A.pipeline.FrameStream(tuple(feats_h.shape), tuple(cams_h.shape), D, dev, siamese=True)
         for dm in fstream.run([(feats_h, cams_h)] * 3):
             pass
@@ -342,7 +351,8 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": None, "peak_source": pk['src'] + " (sustained bf16 = fp16 rate of tcgen05.mma.kind::f16)",
                 "ms_per_launch": t_ms, "launches_timed": 3 * reps, "algorithmic_flops_per_launch": flops,
                 "timing": "the step's conv_b0_0_1 launch (its own tensors) re-issued %d times back to back as a CUDA graph, "
-                          "alone on the GPU, CUDA events around the replay on the launch stream, mean of 3 replays; "
+                          "alone on the GPU (grid as the library sizes it for a lone launch, atvs_set_concurrency(1)), CUDA events "
+                          "around the replay on the launch stream, mean of 3 replays; "
                           "ms_per_launch_in_step = CUDA events around each of the step's %d launches of this layer with the "
                           "step's %d streams sharing the SMs (eager pass); ms_per_launch_events_alone = the same with the "
                           "passes one after the other" % (reps, len(timings['in_step']) // 2, A.pipeline.CONCURRENT_PASSES),
@@ -436,7 +446,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": {"fp16": "fp16 operands / fp32 accumulate (tcgen05 kind::f16)", "bf16": "bf16", "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": common_config(workload, world, sharded),
-        "details": {"cuda_graph": graph is not None, "tensor_flops_per_step": flops_step,
+        "details": {"cuda_graph": value_graphed, "tensor_flops_per_step": flops_step,
                     "tensor_tflops_whole_step": flops_step * maps_per_step * args.steps / (ms_total * 1e-3) / 1e12 / world,
                     "weights": "variables.synthetic_weights() (seeded He-normal under the checkpoint names, logit gain 4); "
                                "tests/test_gpu_parity.py::test_cfg2_full_size_against_oracle checks this exact workload "

@@ -52,6 +52,11 @@ unsigned    atvs_crc32c(const void* data_host, size_t n, unsigned crc);
  * the tensor-path epilogues on the current device since the last reset; synchronises the device; -1 on error.  A
  * non-zero count means the checkpoint's feature scale does not fit fp16 raw storage: rerun with fp32 raw outputs. */
 long long   atvs_saturation_count(int reset);
+/* Scheduling hint (no effect on results): how many independent regularisation passes the caller runs side by side on
+ * its own streams - the 2*(N-1) passes of example.py:144-158 are independent.  The persistent tensor kernels launch
+ * all resident CTAs when a pass has the GPU to itself (n = 1, the default) and fewer, longer CTAs when n passes share
+ * the SMs.  Returns 0.                                                                                          */
+int         atvs_set_concurrency(int n);
 
 /* ---- get_homographies ------------------------------------------- homography_warping.py:179-227
  * left_cam/right_cam (B,2,4,4) f32, depth_start/depth_interval (B) f32 -> out (B,D,3,3) f32.
