@@ -101,3 +101,76 @@ def test_center_image():
     img = (rng.uniform(0, 255, (20, 30, 3))).astype(np.uint8)
     c = P.center_image(img)
     assert c.dtype == np.float32 and np.allclose(c.mean(axis=(0, 1)), 0, atol=1e-5) and np.allclose(c.std(axis=(0, 1)), 1, atol=1e-4)
+
+
+# ------------------------------------------------------------------ resize / crop / mask helpers (preprocess.py:39-100)
+@pytest.fixture(scope='module')
+def pgold():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden_preprocess.npz'))
+
+
+def test_scale_image_equals_reference_cv2(pgold):
+    """scale_image against the reference's own scale_image (= cv2.resize) run by tests/golden/make_golden_preprocess.py:
+    bit-exact for 8-bit images (OpenCV's fixed-point bilinear) and for 'nearest', 1e-6 for float images."""
+    from atvsnet_b200 import preprocess as P
+    img8, dep = pgold['img8'], pgold['dep']
+    for sc in (0.25, 0.5, 0.55, 0.8):
+        assert np.array_equal(P.scale_image(img8, sc), pgold['lin8_%g' % sc]), sc
+        assert np.array_equal(P.scale_image(img8, sc, 'nearest'), pgold['nn8_%g' % sc]), sc
+        assert np.array_equal(P.scale_image(dep, sc, 'nearest'), pgold['nnf_%g' % sc]), sc
+        got = P.scale_image(dep, sc)
+        assert got.dtype == np.float32 and got.shape == pgold['linf_%g' % sc].shape
+        assert np.abs(got - pgold['linf_%g' % sc]).max() <= 2e-6 * np.abs(dep).max(), sc
+    assert P.scale_image(img8, 0.5, 'cubic') is None          # the reference falls through for other modes
+    with pytest.raises(ValueError):
+        P.scale_image(img8[:1, :1], 0.25)
+
+
+def test_scale_image_live_cv2():
+    """where OpenCV is importable: random even-sized images and odd scales, bit-exact (8-bit) / 2e-6 (float)."""
+    cv2 = pytest.importorskip('cv2')
+    from atvsnet_b200 import preprocess as P
+    rng = np.random.default_rng(5)
+    for shape in ((48, 64, 3), (270, 480, 3), (64, 48), (120, 90, 1)):
+        img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        f = rng.standard_normal(shape).astype(np.float32)
+        for sc in (0.25, 0.5, 0.3, 0.4666666, 0.7, 0.9, 1.0):
+            ref = cv2.resize(img, None, fx=sc, fy=sc, interpolation=cv2.INTER_LINEAR).reshape(P.scale_image(img, sc).shape)
+            assert np.array_equal(P.scale_image(img, sc), ref), (shape, sc)
+            ref = cv2.resize(f, None, fx=sc, fy=sc, interpolation=cv2.INTER_LINEAR).reshape(P.scale_image(f, sc).shape)
+            assert np.abs(P.scale_image(f, sc) - ref).max() < 2e-6 * np.abs(f).max(), (shape, sc)
+
+
+def test_scale_crop_mask_equal_reference(pgold):
+    from atvsnet_b200 import preprocess as P
+    imgs, cams, depth = list(pgold['mvs_imgs']), list(pgold['mvs_cams']), pgold['mvs_depth']
+    si, sc, sd = P.scale_mvs_input([i.copy() for i in imgs], [c.copy() for c in cams], depth.copy(), scale=0.5)
+    assert np.array_equal(np.stack(si), pgold['mvs_scaled_imgs'])
+    assert np.array_equal(np.stack(sc), pgold['mvs_scaled_cams'])
+    assert np.array_equal(sd, pgold['mvs_scaled_depth'])
+    ci, cc, cd = P.crop_mvs_input([i.copy() for i in si], [c.copy() for c in sc], sd.copy(), base_image_size=32, max_h=64,
+                                  max_w=96)
+    assert np.array_equal(np.stack(ci), pgold['mvs_crop_imgs'])
+    assert np.array_equal(np.stack(cc), pgold['mvs_crop_cams'])
+    assert np.array_equal(cd, pgold['mvs_crop_depth'])
+    assert np.array_equal(np.stack(P.scale_mvs_camera([c.copy() for c in cc], 0.25)), pgold['mvs_scaled_cams_quarter'])
+    assert np.array_equal(P.mask_depth_image(pgold['dep'], 2.0, 8.0), pgold['mask_2_8'])
+    two = P.scale_mvs_input([imgs[0].copy()], [cams[0].copy()], scale=0.5)
+    assert len(two) == 2
+
+
+def test_crop_to_32_python2_arithmetic():
+    """BASELINE cfg3: a 1080 x 1920 frame is legal only after the crop to 1056 x 1920.  The reference
+    is Python 2: ``int(math.ceil(h / 32) * 32)`` floors first, so 1080 -> 1056 with 12 rows cut above and below, and
+    sizes above (max_h, max_w) are centre-cropped to them; the principal point follows the crop."""
+    from atvsnet_b200 import preprocess as P
+    img = np.zeros((1080, 1920, 3), np.uint8)
+    img[12:1068] = 7
+    cam = np.zeros((2, 4, 4))
+    cam[1, :3, :3] = [[1000.0, 0, 960.0], [0, 1000.0, 540.0], [0, 0, 1]]
+    (out,), (c,) = P.crop_mvs_input([img], [cam.copy()], base_image_size=32, max_h=2000, max_w=2000)
+    assert out.shape == (1056, 1920, 3) and (out == 7).all()
+    assert c[1][1][2] == 540.0 - 12 and c[1][0][2] == 960.0
+    (out,), (c,), d = P.crop_mvs_input([img], [cam.copy()], np.ones((1080, 1920)), base_image_size=32, max_h=480, max_w=896)
+    assert out.shape == (480, 896, 3) and d.shape == (480, 896)
+    assert c[1][1][2] == 540.0 - 300 and c[1][0][2] == 960.0 - 512
