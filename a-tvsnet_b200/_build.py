@@ -23,6 +23,7 @@ SOURCES = {
     "conv_ring_s2.cu": [],
     "conv_deconv.cu": [],
     "conv_deconv_ring.cu": [],
+    "conv_attn_ring.cu": [],
     "fem2d.cu": [],
     "fusion.cu": ["--fmad=false"],
 }

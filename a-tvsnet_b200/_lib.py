@@ -33,6 +33,7 @@ _SIGS = {
     "atvs_attention_partial": [_p, _p, _i, _ll, _i, _i, _p, _p, _p],
     "atvs_attention_finish": [_p, _ll, _i, _p, _p],
     "atvs_attention_raw": [_p, _i, _p, _i, _ll, _i, _i, _i, _p, _p, _p],
+    "atvs_attention_fused": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p],
     "atvs_conv2d_fp32": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "atvs_channel_moments": [_p, _ll, _i, _p, _p],
     "atvs_bn2d_apply": [_p, _p, _p, _ll, _i, _f, _i, _p, _i, _p],

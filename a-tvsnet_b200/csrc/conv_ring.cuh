@@ -27,3 +27,8 @@ int ring_s2_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, 
 bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout);
 int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H, int W, int Cin, int Cout, float* raw_out,
                  int raw16, double* stats, const float* bias, cudaStream_t st);
+
+// attention aggregation in one kernel (conv_attn_ring.cu): all views convolved 8 -> 16 per plane step, combined in the epilogue
+bool attn_ring_applicable(int n_views, int D, int H, int W);
+int attn_ring(const void* const* views, int n_views, int dtype, const void* wimg, int B, int D, int H, int W, float* out,
+              cudaStream_t st);

@@ -382,6 +382,24 @@ static int conv3d_tc_impl(const void* x16, int x_dtype, const void* wpacked, int
                           int stride, int transposed, const float* plane_bias, void* raw_out_v, int raw_dtype,
                           double* stats, atvs_stream_t stream);
 
+extern "C" int atvs_attention_fused(const void* const* x_views, int N, int x_dtype, const void* wpacked, int B, int D, int H,
+                                    int W, int C, float* out, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x_views && wpacked && out, ATVS_E_NULL, "atvs_attention_fused: NULL pointer");
+    ATVS_CHECK_ARG(x_dtype == ATVS_BF16 || x_dtype == ATVS_F16, ATVS_E_DTYPE,
+                   "atvs_attention_fused: x_dtype %d (ATVS_BF16 or ATVS_F16)", x_dtype);
+    ATVS_CHECK_ARG(C == 8, ATVS_E_UNSUP, "atvs_attention_fused: C=%d (8)", C);
+    ATVS_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, ATVS_E_SHAPE, "atvs_attention_fused: bad shape");
+    ATVS_CHECK_ARG(attn_ring_applicable(N, D, H, W), ATVS_E_UNSUP,
+                   "atvs_attention_fused: N=%d (2..8 views), D=%d (>= 3), H=%d, W=%d (>= 8)", N, D, H, W);
+    ATVS_CHECK_ARG((((uintptr_t)wpacked | (uintptr_t)out) & 15) == 0, ATVS_E_SHAPE,
+                   "atvs_attention_fused: buffers must be 16-byte aligned");
+    for (int n = 0; n < N; ++n)
+        ATVS_CHECK_ARG(x_views[n] && ((uintptr_t)x_views[n] & 15) == 0, ATVS_E_NULL,
+                       "atvs_attention_fused: view %d is NULL or not 16-byte aligned", n);
+    return attn_ring(x_views, N, x_dtype, (const char*)wpacked + tap_image_bytes(8, 16, 0), B, D, H, W, out,
+                     (cudaStream_t)stream);
+}
+
 extern "C" int atvs_conv3d_tc(const void* x16, int x_dtype, const void* wpacked, int B, int D, int H, int W, int Cin,
                               int Cout, int stride, int transposed, void* raw_out, int raw_dtype, double* stats,
                               atvs_stream_t stream) {

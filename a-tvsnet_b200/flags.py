@@ -32,6 +32,10 @@ class _Flags(object):
         # (atvs_saturation_count, pipeline.check_saturation): a clamped value is detected, never silent; set 'f32'
         # for a checkpoint whose features exceed ~1e3
         self.first_raw_dtype = 'f16'
+        # attention aggregation (AAM) of the 16-bit path as ONE kernel (atvs_attention_fused: the attention convolutions of
+        # all views + softmax over views + weighted sum, logits kept in TMEM) instead of one 8 -> 16 convolution per view
+        # + atvs_attention_raw; the sharded (multi-GPU) aggregation always uses the latter
+        self.attention_fused = True
 
 
 FLAGS = _Flags()

@@ -523,6 +523,15 @@ def stack_views(views):
     return torch.stack([v.reshape(nvox, c) for v in views], dim=0) if len(views) > 1 else views[0].reshape(1, nvox, c)
 
 
+def attention_fused_ok(views):
+    """the one-kernel AAM (atvs_attention_fused) covers 2..8 views of 8 channels in a 16-bit dtype, D >= 3, H, W >= 8"""
+    if not getattr(FLAGS, 'attention_fused', True) or not isinstance(views, (list, tuple)) or not 2 <= len(views) <= 8:
+        return False
+    v = views[0]
+    return (v.dtype in HALF_DTYPES and v.dim() == 5 and v.shape[-1] == 8 and v.shape[1] >= 3 and v.shape[2] >= 8
+            and v.shape[3] >= 8)
+
+
 def attention_aggregation(cost_volumes, scope, raw=None):
     """network.py:379-408 -> (B,D,H,W,C) fp32.  ``raw``: logits already produced by attention_raw_view()."""
     views = split_views(cost_volumes)
@@ -530,7 +539,13 @@ def attention_aggregation(cost_volumes, scope, raw=None):
     c = shape[-1]
     nvox = views[0].numel() // c
     out = torch.empty((nvox, c), dtype=torch.float32, device=views[0].device)
-    if c % 8 == 0:
+    if raw is None and attention_fused_ok(views):
+        key, w = _attention_weights(scope)
+        B, D, H, W_, _ = shape
+        pk = _packed_weight(key + '/packed', w, c, 2 * c, 0, views[0].dtype)
+        L.call("atvs_attention_fused", view_pointers(views), len(views), L.dtype_code(views[0]), L.ptr(pk), B, D, H, W_, c,
+               L.ptr(out), L.stream())
+    elif c % 8 == 0:
         if raw is None:
             raw = attention_activations_raw(views, scope)
         L.call("atvs_attention_raw", L.ptr(raw), _raw_code(raw), view_pointers(views), len(views), nvox, c,

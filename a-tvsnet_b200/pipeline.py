@@ -174,8 +174,10 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
     # attention logits (N,V,16), allocated on the calling stream before the passes fan out: every view's 8->16
     # attention convolution runs on that view's stream right behind its forward pass instead of in the serial tail
     B_, _, h_, w_, _ = features.shape
-    att_raw = N.attention_raw_alloc(len(mine), torch.empty((B_, int(depth_num), h_, w_, 8), dtype=N.act_dtype(),
-                                                           device='meta'), device=features.device)
+    like = torch.empty((B_, int(depth_num), h_, w_, 8), dtype=N.act_dtype(), device='meta')
+    # one-kernel AAM (atvs_attention_fused): no per-view logits at all; the sharded aggregation needs them
+    fused_att = group is None and N.attention_fused_ok([like] * len(mine))
+    att_raw = None if fused_att else N.attention_raw_alloc(len(mine), like, device=features.device)
 
     feats16 = features_act(features)     # on the calling stream, before the passes fan out
     # scheduling hint for the persistent tensor kernels: `nstreams` passes share the SMs (fewer, longer CTAs per launch)
@@ -185,7 +187,8 @@ def run_multiview(features, cams, depth_num, siamese=True, upsample=True, group=
         if kind == 'r':
             return stage1_reverse(features, cams, depth_num, ds, di, v, feats16)
         out = stage1_forward(features, cams, depth_num, ds, di, v, feats16)
-        N.attention_raw_view(att_raw, mine.index(v), N.to_act(out[0]), 'attention_aggregate')
+        if att_raw is not None:
+            N.attention_raw_view(att_raw, mine.index(v), N.to_act(out[0]), 'attention_aggregate')
         return out
 
     if nstreams == 1:

@@ -176,6 +176,14 @@ int atvs_attention_raw(const void* act_raw, int act_dtype /* ATVS_F32 | ATVS_F16
                        long long V, int C, int x_dtype, int mode, const float* gmax, float* out,
                        atvs_stream_t stream);
 
+/* The whole module in ONE kernel (csrc/conv_attn_ring.cu): the 8 -> 16 attention convolution [W_unique | W_shared] of
+ * every view, ReLU, softmax over the views and the weighted sum, with the logits kept in TMEM (never in HBM).
+ * network.py:282-351 + :379-408 for C = 8 channels and 2..8 views of one 16-bit dtype.
+ * x_views: HOST array of N device pointers, each (B,D,H,W,8) x_dtype; wpacked: atvs_pack_conv_weights_tc(Cin 8,
+ * Cout 16, not transposed) of the concatenated kernel, same dtype; out (B,D,H,W,8) fp32.  D >= 3, H, W >= 8.      */
+int atvs_attention_fused(const void* const* x_views, int N, int x_dtype /* ATVS_BF16 | ATVS_F16 */, const void* wpacked,
+                         int B, int D, int H, int W, int C, float* out, atvs_stream_t stream);
+
 /* ---- 2-D feature extraction module (FEM, ResNetDS2SPP) --- cnn_wrapper/atvsnet.py:254-292, network.py:142-215, 552-671
  * fp32 NHWC CUDA-core parity path of SURVEY.md 8(f) row N1; atvs_conv2d_tc below is the tensor-core path of its
  * stride-1 convolutions.

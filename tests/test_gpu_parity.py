@@ -585,6 +585,46 @@ def test_attention_aggregation(A, golden, gweights):
     assert rel_err(npy(keepb), golden['aam1_keep']) < 2e-2
 
 
+@HALF
+@pytest.mark.parametrize('nv,B,D,H,W', [(2, 1, 5, 11, 13), (3, 1, 8, 16, 24), (4, 2, 6, 20, 9), (4, 1, 16, 32, 40),
+                                         (5, 1, 4, 17, 8), (8, 1, 3, 8, 12)])
+def test_attention_fused(A, half, nv, B, D, H, W):
+    """atvs_attention_fused (one kernel: attention convolutions of all views in TMEM + softmax over views + weighted sum,
+    network.py:282-351, 379-408) against the oracle module on the SAME 16-bit-rounded views and weights (fp32 everywhere
+    else: only the summation order and exp2f differ), on ragged tiles, several view counts (kernels built for 2 / 4 / 8)
+    and batches; and against the two-kernel path, whose only difference is its fp16 storage of the logits."""
+    from oracle import network as onet
+    rng = np.random.default_rng(nv * 100 + D)
+    w = A.variables.synthetic_weights(seed=3)
+    ku, ks = 'attention_aggregate/attention_activation/weight_unique', 'attention_aggregate/attention_activation/weight_shared'
+    # logits of a few units, like a trained module's: scale the He-normal kernels up
+    w[ku] = (w[ku] * 3).astype(np.float32)
+    w[ks] = (w[ks] * 3).astype(np.float32)
+    A.variables.load_weights(w)
+    rnd = lambda a: torch.from_numpy(a).to(half).float().numpy()
+    xs = rnd(np.maximum(rng.standard_normal((B, D, H, W, 8, nv)), -0.5).astype(np.float32))
+    wo = dict(w)
+    wo[ku], wo[ks] = rnd(w[ku]), rnd(w[ks])
+    ref = onet.AttAggregation_keepchannel({'data': xs}, wo).get_output()
+    views = [cu(xs[..., n]).to(half) for n in range(nv)]
+    A.FLAGS.precision = PREC[half]
+    try:
+        assert A.network.attention_fused_ok(views)
+        A.cost_volume_aggregation(views, keepchannel=True)           # packs the weight image
+        n0 = A._lib.load().atvs_launch_count()
+        got = A.cost_volume_aggregation(views, keepchannel=True)
+        assert A._lib.load().atvs_launch_count() - n0 == 1          # ONE kernel
+        A.FLAGS.attention_fused = False
+        two = A.cost_volume_aggregation(views, keepchannel=True)
+    finally:
+        A.FLAGS.attention_fused = True
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+    assert got.shape == (B, D, H, W, 8) and got.dtype == torch.float32
+    scale = np.abs(ref).max()
+    assert np.abs(npy(got) - ref).max() < 2e-5 * scale, np.abs(npy(got) - ref).max() / scale
+    assert np.abs(npy(two) - npy(got)).max() < 64 * HALF_EPS[torch.float16] * scale      # fp16 logits of the two-kernel path
+
+
 def test_prob2depth(A, golden):
     from oracle import model as om
     vol, ds, di = golden['p2d_vol'], golden['p2d_start'], golden['p2d_interval']
