@@ -338,12 +338,32 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
     return bytes;
 }
 
+#ifndef TC_SHARED_MINTILES
+#define TC_SHARED_MINTILES 1
+#endif
 static size_t tap_image_bytes(int Cin, int Cout, int transposed) {
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);
     size_t elems = 0;
     const int ncls = transposed ? 8 : 1;
     for (int c = 0; c < ncls; ++c) elems += (size_t)ntaps_padded(Cin, transposed, c) * sp.nslabs * sp.npad * Cin;
     return (elems * 2 + 255) & ~(size_t)255;
+}
+
+// CTAs of a per-tap launch.  Every CTA pays a fixed cost (TMEM allocation, all taps' weights into shared memory, pipeline
+// fill) worth several tiles; a launch that owns the GPU wants one CTA per SM, but in a step whose passes share the SMs
+// (atvs_set_concurrency > 1) fewer CTAs with more tiles each spend less SM time on the same work.
+// ATVS_TC_MINTILES: tiles per CTA when the SMs are shared.
+static int tc_grid(long long nwork, int sms) {
+    int mint = 1;
+    if (atvs_concurrency() > 1) {
+        mint = TC_SHARED_MINTILES;
+        if (const char* e = getenv("ATVS_TC_MINTILES")) mint = atoi(e) > 0 ? atoi(e) : mint;
+    }
+    long long g = nwork / mint;
+    if (g < 1) g = 1;
+    if (g > sms) g = sms;
+    if (g > nwork) g = nwork;
+    return (int)g;
 }
 
 extern "C" int atvs_pack_conv_weights_tc(const float* kernel, int Cin, int Cout, int transposed, int dtype, void* wpacked,
@@ -577,7 +597,7 @@ static int conv3d_tc_impl(const void* x_bf16, int x_dtype, const void* wpacked, 
             const size_t smem = 1024 + wbytes + (size_t)nst * stage_bytes + (2 * nst + 5) * 8 + 16;
             const int sms = atvs_num_sms();
             const long long nwork = p.ntiles * p.ncls;
-            const int grid = (int)(nwork < sms ? nwork : sms);
+            const int grid = tc_grid(nwork, sms);
             int rc = 0;
 #define TC_CASE(CI, NP) if (Cin == CI && sp.npad == NP) rc = launch_tc<CI, NP>(maps, p, raw_out, stats, plane_bias, smem, grid, st); else
             TC_CASE(8, 16) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32) TC_CASE(32, 64)

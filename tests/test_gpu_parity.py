@@ -622,7 +622,9 @@ def test_attention_fused(A, half, nv, B, D, H, W):
     assert got.shape == (B, D, H, W, 8) and got.dtype == torch.float32
     scale = np.abs(ref).max()
     assert np.abs(npy(got) - ref).max() < 2e-5 * scale, np.abs(npy(got) - ref).max() / scale
-    assert np.abs(npy(two) - npy(got)).max() < 64 * HALF_EPS[torch.float16] * scale      # fp16 logits of the two-kernel path
+    d2 = np.abs(npy(two) - npy(got)).max() / scale
+    print("attention fused vs two-kernel path (fp16 logits): max diff / scale %.2e" % d2)
+    assert d2 < 16 * HALF_EPS[torch.float16]
 
 
 def test_prob2depth(A, golden):
