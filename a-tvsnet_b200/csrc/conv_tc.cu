@@ -339,7 +339,7 @@ extern "C" size_t atvs_packed_weight_bytes(int Cin, int Cout, int transposed) {
 }
 
 #ifndef TC_SHARED_MINTILES
-#define TC_SHARED_MINTILES 1
+#define TC_SHARED_MINTILES 4      // whole cfg2 step: 5.51 (1) 5.47 (2) 5.45 (4) 5.45 (6) 5.47 (8) 5.71 ms (12)
 #endif
 static size_t tap_image_bytes(int Cin, int Cout, int transposed) {
     const SlabPlan sp = plan_slabs(Cin, Cout, transposed ? 8 : 27);

@@ -57,7 +57,7 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.skip = [], None, gpu_index, 0
 
     def start(self):
         try:
@@ -73,6 +73,16 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def wait_first(self, timeout=8.0):
+        """block until nvidia-smi delivers its first sample (its start-up takes 0.1-1 s, longer with 8 ranks starting one
+        each), then forget what was sampled so far: everything kept from here on falls inside the timed region."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.skip = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
@@ -82,7 +92,7 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in self.rows[self.skip:]:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -258,8 +268,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- timed region 1: inputs resident in HBM ----------------
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    sampler.wait_first()
+    barrier()
     ms_total, res = timed_steps(run_step, args.steps, torch, barrier)
 
     # ---------------- timed region 2: end to end from / to pinned host memory ----------------
@@ -506,9 +517,20 @@ def run_sharded_cfg3(A, dist, torch, dev, rank, world, local_rank, barrier, step
 
     for _ in range(2):
         o = step_sh()
-    sampler = ClockSampler(local_rank)
+    # enough steps for >= ~0.7 s of timed region (the 50 ms clock sampler must see it: 5 steps at 8 GPUs are 0.12 s)
     barrier()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    o = step_sh()
+    w1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    steps = int(min(40, max(steps, 700.0 / max(float(est[0]), 1.0) + 1)))
+    sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
+    barrier()
     ms, o = timed_steps(step_sh, steps, torch, barrier)
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
