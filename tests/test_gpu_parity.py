@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 HALF = pytest.mark.parametrize('half', [torch.float16, torch.bfloat16], ids=['f16', 'bf16'])
 HALF_EPS = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}
 PREC = {torch.float16: 'fp16', torch.bfloat16: 'bf16'}
+MAXB_CRM = 0.04     # bf16 (k = 1): max elementwise CRM error / range (measured 1.1e-2); fp16 is held to an 8th of it (measured 2.3e-3)
 
 
 @pytest.fixture(scope='module')
@@ -116,6 +117,19 @@ def test_build_cost_volume(A, golden):
     assert np.array_equal(cv, om.build_cost_volume(ref, view, c, 4, ds, di, 0, 1))
     bad = np.abs(cv - golden['cv_concat']).max(axis=-1) > 2e-4 * np.abs(cv).max()
     assert bad.mean() < 1e-3
+    # WHICH voxels differ from the reference-code golden: only samples that land within 2e-3 px of the validity boundary
+    # (x = 0 | W-1, y = 0 | H-1, homography_warping.py:39-43), where the golden's LAPACK matrix inverse and the cofactor
+    # inverse used here (homographies equal to 5e-6) put the sample on different sides of the strict mask
+    from oracle import homography_warping as ohw_
+    Hs = ohw_.get_homographies(c[:, 0], c[:, 1], 4, ds, di).astype(np.float64)
+    hh, ww = view.shape[1:3]
+    ys, xs = np.mgrid[0:hh, 0:ww]
+    pix = np.stack([xs + 0.5, ys + 0.5, np.ones_like(xs, dtype=np.float64)], 0).reshape(3, -1)
+    for d in range(4):
+        q = Hs[0, d] @ pix
+        x, y = q[0] / q[2] - 0.5, q[1] / q[2] - 0.5
+        edge = (np.abs(x) < 2e-3) | (np.abs(y) < 2e-3) | (np.abs(x - (ww - 1)) < 2e-3) | (np.abs(y - (hh - 1)) < 2e-3)
+        assert not (bad[0, d].reshape(-1) & ~edge).any(), (d, int((bad[0, d].reshape(-1) & ~edge).sum()))
     cv, H = A.build_cost_volume(cu(view), cu(ref), cu(c), 4, cu(ds), cu(di), 1, 0, output_homo=True)
     assert np.array_equal(npy(cv), om.build_cost_volume(view, ref, c, 4, ds, di, 1, 0))
     assert H.shape == (1, 4, 3, 3)
@@ -557,9 +571,15 @@ def test_cost_volume_reasoning_bf16(A, golden, gweights, half):
     # the 11-bit format)
     k = HALF_EPS[half] / 2.0 ** -8
     e = np.abs(npy(filt) - golden['crm_filtered'])
+    s_f = np.abs(golden['crm_filtered']).max()
     assert e.mean() < k * (0.03 * np.abs(golden['crm_filtered']).mean() + 0.03)
-    e = np.abs(npy(prob) - golden['crm_prob'])
-    assert e.mean() < k * 0.05 * np.abs(golden['crm_prob']).std()
+    e2 = np.abs(npy(prob) - golden['crm_prob'])
+    s_p = np.abs(golden['crm_prob']).max()
+    print("CRM %s vs reference-graph golden: filtered mean %.2e max %.2e of max|x|, logits mean %.2e max %.2e of max|x|"
+          % (PREC[half], e.mean() / s_f, e.max() / s_f, e2.mean() / s_p, e2.max() / s_p))
+    assert e2.mean() < k * 0.05 * np.abs(golden['crm_prob']).std()
+    # elementwise: no voxel further than MAXB of the tensor's range from the reference-graph value
+    assert e.max() < k * MAXB_CRM * s_f and e2.max() < k * MAXB_CRM * s_p
 
 
 def test_attention_aggregation(A, golden, gweights):
@@ -624,7 +644,7 @@ def test_attention_fused(A, half, nv, B, D, H, W):
     assert np.abs(npy(got) - ref).max() < 2e-5 * scale, np.abs(npy(got) - ref).max() / scale
     d2 = np.abs(npy(two) - npy(got)).max() / scale
     print("attention fused vs two-kernel path (fp16 logits): max diff / scale %.2e" % d2)
-    assert d2 < 16 * HALF_EPS[torch.float16]
+    assert d2 < 4 * HALF_EPS[torch.float16]          # measured 4-7e-4
 
 
 def test_prob2depth(A, golden):
