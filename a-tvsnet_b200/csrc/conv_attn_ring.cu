@@ -72,6 +72,19 @@ __device__ __forceinline__ int aunit_iend(const AttnParams& p, const AUnit& u) {
     return (u.z0 + u.zlen == p.D) ? u.zlen : u.zlen + 1;
 }
 
+// softmax over <= 8 views: arguments are <= 0 (max subtracted), a flushed-to-zero tail and 1-2 ulp are far below the
+// 16-bit operands' rounding; exp2f() / IEEE division cost 6-8 instructions each, 40 of them per voxel
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool F16>
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -300,22 +313,19 @@ k_attention_ring(const __grid_constant__ AttnParams p, const uint8_t* __restrict
                 const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + grp * (uint32_t)AR_CP;
                 uint64_t* const tempty_bar = &tempty[grp];
                 if (++grp == (uint32_t)G) { grp = 0; gphase ^= 1; }
+                // l_n = relu(u_n) - relu(s_n): the "+ sum_m s_m" of network.py:344 is the same for every view and cancels in
+                // the softmax over views (as in the sharded form, pipeline.aggregate), so it is not formed at all
                 float a[NMAX][8];
-                float S[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) S[q] = 0.f;
 #pragma unroll
                 for (int n = 0; n < NMAX; ++n) {
                     if (n < NV) {
+                        // one view per TMEM round trip: two at a time costs the 4-view build (96 registers at two CTAs
+                        // per SM) 80 bytes of spills and 14 us
                         float us[16];
                         tc_ld16(taddr + (uint32_t)n * VIEW_COLS, us);
                         tc_wait_ld();
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float sq = fmaxf(us[8 + q], 0.f);
-                            a[n][q] = fmaxf(us[q], 0.f) - sq;
-                            S[q] = (n == 0) ? sq : S[q] + sq;
-                        }
+                        for (int q = 0; q < 8; ++q) a[n][q] = fmaxf(us[q], 0.f) - fmaxf(us[8 + q], 0.f);
                         tc_st8_zero(taddr + (uint32_t)n * VIEW_COLS);
                         tc_st8_zero(taddr + (uint32_t)n * VIEW_COLS + 8);
                     }
@@ -325,40 +335,32 @@ k_attention_ring(const __grid_constant__ AttnParams p, const uint8_t* __restrict
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
                 if (!ok) continue;
-                float m[8], den[8], res[8];
+                constexpr float LOG2E = 1.4426950408889634f;
+                float mneg[8], den[8], res[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float mm = -INFINITY;
+                    float mm = a[0][q];
 #pragma unroll
-                    for (int n = 0; n < NMAX; ++n)
-                        if (n < NV) {
-                            a[n][q] += S[q];
-                            mm = fmaxf(mm, a[n][q]);
-                        }
-                    m[q] = mm;
+                    for (int n = 1; n < NMAX; ++n)
+                        if (n < NV) mm = fmaxf(mm, a[n][q]);
+                    mneg[q] = -mm * LOG2E;
                     den[q] = 0.f;
                     res[q] = 0.f;
                 }
 #pragma unroll
                 for (int n = 0; n < NMAX; ++n)
                     if (n < NV) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            a[n][q] = exp2f((a[n][q] - m[q]) * 1.4426950408889634f);
-                            den[q] += a[n][q];
-                        }
-                    }
-                float inv[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) inv[q] = 1.0f / den[q];
-#pragma unroll
-                for (int n = 0; n < NMAX; ++n)
-                    if (n < NV) {
                         float xx[8];
                         unpack8<F16>(xr[n], xx);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) res[q] = fmaf(a[n][q] * inv[q], xx[q], res[q]);
+                        for (int q = 0; q < 8; ++q) {
+                            const float e = ex2_approx(fmaf(a[n][q], LOG2E, mneg[q]));      // exp(l_n - max)
+                            den[q] += e;
+                            res[q] = fmaf(e, xx[q], res[q]);
+                        }
                     }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) res[q] *= rcp_approx(den[q]);
                 float4* o = reinterpret_cast<float4*>(out + voff);
                 o[0] = make_float4(res[0], res[1], res[2], res[3]);
                 o[1] = make_float4(res[4], res[5], res[6], res[7]);

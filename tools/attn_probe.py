@@ -36,7 +36,7 @@ def timed(fn, iters=10):
 
 V = D * H * W
 alg = nv * V * 16 + V * 32
-for fused in (True, False):
+for fused in ((True,) if os.environ.get("FUSED_ONLY") else (True, False)):
     A.FLAGS.attention_fused = fused
     us = timed(lambda: A.cost_volume_aggregation(views, keepchannel=True))
     print(json.dumps({"fused": fused, "us": us, "knobs": {k: v for k, v in os.environ.items() if k.startswith('ATVS_ATTN')},
