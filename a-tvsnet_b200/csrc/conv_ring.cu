@@ -134,7 +134,7 @@ __device__ __forceinline__ void ring_window(int f, int len, uint32_t& row_off_by
     }
 }
 
-template <int CIN, int CP, int MT, int MINB>
+template <int CIN, int CP, int MT, int MINB, bool FAST>
 __global__ void __launch_bounds__(RG_THREADS, MINB)
 k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams p,
               const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
@@ -390,6 +390,11 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
         for (int k = 0; k < 2 * CP; ++k) run[k] = 0.f;
         const bool vec4 = (p.ncols & 3) == 0 && (p.Cout & 3) == 0;
         const int vec = raw_vec_mode(out, p.ncols, p.Cout, p.coff);
+        // the CRM's layers: full slab of CP columns, saturated fp16 rows of whole 16-byte groups.  Their plane step is bound by
+        // this warp's instruction stream (one epilogue warp per SM sub-partition and CTA: ~270 dependent instructions per
+        // plane through the generic row store with its per-column predicates and 64-bit index arithmetic), so they take a
+        // straight-line path: no column predicates, row pointer carried from plane to plane.
+        constexpr bool fast = FAST;      // host: ncols == CP, 32-byte aligned fp16 rows (ring_conv)
         uint32_t grp = 0, gphase = 0;
         const bool late_release = RING_LATE_RELEASE && !(p.dbg & 16);      // ATVS_RING_DEBUG bit 16: release before the stores
         TRACE_DECL
@@ -400,6 +405,7 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
             const bool yok = y < p.H;
             const size_t obase = ((((size_t)un.b * p.D + un.z0) * p.H + (yok ? y : 0)) * p.W) * p.Cout + p.coff;
             const size_t zstride = (size_t)p.H * p.W * p.Cout;
+            __half* orow16 = reinterpret_cast<__half*>(out) + obase + (size_t)xq * p.Cout;    // fast path: this thread's row, plane t
             // depth-invariant part of the layer (the tiled reference-feature half of the cost volume): the interior-plane
             // class is the same for all but the first and last plane of the volume - fetched once per unit
             // (8-channel layers only: wider accumulator rows would spill)
@@ -446,7 +452,49 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                 if (!late_release) release();
                 TRACE(2);
                 TRACE_NEXT();
-                if (yok && !(p.dbg & 4)) {
+                if (FAST && yok && !(p.dbg & 4)) {
+                    const int z = un.z0 + t;
+                    const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
+#pragma unroll
+                    for (int mt = 0; mt < RG_MT; ++mt) {
+                        const int xm = xq + 8 * mt;
+                        if (xm < p.W) {
+                            if (bias != nullptr) {
+                                if (HOIST && zc == 1) {
+#pragma unroll
+                                    for (int c = 0; c < CP; ++c) v[mt][c] += bint[HOIST ? mt : 0][HOIST ? c : 0];
+                                } else {
+                                    const float4* brow = reinterpret_cast<const float4*>(
+                                        bias + ((((size_t)un.b * 3 + zc) * p.H + y) * p.W + xm) * p.Cout + p.coff);
+#pragma unroll
+                                    for (int c = 0; c < CP; c += 4) {
+                                        const float4 bv = __ldg(brow + (c >> 2));
+                                        v[mt][c] += bv.x; v[mt][c + 1] += bv.y; v[mt][c + 2] += bv.z; v[mt][c + 3] += bv.w;
+                                    }
+                                }
+                            }
+                            float m = fabsf(v[mt][0]);
+#pragma unroll
+                            for (int c = 1; c < CP; ++c) m = fmaxf(m, fabsf(v[mt][c]));
+                            if (m > 65504.f) atomicAdd(p.sat, 1ULL);
+                            __half* op = orow16 + mt * 8 * p.Cout;
+#pragma unroll
+                            for (int c = 0; c < CP; c += 8) {
+                                uint4 u;
+                                u.x = pack_f16x2_sat(v[mt][c], v[mt][c + 1]); u.y = pack_f16x2_sat(v[mt][c + 2], v[mt][c + 3]);
+                                u.z = pack_f16x2_sat(v[mt][c + 4], v[mt][c + 5]); u.w = pack_f16x2_sat(v[mt][c + 6], v[mt][c + 7]);
+                                *reinterpret_cast<uint4*>(op + c) = u;
+                            }
+                            if (stats != nullptr) {
+#pragma unroll
+                                for (int c = 0; c < CP; ++c) {
+                                    run[c] += v[mt][c];
+                                    run[CP + c] = fmaf(v[mt][c], v[mt][c], run[CP + c]);
+                                }
+                            }
+                        }
+                    }
+                } else if (!FAST && yok && !(p.dbg & 4)) {
                 const int z = un.z0 + t;
                 const int zc = (z == 0) ? 0 : (z == p.D - 1 ? 2 : 1);
 #pragma unroll
@@ -483,6 +531,7 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                     }
                 }
                 }
+                orow16 += zstride;
                 if (late_release) release();
             }
         }
@@ -542,17 +591,27 @@ __global__ void k_pack_ring(const float* __restrict__ w, int Cin, int Cout, int 
     }
 }
 
+template <int CIN, int CP, int MT, int MINB, bool FAST>
+int launch_ring1(const uint16_t* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
+                 const float* bias, size_t smem, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, CP, MT, MINB, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    k_conv3d_ring<CIN, CP, MT, MINB, FAST><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
+// FAST epilogue: the slab fills its CP columns and the rows are saturated fp16 in whole, 32-byte aligned groups of 8
 template <int CIN, int CP, int MT, int MINB>
 int launch_ring(const uint16_t* x, const RingParams& p, const uint8_t* wimg, float* out, double* stats,
                 const float* bias, size_t smem, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring<CIN, CP, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    k_conv3d_ring<CIN, CP, MT, MINB><<<grid, RG_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
-    ATVS_LAUNCH_CHECK();
-    return 0;
+    const bool fast = p.ncols == CP && p.raw16 && ((p.Cout | p.coff) & 7) == 0 && (((uintptr_t)out) & 31) == 0 &&
+                      (bias == nullptr || (((uintptr_t)bias) & 15) == 0) && !(p.dbg & 32);
+    return fast ? launch_ring1<CIN, CP, MT, MINB, true>(x, p, wimg, out, stats, bias, smem, grid, st)
+                : launch_ring1<CIN, CP, MT, MINB, false>(x, p, wimg, out, stats, bias, smem, grid, st);
 }
 
 size_t ring_slab_bytes(int Cin, int cp) {
