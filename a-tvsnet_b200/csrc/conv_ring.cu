@@ -642,7 +642,10 @@ int ring_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, cud
 }
 
 bool ring_applicable(int B, int D, int H, int W, int stride, int transposed) {
-    const long long minvox = getenv("ATVS_RING_MINVOX") ? atoll(getenv("ATVS_RING_MINVOX")) : 65536;
+    // smaller volumes: the per-tap TMA kernel (conv_tc.cu).  Alone it is as fast there, but it fetches every input voxel 27
+    // times through L2 and spends 5 x the SM time of the ring on a 32 -> 32 layer of 32x32x40 voxels: inside the step the
+    // ring wins from ~32k voxels (5.21 -> 5.05 ms per cfg2 depth map with the threshold lowered from 65536)
+    const long long minvox = getenv("ATVS_RING_MINVOX") ? atoll(getenv("ATVS_RING_MINVOX")) : 32768;
     return !transposed && stride == 1 && (long long)D * H * W >= minvox && H >= 8 && W >= 8;
 }
 

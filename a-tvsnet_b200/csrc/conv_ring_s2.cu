@@ -425,13 +425,17 @@ int ring_s2_pack(const float* kernel, int Cin, int Cout, int dtype, void* wimg, 
     return 0;
 }
 
+#ifndef RING_S2_MINVOX
+#define RING_S2_MINVOX 32768       // output voxels from which the plane ring replaces the per-tap TMA kernel (131072 -> 32768: 5.03 -> 5.00 ms per cfg2 depth map)
+#endif
 bool ring_s2_applicable(int B, int D, int H, int W, int Cin, int Cout) {
     // Cin = 32 needs ~200 KB of ring planes per CTA: standalone it beats the per-tap TMA kernel (73 vs 88 us
     // at cfg2), but it monopolises the SM while the other streams of a step want to co-run (measured
     // +0.25 ms per depth map), so it is opt-in (ATVS_RING_S2_MAXCIN=32)
     const char* e = getenv("ATVS_RING_S2_MAXCIN");
     if (Cin > (e ? atoi(e) : 16)) return false;
-    return ring_s2_supported(Cin, Cout) && ((D | H | W) & 1) == 0 && (long long)(D / 2) * (H / 2) * (W / 2) >= 131072 &&
+    const long long minvox = getenv("ATVS_RING_S2_MINVOX") ? atoll(getenv("ATVS_RING_S2_MINVOX")) : RING_S2_MINVOX;
+    return ring_s2_supported(Cin, Cout) && ((D | H | W) & 1) == 0 && (long long)(D / 2) * (H / 2) * (W / 2) >= minvox &&
            getenv("ATVS_NO_RING_S2") == nullptr;
 }
 
@@ -457,6 +461,7 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
     int nring = (int)((budget - fixed) / slot);
     if (nring > 8) nring = 8;
     if (const char* e = getenv("ATVS_RING_R")) nring = atoi(e) < nring ? atoi(e) : nring;
+    if (const char* e = getenv("ATVS_S2_R")) nring = atoi(e) < nring && atoi(e) >= 2 ? atoi(e) : nring;
     if (nring < 2) {
         atvs_set_error("atvs_conv3d_bf16(ring s2): weights do not fit next to 2 ring planes (Cin=%d Cout=%d)", Cin, Cout);
         return ATVS_E_UNSUP;
