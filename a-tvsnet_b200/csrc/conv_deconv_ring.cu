@@ -298,7 +298,7 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
         for (int k = 0; k < 2 * COUT; ++k) run[k] = 0.f;
         float vmax = 0.f;
         const int vec = raw_vec_mode(out, COUT, COUT, 0);
-        const bool fast16 = p.raw16 && COUT == 8 && (((uintptr_t)out) & 31) == 0;
+        const bool fast16 = p.raw16 && (COUT % 8) == 0 && (((uintptr_t)out) & 31) == 0;
         const int Ho = 2 * p.H, Wo = 2 * p.W, Do = 2 * p.D;
         // a unit starts on an even group and consumes an even number of groups: set s only ever sees groups of parity s
         uint32_t grp = (uint32_t)set, gphase = 0;
@@ -335,7 +335,10 @@ k_deconv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ DrParams
                     // classes (py, 0) and (py, 1) are x neighbours: 2 * Cout contiguous output values
                     const size_t off = ((((size_t)un.b * Do + oz) * Ho + (2 * y + py)) * Wo + 2 * xq) * COUT;
                     const float* vv = v + py * 2 * COUT;
-                    if (fast16) store_f16x16(reinterpret_cast<__half*>(out) + off, vv);
+                    if (fast16) {
+#pragma unroll
+                        for (int c = 0; c < 2 * COUT; c += 16) store_f16x16(reinterpret_cast<__half*>(out) + off + c, vv + c);
+                    }
                     else store_raw_row<2 * COUT>(out, off, vv, 2 * COUT, vec, p.raw16, nullptr);
 #pragma unroll
                     for (int c = 0; c < 2 * COUT; ++c) {
