@@ -52,6 +52,9 @@ constexpr int RG_PRODUCERS = 128;
 constexpr int RG_THREADS = 288;
 constexpr int RG_MAXG = 15;
 constexpr int RG_MAXR = 16;      // ring slots (mbarrier pairs)
+#ifndef RING_NOINC_DEFAULT
+#define RING_NOINC_DEFAULT 0
+#endif
 #ifndef RING_LATE_RELEASE
 #define RING_LATE_RELEASE 0       // 1: release an accumulator group after the plane's stores instead of before them (zeroing
                                   // overlapped with the conversion): measured 31.7 vs 31.9 us per 8 -> 8 layer in steady state, kept off
@@ -68,6 +71,7 @@ struct RingParams {
     int wbytes;
     int dbg;            // ATVS_RING_DEBUG bit mask (tools/conv_probe.py): 1 no loads, 2 no MMAs, 4 no stores, 8 no zeroing
     long long nunits;
+    int noinc;          // 1: planes published by cp.async.mbarrier.arrive.noinc (producers never wait), consumer-side proxy fence
     int balanced;       // 1: every CTA owns one contiguous range of the linear (tile column, z) plane sequence
     long long total;    // balanced: tile columns * D
 };
@@ -159,7 +163,7 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
     const int R = p.nring;
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
-            mbar_init(&full[s], RG_PRODUCERS / 32);      // one arrival per producer WARP (lane 0, after __syncwarp)
+            mbar_init(&full[s], p.noinc ? RG_PRODUCERS : RG_PRODUCERS / 32);      // per thread (noinc) | per producer WARP
             mbar_init(&empty[s], 1);
         }
         for (int g = 0; g < G; ++g) {
@@ -263,6 +267,15 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                     }
                 }
                 TRACE(1);
+                if (p.noinc) {
+                    // the plane's mbarrier tracks this thread's copies: it completes when all 128 threads' copies have landed;
+                    // nothing to wait for here (the ring's `empty` barriers bound the planes in flight)
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+                    if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
+                    TRACE(2);
+                    TRACE_NEXT();
+                    continue;
+                }
                 if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
                 if (++gopen == (uint32_t)PG) {
                     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -279,7 +292,8 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
             pplanes += gopen;
             ++pending;
         }
-        publish(0);
+        if (p.noinc) asm volatile("cp.async.wait_all;" ::: "memory");      // no copy outlives the CTA's shared memory
+        else publish(0);
         if (ptid == 0) TRACE_DUMP("P");
     } else if (warp == 4) {
         // ===================== MMA issuer (elected lane) =====================
@@ -342,6 +356,8 @@ k_conv3d_ring(const uint16_t* __restrict__ x, const __grid_constant__ RingParams
                 TRACE(0);
                 mbar_wait(&full[slot], sphase);
                 TRACE(1);
+                // cp.async wrote the plane through the generic proxy; the MMA reads it through the async proxy
+                if (p.noinc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tc_fence_after();
                 const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
                 if (p.dbg & 2) {
@@ -697,6 +713,8 @@ int ring_conv(const void* x16, int dtype, const void* wimg, int B, int D, int H,
     p.pg = 1;          // grouped publishing (ATVS_RING_PG=2..4) measured no faster: profiles/r02_ring_probe.txt
     if (const char* e = getenv("ATVS_RING_PG")) p.pg = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : p.pg;
     while (p.pg > 1 && 2 * p.pg + 1 > nring) --p.pg;
+    p.noinc = RING_NOINC_DEFAULT;
+    if (const char* e = getenv("ATVS_RING_NOINC")) p.noinc = atoi(e) != 0;
     p.pf = (nring - 1) / p.pg;                      // groups in flight: pf * pg < nring keeps the ring deadlock-free
     if (p.pf > 4) p.pf = 4;
     if (const char* e = getenv("ATVS_RING_PF")) {
