@@ -45,9 +45,13 @@ struct S2Params {
     long long total;            // tile columns * Do
 };
 
-template <int CIN, int CP>
+// KPH: K phases of an input plane.  A ring slot holds CIN / KPH channels of the plane; the phases of a plane are staged
+// and multiplied one after the other into the same accumulators.  32 input channels as 2 phases of 16 halve the slot
+// (39 -> 20 KB), so that 4 slots + the weights fit two CTAs per SM (one CTA with ~190 KB of planes starves the passes
+// that share the SM: ATVS_RING_S2_MAXCIN history in DESIGN.md).
+template <int CIN, int CP, int KPH = 1>
 struct S2Cfg {
-    static constexpr int NKC = CIN / 8;
+    static constexpr int NKC = CIN / 8 / KPH;                       // 8-channel chunks per slot
     static constexpr int SLOT_BYTES = (NKC * S2_PITCH + 127) / 128 * 128;
     static constexpr int NSTEPS = (CIN >= 16) ? 9 * (CIN / 16) : 5;
     static constexpr int NROWS = 3 * CP;
@@ -87,12 +91,13 @@ __host__ __device__ constexpr uint32_t s2_tap_off(int tap) {
 __host__ __device__ constexpr int s2_pair_a(int s) { return s == 0 ? 0 : s == 1 ? 2 : s == 2 ? 5 : s == 3 ? 6 : 8; }
 __host__ __device__ constexpr int s2_pair_b(int s) { return s == 0 ? 1 : s == 1 ? 3 : s == 2 ? 4 : s == 3 ? 7 : 7; }
 
-template <int CIN, int CP, int MINB>
+template <int CIN, int CP, int MINB, int KPH>
 __global__ void __launch_bounds__(S2_THREADS, MINB)
 k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Params p,
                  const uint8_t* __restrict__ wimg, float* __restrict__ out, double* __restrict__ stats,
                  const float* __restrict__ bias) {
-    using Cfg = S2Cfg<CIN, CP>;
+    using Cfg = S2Cfg<CIN, CP, KPH>;
+    static_assert(KPH == 1 || (CIN >= 32 && (CIN / 16) % KPH == 0), "K phases: whole K=16 steps");
     constexpr int G = S2_G;
 
     extern __shared__ uint8_t smem_raw[];
@@ -184,26 +189,29 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
             }
             const uint16_t* zbase = x + ((size_t)un.b * p.D + 2 * un.z0) * zstride_in;
             for (int i = 0; i <= iend; ++i, zbase += zstride_in) {
-                mbar_wait(&empty[slot], sphase ^ 1);
-                const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
 #pragma unroll
-                for (int k = 0; k < NITEM; ++k) {
-                    if (goff[k] != -2) {
-                        const int j = ptid + k * S2_PRODUCERS;
-                        const int c = j % Cfg::NKC, v = j / Cfg::NKC;
-                        const int iy = v / S2_IW, ix = v - iy * S2_IW;
-                        const uint32_t soff = (uint32_t)(c * S2_PITCH +
-                                                         ((((iy & 1) << 1) | (ix & 1)) * S2_SUB + (iy >> 1) * S2_SC + (ix >> 1)) * 16);
-                        const bool ok = goff[k] >= 0;
-                        const uint16_t* src = ok ? zbase + goff[k] : x;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + soff), "l"(src),
-                                     "r"(ok ? 16 : 0)
-                                     : "memory");
+                for (int h = 0; h < KPH; ++h) {            // phase h: channels [h * 8 NKC, (h + 1) * 8 NKC) of the plane
+                    mbar_wait(&empty[slot], sphase ^ 1);
+                    const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < NITEM; ++k) {
+                        if (goff[k] != -2) {
+                            const int j = ptid + k * S2_PRODUCERS;
+                            const int c = j % Cfg::NKC, v = j / Cfg::NKC;
+                            const int iy = v / S2_IW, ix = v - iy * S2_IW;
+                            const uint32_t soff = (uint32_t)(c * S2_PITCH +
+                                                             ((((iy & 1) << 1) | (ix & 1)) * S2_SUB + (iy >> 1) * S2_SC + (ix >> 1)) * 16);
+                            const bool ok = goff[k] >= 0;
+                            const uint16_t* src = ok ? zbase + goff[k] + h * (Cfg::NKC * 8) : x;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + soff), "l"(src),
+                                         "r"(ok ? 16 : 0)
+                                         : "memory");
+                        }
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
+                    if (++pending >= (uint32_t)PF) publish(PF - 1);
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
-                if (++pending >= (uint32_t)PF) publish(PF - 1);
             }
         }
         publish(0);
@@ -217,15 +225,21 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
             constexpr uint32_t A_LBO = (CIN >= 16) ? ((uint32_t)(S2_PITCH >> 4) << 16) : 0u;
             const uint32_t a_lo_ring = (smem_u32(ring) >> 4) | A_LBO;
             const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | ((uint32_t)((Cfg::NROWS * 16) >> 4) << 16);
-            auto issue_plane = [&](uint32_t dcol, uint32_t a_lo0, uint32_t b_lo, uint32_t idesc) {
+            // the MMAs of phase h of a plane: K=16 steps ks in [h * KS / KPH, (h + 1) * KS / KPH) of every in-plane tap; the
+            // slot holds the phase's chunks from 0, the weight image holds all steps (tap-major)
+            auto issue_plane = [&](uint32_t dcol, uint32_t a_lo0, uint32_t b_lo, uint32_t idesc, int h) {
+                constexpr int KS = (CIN >= 16) ? CIN / 16 : 1;
+                constexpr int KSP = KS / KPH > 0 ? KS / KPH : 1;
 #pragma unroll
-                for (int s = 0; s < Cfg::NSTEPS; ++s) {
+                for (int sl = 0; sl < Cfg::NSTEPS / KPH; ++sl) {
                     uint32_t aoff;
+                    int s;
                     if (CIN >= 16) {
-                        constexpr int KS = (CIN >= 16) ? CIN / 16 : 1;
-                        const int tp = s / KS, ks = s % KS;
-                        aoff = (uint32_t)((2 * ks * S2_PITCH) >> 4) + (s2_tap_off(tp) >> 4);
+                        const int tp = sl / KSP, ksl = sl % KSP;
+                        s = tp * KS + h * KSP + ksl;
+                        aoff = (uint32_t)((2 * ksl * S2_PITCH) >> 4) + (s2_tap_off(tp) >> 4);
                     } else {
+                        s = sl;
                         const uint32_t offa = s2_tap_off(s2_pair_a(s)), offb = s2_tap_off(s2_pair_b(s));
                         aoff = (offa >> 4) | (((offb - offa) >> 4) << 16);
                     }
@@ -251,24 +265,27 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                         mbar_wait(&tempty[gw], gwphase ^ 1);
                         if (++gw == (uint32_t)G) { gw = 0; gwphase ^= 1; }
                     }
+                    const uint32_t gprev = (gcur == 0) ? (uint32_t)G - 1 : gcur - 1;
+#pragma unroll
+                    for (int h = 0; h < KPH; ++h) {
                     mbar_wait(&full[slot], sphase);
                     tc_fence_after();
                     const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
-                    const uint32_t gprev = (gcur == 0) ? (uint32_t)G - 1 : gcur - 1;
                     if (!even) {
-                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W1 * 16u) >> 4), ring_idesc(CP) | p.fmt);
+                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W1 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
                     } else if (j == 0) {
-                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
+                        issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
                     } else if (j >= un.zlen) {
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
                     } else if (gcur != 0) {
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(2 * CP) | p.fmt);
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(2 * CP) | p.fmt, h);
                     } else {                           // the pair wraps around the accumulator ring
-                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
-                        issue_plane(tmem_base, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt);
+                        issue_plane(tmem_base + gprev * (uint32_t)CP, a_lo0, b_lo0 + ((W_W2W0 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
+                        issue_plane(tmem_base, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
                     }
                     tc_commit(&empty[slot]);
                     if (++slot == (uint32_t)R) { slot = 0; sphase ^= 1; }
+                    }
                     // output planes whose last contribution this was
                     const int tlast = (i == iend) ? un.zlen - 1 : (even ? j - 1 : -1);
                     while (tdone <= tlast) {
@@ -391,15 +408,15 @@ __global__ void k_pack_ring_s2(const float* __restrict__ w, int Cin, int Cout, i
     }
 }
 
-template <int CIN, int CP, int MINB>
+template <int CIN, int CP, int MINB, int KPH = 1>
 int launch_s2(const uint16_t* x, const S2Params& p, const uint8_t* wimg, float* out, double* stats,
               const float* bias, size_t smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring_s2<CIN, CP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ATVS_CUDA(cudaFuncSetAttribute(k_conv3d_ring_s2<CIN, CP, MINB, KPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_conv3d_ring_s2<CIN, CP, MINB><<<grid, S2_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
+    k_conv3d_ring_s2<CIN, CP, MINB, KPH><<<grid, S2_THREADS, smem, st>>>(x, p, wimg, out, stats, bias);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
@@ -453,7 +470,10 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
     p.nXT = (p.Wo + S2_TX - 1) / S2_TX;
     p.nYT = (p.Ho + S2_TY - 1) / S2_TY;
     p.wbytes = (int)s2_slab_bytes(Cin, cp);
-    const size_t slot = ((size_t)(Cin / 8) * S2_PITCH + 127) / 128 * 128;
+    // 32 input channels: two K phases of 16 per plane (S2Cfg) unless ATVS_S2_KPH=1
+    int kph = Cin == 32 ? 2 : 1;
+    if (const char* e = getenv("ATVS_S2_KPH")) kph = (Cin == 32 && atoi(e) == 2) ? 2 : 1;
+    const size_t slot = ((size_t)(Cin / 8 / kph) * S2_PITCH + 127) / 128 * 128;
     const size_t fixed = 128 + (size_t)((p.wbytes + 127) & ~127) + (2 * 8 + 2 * S2_G + 1) * 8 + 16;
     int minb = (cp < 32 && fixed + 4 * slot <= 110 * 1024) ? 2 : 1;
     if (const char* e = getenv("ATVS_RING_MINB")) minb = atoi(e) == 1 ? 1 : minb;
@@ -504,6 +524,13 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
         rc = (minb == 2) ? launch_s2<CI, CPV, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st) \
                          : launch_s2<CI, CPV, 1>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st); \
     } else
+        if (Cin == 32 && kph == 2 && cp == 16) {
+            rc = (minb == 2) ? launch_s2<32, 16, 2, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st)
+                             : launch_s2<32, 16, 1, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st);
+        } else if (Cin == 32 && kph == 2 && cp == 32) {
+            rc = (minb == 2) ? launch_s2<32, 32, 2, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st)
+                             : launch_s2<32, 32, 1, 2>((const uint16_t*)x16, p, wi, raw_out, stats, bias, smem, grid, st);
+        } else
         S2_CASE(8, 16) S2_CASE(8, 32) S2_CASE(16, 16) S2_CASE(16, 32) S2_CASE(32, 16) S2_CASE(32, 32)
         {
             atvs_set_error("atvs_conv3d_bf16(ring s2): no kernel for Cin=%d CP=%d", Cin, cp);

@@ -331,9 +331,13 @@ S2_RING_CASES = [(8, 16, (1, 32, 128, 160)), (32, 16, (1, 16, 128, 192)), (16, 3
 
 
 @HALF
+@pytest.mark.parametrize('kph', [2, 1])
 @pytest.mark.parametrize('cin,cout,shape', S2_RING_CASES)
-def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
-    """large stride-2 volumes take the de-interleaving ring kernel (conv_ring_s2.cu)."""
+def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half, kph):
+    """large stride-2 volumes take the de-interleaving ring kernel (conv_ring_s2.cu); 32 input channels as two K phases
+    of 16 per plane (the default) or as one 32-channel slot (ATVS_S2_KPH=1)."""
+    if kph == 1 and cin != 32:
+        pytest.skip("K phases only exist for 32 input channels")
     from oracle import network as onet
     from atvsnet_b200.network import conv3d_raw
     assert (shape[1] // 2) * (shape[2] // 2) * (shape[3] // 2) >= 32768 or True
@@ -341,12 +345,13 @@ def test_conv3d_bf16_stride2_ring(A, cin, cout, shape, half):
     xb = torch.from_numpy(x).to(half)
     wb = torch.from_numpy(w).to(half).float()
     A.variables.packed_cache().clear()
-    os.environ['ATVS_RING_S2_MAXCIN'] = '32'           # Cin = 32 is opt-in (see ring_s2_applicable)
+    os.environ['ATVS_RING_S2_MAXCIN'] = '32'
+    os.environ['ATVS_S2_KPH'] = str(kph)
     try:
         raw, stats = conv3d_raw(xb.cuda(), 's2ring_%d_%d' % (cin, cout), wb.cuda(), cout, 2, False, True)
         torch.cuda.synchronize()
     finally:
-        del os.environ['ATVS_RING_S2_MAXCIN']
+        del os.environ['ATVS_RING_S2_MAXCIN'], os.environ['ATVS_S2_KPH']
     ref = onet.conv3d(xb.float().numpy(), wb.numpy(), 2)
     assert raw.shape == ref.shape
     assert rel_err(npy(raw), ref) < 1e-4
