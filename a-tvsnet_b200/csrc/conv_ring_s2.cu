@@ -40,6 +40,7 @@ struct S2Params {
     int nXT, nYT, nZS, ZS;
     int nring;
     int wbytes;
+    int dbg;                    // ATVS_RING_DEBUG bit mask: 1 no loads, 2 no MMAs, 4 no stores (tools/steady_probe.py)
     long long nunits;
     int balanced;               // ring_common.cuh RingSpan: 1 = balanced ranges of output planes
     long long total;            // tile columns * Do
@@ -195,7 +196,7 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                     const uint32_t dst0 = ring_u32 + slot * (uint32_t)Cfg::SLOT_BYTES;
 #pragma unroll
                     for (int k = 0; k < NITEM; ++k) {
-                        if (goff[k] != -2) {
+                        if (goff[k] != -2 && !(p.dbg & 1)) {
                             const int j = ptid + k * S2_PRODUCERS;
                             const int c = j % Cfg::NKC, v = j / Cfg::NKC;
                             const int iy = v / S2_IW, ix = v - iy * S2_IW;
@@ -271,7 +272,8 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                     mbar_wait(&full[slot], sphase);
                     tc_fence_after();
                     const uint32_t a_lo0 = a_lo_ring + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
-                    if (!even) {
+                    if (p.dbg & 2) {
+                    } else if (!even) {
                         issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W1 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
                     } else if (j == 0) {
                         issue_plane(tmem_base + gcur * (uint32_t)CP, a_lo0, b_lo0 + ((W_W0 * 16u) >> 4), ring_idesc(CP) | p.fmt, h);
@@ -333,7 +335,7 @@ k_conv3d_ring_s2(const uint16_t* __restrict__ x, const __grid_constant__ S2Param
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
-                if (!valid) continue;
+                if (!valid || (p.dbg & 4)) continue;
                 const size_t ooff = obase + (size_t)t * zstride;
                 if (bias != nullptr) {
                     // depth-invariant part of the layer (the tiled reference-feature half of the cost volume)
@@ -470,6 +472,10 @@ int ring_s2_conv(const void* x16, int dtype, const void* wimg, int B, int D, int
     p.nXT = (p.Wo + S2_TX - 1) / S2_TX;
     p.nYT = (p.Ho + S2_TY - 1) / S2_TY;
     p.wbytes = (int)s2_slab_bytes(Cin, cp);
+    {
+        const char* e = getenv("ATVS_RING_DEBUG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     // 32 input channels: two K phases of 16 per plane (S2Cfg) unless ATVS_S2_KPH=1
     int kph = Cin == 32 ? 2 : 1;
     if (const char* e = getenv("ATVS_S2_KPH")) kph = (Cin == 32 && atoi(e) == 2) ? 2 : 1;
