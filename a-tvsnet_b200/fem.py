@@ -89,12 +89,33 @@ def conv2d(x, kernel, stride=1, rate=1, bias=None, relu=False, padding='SAME', e
     return out
 
 
+BATCH_VIEWS = True       # extract_features: one batch over the views (fp32 path)
+
+# independent statistic groups along the batch dimension (extract_features runs the towers of all views as ONE batch:
+# 5 x the pixels per convolution launch fills the SMs, the batch statistics stay per view as in the reference)
+_GROUPS = 1
+
+
 def batch_norm(x, beta=None, relu=False, stats=None, out_dtype=torch.float32):
     """batch statistics over (B,H,W), biased variance, eps 1e-3, optional ``+ beta``, optional ReLU.  ``stats``: moments
-    already accumulated by the producing convolution's epilogue; ``out_dtype`` fp16 feeds a tensor-core convolution."""
+    already accumulated by the producing convolution's epilogue; ``out_dtype`` fp16 feeds a tensor-core convolution.
+    With ``_GROUPS`` = G > 1 the batch is G groups of B / G samples, each normalised with its own statistics."""
     x = L.f32c(x)
     C = x.shape[-1]
     count = x.numel() // C
+    G = _GROUPS
+    if G > 1:
+        if stats is not None or x.shape[0] % G:
+            raise RuntimeError("batch_norm: grouped statistics need a batch divisible by %d and no precomputed moments" % G)
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        st = torch.zeros((G, 2 * C), dtype=torch.float64, device=x.device)
+        bg = x.shape[0] // G
+        for g in range(G):
+            xs, os_ = x[g * bg:(g + 1) * bg], out[g * bg:(g + 1) * bg]
+            L.call("atvs_channel_moments", L.ptr(xs), count // G, C, L.ptr(st[g]), L.stream())
+            L.call("atvs_bn2d_apply", L.ptr(xs), L.ptr(st[g]), L.ptr(beta), count // G, C, BN_EPS, int(relu), L.ptr(os_),
+                   L.F16 if out_dtype == torch.float16 else L.F32, L.stream())
+        return out
     if stats is None:
         stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
         L.call("atvs_channel_moments", L.ptr(x), count, C, L.ptr(stats), L.stream())
@@ -205,5 +226,16 @@ def extract_features(images):
     """model.py:420-425 TVSNet_feature_extraction over all views: images (B,N,H,W,3) -> features (B,N,H/4,W/4,32).
     One tower per VIEW on the (B,H,W,3) slice, as in the reference: batch statistics are taken over the whole batch B
     of that view (B = 1 in example.py), never across views."""
-    N = images.shape[1]
-    return torch.stack([ResNetDS2SPP(images[:, n]) for n in range(N)], dim=1)
+    global _GROUPS
+    B, N = images.shape[0], images.shape[1]
+    if tensor_path() or N == 1 or not BATCH_VIEWS:
+        return torch.stack([ResNetDS2SPP(images[:, n]) for n in range(N)], dim=1)
+    # all views as one batch (view-major), statistics per view: the same numbers as one tower per view, with 5 x the
+    # pixels per convolution launch (the 1/4-resolution layers leave most SMs idle on one 640x512 image)
+    stacked = L.f32c(images).transpose(0, 1).reshape((N * B,) + tuple(images.shape[2:])).contiguous()
+    _GROUPS = N
+    try:
+        feat = ResNetDS2SPP(stacked)
+    finally:
+        _GROUPS = 1
+    return feat.reshape((N, B) + tuple(feat.shape[1:])).transpose(0, 1).contiguous()

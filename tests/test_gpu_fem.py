@@ -177,3 +177,26 @@ def test_images_to_depth_end_to_end(A):
         A.FLAGS.precision = A.flags.DEFAULT_PRECISION
     rng_ = float((D - 1) * cams[0, 0, 1, 3, 1])
     assert float(np.abs(out['depth_up'].cpu().numpy() - ref['depth_agg_init_up']).mean()) / rng_ < 1e-3
+
+
+def test_extract_features_batched_views_equal_per_view_towers(A):
+    """extract_features runs the towers of all views as ONE batch (view-major) with batch statistics per view
+    (fem._GROUPS): the same numbers as one tower per (B,H,W,3) view slice, the form of model.py:420-425 - for B = 1
+    (example.py) and for B = 2 (statistics over the two samples of a view, never across views)."""
+    from gen_common import fem_weights
+    A.variables.load_weights(fem_weights(5))
+    rng = np.random.default_rng(21)
+    A.FLAGS.precision = 'fp32'
+    try:
+        for B, nv, H, W in ((1, 4, 64, 96), (2, 3, 48, 64)):
+            imgs = cu((127.5 + 50 * rng.standard_normal((B, nv, H, W, 3))).clip(0, 255).astype(np.float32))
+            got = A.fem.extract_features(imgs)
+            A.fem.BATCH_VIEWS = False
+            try:
+                ref = A.fem.extract_features(imgs)
+            finally:
+                A.fem.BATCH_VIEWS = True
+            assert tuple(got.shape) == (B, nv, H // 4, W // 4, 32)
+            assert rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    finally:
+        A.FLAGS.precision = A.flags.DEFAULT_PRECISION
