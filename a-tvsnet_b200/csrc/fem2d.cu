@@ -8,6 +8,7 @@
 // fp32 CUDA-core kernels (register-tiled direct convolution): the PARITY path of this row.  The tensor-core (tcgen05)
 // version - channel-chunked taps, dilation, bias/ReLU epilogue - is the next step; see DESIGN.md section 6.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -17,17 +18,21 @@ struct Conv2dParams {
     int tiles_x, tiles_y;
 };
 
-constexpr int C2_TH = 8, C2_CO = 32, C2_KC = 16;      // tile: 8 rows x (8 * PX) pixels, 32 output channels
+constexpr int C2_TH = 8, C2_CO = 32, C2_KC = 32;      // tile: 8 rows x (8 * PX) pixels, 32 output channels, 32-channel K steps
+constexpr int C2_WPT = C2_KC * C2_CO / 256;             // weights per thread and K step
+constexpr int C2_UNROLL = 8;                            // all 8 four-channel sub-steps of a K step unrolled: 20.7 ms per cfg2 frame (4: 22.3)
 
 // block = 256 threads = 64 pixel groups (PX consecutive x) x 4 groups of 8 output channels; one 8 x (8*PX) pixel tile
 // and 32 output channels per block.  Per (tap, 16-channel chunk) the weights [16][32] are staged in shared memory; a
 // thread does PX*32 FMAs per PX input float4 loads and 8 weight LDS.128.  PX = 4 for the large maps, PX = 2 when that
 // would leave the SMs with about one block each (the 1/4-resolution layers: occupancy 14 % with PX = 4).
-template <int K, int PX>
+template <int K, int PX, int CT>
 __global__ void __launch_bounds__(256)
 k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               const Conv2dParams p, float* __restrict__ out) {
-    __shared__ __align__(16) float ws[C2_KC][C2_CO];
+    constexpr int CO = 4 * CT;                               // output channels per block: 4 thread groups x CT
+    constexpr int WPT = C2_KC * CO / 256;
+    __shared__ __align__(16) float ws[2][C2_KC][CO];         // double buffered: ONE barrier per K step
     const int t = threadIdx.x;
     const int cg = t & 3, q = t >> 2;
     const int qy = q >> 3, qx = q & 7;
@@ -36,31 +41,41 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
     tile /= p.tiles_x;
     const int ty = tile % p.tiles_y;
     const int b = tile / p.tiles_y;
-    const int co0 = blockIdx.y * C2_CO;
+    const int co0 = blockIdx.y * CO;
     const int oy = ty * C2_TH + qy;
     const int ox0 = tx * (8 * PX) + qx * PX;
-    float acc[PX][8];
+    float acc[PX][CT];
 #pragma unroll
     for (int j = 0; j < PX; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+        for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
     const bool vec = (p.Cin & 3) == 0;
     const float* xb = x + (size_t)b * p.H * p.W * p.Cin;
     // flattened (tap, 16-channel chunk) loop; the weights of step it+1 are fetched into registers while step it computes
     const int nch = (p.Cin + C2_KC - 1) / C2_KC;
     const int nit = K * K * nch;
-    float wnext[2];
+    float wnext[WPT];
     auto fetch = [&](int it) {
         const int tap = it / nch, c0 = (it - tap * nch) * C2_KC;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < WPT; ++r) {
             const int i = t + r * 256;
-            const int ci = i / C2_CO, co = i % C2_CO;
+            const int ci = i / CO, co = i % CO;
             wnext[r] = (c0 + ci < p.Cin && co0 + co < p.Cout) ? __ldg(w + ((size_t)tap * p.Cin + c0 + ci) * p.Cout + co0 + co) : 0.f;
         }
     };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < WPT; ++r) {
+            const int i = t + r * 256;
+            ws[buf][i / CO][i % CO] = wnext[r];
+        }
+    };
     fetch(0);
+    stage(0);
+    __syncthreads();
     for (int it = 0; it < nit; ++it) {
+        const int cur = it & 1;
         const int tap = it / nch, c0 = (it - tap * nch) * C2_KC;
         const int ky = tap / K, kx = tap % K;
         const int iy = oy * p.stride - p.pad_t + ky * p.rate;
@@ -72,15 +87,8 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
             ix[j] = (ox0 + j) * p.stride - p.pad_l + kx * p.rate;
             ok[j] = yok && (ox0 + j) < p.Wo && ix[j] >= 0 && ix[j] < p.W;
         }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int i = t + r * 256;
-            ws[i / C2_CO][i % C2_CO] = wnext[r];
-        }
-        __syncthreads();
-        if (it + 1 < nit) fetch(it + 1);
-#pragma unroll
+        if (it + 1 < nit) fetch(it + 1);       // global -> registers while this step computes
+#pragma unroll C2_UNROLL
         for (int c4 = 0; c4 < C2_KC; c4 += 4) {
             if (c0 + c4 >= p.Cin) break;
             float in[PX][4];
@@ -99,28 +107,33 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
             }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                const float4 w0 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&ws[c4 + cc][cg * 8 + 4]);
 #pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    const float a = in[j][cc];
-                    acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
-                    acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
-                    acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
-                    acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
+                for (int c8 = 0; c8 < CT; c8 += 8) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[cur][c4 + cc][cg * CT + c8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[cur][c4 + cc][cg * CT + c8 + 4]);
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+                        const float a = in[j][cc];
+                        acc[j][c8 + 0] = fmaf(a, w0.x, acc[j][c8 + 0]); acc[j][c8 + 1] = fmaf(a, w0.y, acc[j][c8 + 1]);
+                        acc[j][c8 + 2] = fmaf(a, w0.z, acc[j][c8 + 2]); acc[j][c8 + 3] = fmaf(a, w0.w, acc[j][c8 + 3]);
+                        acc[j][c8 + 4] = fmaf(a, w1.x, acc[j][c8 + 4]); acc[j][c8 + 5] = fmaf(a, w1.y, acc[j][c8 + 5]);
+                        acc[j][c8 + 6] = fmaf(a, w1.z, acc[j][c8 + 6]); acc[j][c8 + 7] = fmaf(a, w1.w, acc[j][c8 + 7]);
+                    }
                 }
             }
         }
+        if (it + 1 < nit) stage(cur ^ 1);      // the other buffer: its readers passed the barrier of the previous step
+        __syncthreads();
     }
     if (oy >= p.Ho) return;
-    const int co = co0 + cg * 8;
+    const int co = co0 + cg * CT;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
         const int ox = ox0 + j;
         if (ox >= p.Wo) continue;
         float* o = out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + co;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < CT; ++c) {
             if (co + c >= p.Cout) break;
             float v = acc[j][c] + (bias ? __ldg(bias + co + c) : 0.f);
             if (p.relu) v = fmaxf(v, 0.f);
@@ -278,17 +291,25 @@ extern "C" int atvs_conv2d_fp32(const float* x, const float* kernel, const float
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
     p.stride = stride; p.rate = rate; p.pad_t = pad_top; p.pad_l = pad_left; p.relu = relu;
     p.tiles_y = (Ho + C2_TH - 1) / C2_TH;
-    const int slabs = (Cout + C2_CO - 1) / C2_CO;
+    // 16 output channels per thread (64 per block) where the layer has them and the grid still fills the SMs: the input
+    // pixel a thread loads then feeds twice the FMAs (ATVS_FEM_CT=8 forces the 8-channel tile)
+    int ct = 8;      // measured at cfg2 (5 views batched): 20.7 ms per frame with 8 channels per thread, 23.9 with 16 (168 registers: one block per SM)
+    if (const char* e = getenv("ATVS_FEM_CT")) ct = (atoi(e) == 16 && Cout % 64 == 0) ? 16 : (atoi(e) == 8 ? 8 : ct);
+    if (ct == 16 && (long long)B * ((Wo + 31) / 32) * p.tiles_y * (Cout / 64) < 3LL * atvs_num_sms()) ct = 8;
+    const int slabs = (Cout + 4 * ct - 1) / (4 * ct);
     // 4 pixels per thread unless that leaves fewer than ~4 blocks per SM
     int px = 4;
     if ((long long)B * ((Wo + 31) / 32) * p.tiles_y * slabs < 3LL * atvs_num_sms()) px = 2;
     p.tiles_x = (Wo + 8 * px - 1) / (8 * px);
     dim3 grid((unsigned)((long long)B * p.tiles_x * p.tiles_y), (unsigned)slabs);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ksize == 1 && px == 4) k_conv2d_fp32<1, 4><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
-    else if (ksize == 1) k_conv2d_fp32<1, 2><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
-    else if (px == 4) k_conv2d_fp32<3, 4><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
-    else k_conv2d_fp32<3, 2><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    if (ct == 16) {
+        if (ksize == 1) k_conv2d_fp32<1, 4, 16><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+        else k_conv2d_fp32<3, 4, 16><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    } else if (ksize == 1 && px == 4) k_conv2d_fp32<1, 4, 8><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else if (ksize == 1) k_conv2d_fp32<1, 2, 8><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else if (px == 4) k_conv2d_fp32<3, 4, 8><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
+    else k_conv2d_fp32<3, 2, 8><<<grid, 256, 0, st>>>(x, kernel, bias, p, out);
     ATVS_LAUNCH_CHECK();
     return 0;
 }
