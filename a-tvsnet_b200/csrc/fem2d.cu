@@ -10,6 +10,13 @@
 #include "common.cuh"
 #include <cstdlib>
 
+#ifndef C2_MINB
+#define C2_MINB 3
+#endif
+#ifndef C2_FFMA2
+#define C2_FFMA2 1
+#endif
+
 namespace {
 
 struct Conv2dParams {
@@ -17,6 +24,21 @@ struct Conv2dParams {
     int stride, rate, pad_t, pad_l, relu;
     int tiles_x, tiles_y;
 };
+
+// d0 += a.x * b.x, d1 += a.y * b.y as ONE fma.rn.f32x2 (sm_100 FFMA2)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float2 a, float2 b) {
+#if C2_FFMA2
+    unsigned long long d, ua, ub;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+#else
+    d0 = fmaf(a.x, b.x, d0);
+    d1 = fmaf(a.y, b.y, d1);
+#endif
+}
 
 constexpr int C2_TH = 8, C2_CO = 32, C2_KC = 32;      // tile: 8 rows x (8 * PX) pixels, 32 output channels, 32-channel K steps
 constexpr int C2_WPT = C2_KC * C2_CO / 256;             // weights per thread and K step
@@ -27,7 +49,7 @@ constexpr int C2_UNROLL = 8;                            // all 8 four-channel su
 // thread does PX*32 FMAs per PX input float4 loads and 8 weight LDS.128.  PX = 4 for the large maps, PX = 2 when that
 // would leave the SMs with about one block each (the 1/4-resolution layers: occupancy 14 % with PX = 4).
 template <int K, int PX, int CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CT == 16 ? 1 : C2_MINB)
 k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               const Conv2dParams p, float* __restrict__ out) {
     constexpr int CO = 4 * CT;                               // output channels per block: 4 thread groups x CT
@@ -113,11 +135,12 @@ k_conv2d_fp32(const float* __restrict__ x, const float* __restrict__ w, const fl
                     const float4 w1 = *reinterpret_cast<const float4*>(&ws[cur][c4 + cc][cg * CT + c8 + 4]);
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
-                        const float a = in[j][cc];
-                        acc[j][c8 + 0] = fmaf(a, w0.x, acc[j][c8 + 0]); acc[j][c8 + 1] = fmaf(a, w0.y, acc[j][c8 + 1]);
-                        acc[j][c8 + 2] = fmaf(a, w0.z, acc[j][c8 + 2]); acc[j][c8 + 3] = fmaf(a, w0.w, acc[j][c8 + 3]);
-                        acc[j][c8 + 4] = fmaf(a, w1.x, acc[j][c8 + 4]); acc[j][c8 + 5] = fmaf(a, w1.y, acc[j][c8 + 5]);
-                        acc[j][c8 + 6] = fmaf(a, w1.z, acc[j][c8 + 6]); acc[j][c8 + 7] = fmaf(a, w1.w, acc[j][c8 + 7]);
+                        // two IEEE FMAs per instruction (FFMA2): same results, half the issue slots
+                        const float2 a2 = make_float2(in[j][cc], in[j][cc]);
+                        ffma2(acc[j][c8 + 0], acc[j][c8 + 1], a2, make_float2(w0.x, w0.y));
+                        ffma2(acc[j][c8 + 2], acc[j][c8 + 3], a2, make_float2(w0.z, w0.w));
+                        ffma2(acc[j][c8 + 4], acc[j][c8 + 5], a2, make_float2(w1.x, w1.y));
+                        ffma2(acc[j][c8 + 6], acc[j][c8 + 7], a2, make_float2(w1.z, w1.w));
                     }
                 }
             }
