@@ -388,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and args.precision != 'fp32':
         kernels = hbm_kernel_lines(A, feats_d, cams_d, D, h, w, N.act_dtype())
         if roof is not None:
-            roof["traffic"], roof["traffic_source"] = ncu_traffic("k_conv3d_ring<32, 8, 2,")
+            roof["traffic"], roof["traffic_source"] = ncu_traffic("k_conv3d_ring<32, 8, 2, 2,")
 
     # ---------------- N = 1: the same depth map from IMAGES, and the whole four-stage schedule ----------------
     extras = {}
