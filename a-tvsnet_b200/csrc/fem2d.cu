@@ -198,6 +198,49 @@ k_channel_moments(const float* __restrict__ x, long long count, int C, double* _
     }
 }
 
+// few channels that do not divide 256 (the 3-channel image in front of the shallow feature net's first BN: the general
+// path above issues two fp64 atomics per ELEMENT onto 2 C addresses - 404 us for a 512x640x3 image): a thread walks whole
+// pixels and keeps all C running sums, one warp reduction and 2 C atomics per block at the end
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+k_channel_moments_small(const float* __restrict__ x, long long count, int C, double* __restrict__ stats) {
+    __shared__ double sh[8][2 * CMAX];
+    double s[CMAX], s2[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) s[c] = s2[c] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < count; px += stride) {
+        const float* r = x + px * C;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+                const double v = (double)r[c];
+                s[c] += v;
+                s2[c] += v * v;
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            s[c] += __shfl_xor_sync(0xffffffffu, s[c], off);
+            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], off);
+        }
+        if (lane == 0) { sh[warp][c] = s[c]; sh[warp][CMAX + c] = s2[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * CMAX) {
+        const int c = threadIdx.x % CMAX, hi = threadIdx.x / CMAX;
+        if (c < C) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += sh[w][hi * CMAX + c];
+            atomicAdd(&stats[hi * C + c], a);
+        }
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_bn2d_apply(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ beta, long long count,
@@ -342,7 +385,13 @@ extern "C" int atvs_channel_moments(const float* x, long long count, int C, doub
     ATVS_CHECK_ARG(count > 0 && C > 0, ATVS_E_SHAPE, "atvs_channel_moments: count=%lld C=%d", count, C);
     unsigned g = ew_grid(count * C);
     if (g > 592) g = 592;          // fp64 atomics per block: keep the tail short
-    k_channel_moments<<<g, 256, 0, (cudaStream_t)stream>>>(x, count, C, stats);
+    if (C <= 8 && (256 % C) != 0) {
+        unsigned gs = ew_grid(count);
+        if (gs > 592) gs = 592;
+        k_channel_moments_small<8><<<gs, 256, 0, (cudaStream_t)stream>>>(x, count, C, stats);
+    } else {
+        k_channel_moments<<<g, 256, 0, (cudaStream_t)stream>>>(x, count, C, stats);
+    }
     ATVS_LAUNCH_CHECK();
     return 0;
 }

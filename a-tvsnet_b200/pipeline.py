@@ -244,11 +244,13 @@ def run_example_schedule(images, cams, depth_num, features=None):
     di = cams[:, 0, 1, 3, 1].contiguous()
     n_views = cams.shape[1]
     refined_costs, refined_probs = [], []
-    for n, v in enumerate(range(1, n_views)):
-        rp, rc = refine.TVSNet_refine(out['depth'], out['depth_views'][n], out['prob_volume_agg'], out['cost_volume_agg'],
-                                      images, cams, depth_num, ds, di, v)
-        refined_probs.append(rp)
-        refined_costs.append(rc)
+    images = L.f32c(images)
+    with refine.shallow_cache():       # the reference view's shallow features once, not once per source
+        for n, v in enumerate(range(1, n_views)):
+            rp, rc = refine.TVSNet_refine(out['depth'], out['depth_views'][n], out['prob_volume_agg'], out['cost_volume_agg'],
+                                          images, cams, depth_num, ds, di, v)
+            refined_probs.append(rp)
+            refined_costs.append(rc)
     cost_ref = N.attention_aggregation(refined_costs, 'attention_aggregate_refine')
     prob_ref = OutputConv_refine({'data': cost_ref}).get_output().squeeze(-1)
     out['depth_refined'], _ = _prob2depth(prob_ref, ds, di, 1, False)

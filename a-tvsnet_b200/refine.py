@@ -58,9 +58,36 @@ def shallow_features(image):
     return fem.conv2d(x, V.get_variable('global_refine_shallow_feature/kernel'))
 
 
+_SHALLOW_MEMO = None      # view id -> shallow feature map, while a schedule over ONE image tensor is running
+
+
+class shallow_cache(object):
+    """``with refine.shallow_cache():`` around a schedule that refines several source views of the same images: the
+    shallow features of a view are computed once (the reference recomputes the reference view's for every source,
+    model.py:143-154 inside model.py:248).  Same numbers, (N-2) towers less."""
+
+    def __enter__(self):
+        global _SHALLOW_MEMO
+        self.prev, _SHALLOW_MEMO = _SHALLOW_MEMO, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _SHALLOW_MEMO
+        _SHALLOW_MEMO = self.prev
+        return False
+
+
 def extract_feature_shallow(images, ref_id=0, view_id=1):
     """model.py:143-154."""
-    return shallow_features(images[:, ref_id]), shallow_features(images[:, view_id])
+    if _SHALLOW_MEMO is None:
+        return shallow_features(images[:, ref_id]), shallow_features(images[:, view_id])
+    key = (images.data_ptr(), tuple(images.shape))
+    out = []
+    for v in (ref_id, view_id):
+        if (key, v) not in _SHALLOW_MEMO:
+            _SHALLOW_MEMO[(key, v)] = shallow_features(images[:, v])
+        out.append(_SHALLOW_MEMO[(key, v)])
+    return tuple(out)
 
 
 def _pad_channels(x, cpad, dt):

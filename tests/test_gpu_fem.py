@@ -200,3 +200,17 @@ def test_extract_features_batched_views_equal_per_view_towers(A):
             assert rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-6
     finally:
         A.FLAGS.precision = A.flags.DEFAULT_PRECISION
+
+
+def test_channel_moments_few_channels(A):
+    """atvs_channel_moments on channel counts that do not divide 256 (the 3-channel image in front of the shallow feature
+    net's first BN takes the pixel-walking kernel): sums against NumPy fp64."""
+    rng = np.random.default_rng(3)
+    for C, count in ((3, 70001), (5, 4099), (6, 257), (7, 1), (3, 327680)):
+        x = rng.standard_normal((count, C)).astype(np.float32) * 3 + 1
+        st = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+        A._lib.call("atvs_channel_moments", A._lib.ptr(cu(x)), count, C, A._lib.ptr(st), A._lib.stream())
+        got = st.cpu().numpy()
+        x64 = x.astype(np.float64)
+        assert np.allclose(got[:C], x64.sum(0), rtol=1e-12, atol=1e-9)
+        assert np.allclose(got[C:], (x64 ** 2).sum(0), rtol=1e-12, atol=1e-9)
