@@ -27,6 +27,7 @@ _SIGS = {
     "atvs_bn_relu_add_pair": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p, _p, _i, _p],
     "atvs_set_concurrency": [_i],
     "atvs_cast": [_p, _i, _p, _i, _ll, _p],
+    "atvs_pad_cast": [_p, _ll, _i, _i, _p, _i, _p],
     "atvs_add": [_p, _p, _p, _i, _ll, _p],
     "atvs_attention_combine": [_p, _p, _i, _ll, _i, _i, _p, _p],
     "atvs_attention_local_max": [_p, _i, _ll, _i, _i, _p, _p],

@@ -724,6 +724,39 @@ extern "C" int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
     return 0;
 }
 
+// fp32 rows of C channels -> 16-bit rows of Cpad >= C channels, the extra channels zero: one pass instead of
+// zero fill + strided copy + cast (the refinement U-Net's 48 / 19 / 1-channel input groups, refine._pad_channels)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k_pad_cast(const float* __restrict__ x, long long rows, int C, int Cpad, OutT* __restrict__ out) {
+    const long long n = rows * (long long)(Cpad >> 3);          // one thread per 8 output channels (16 bytes)
+    const int g8 = Cpad >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / g8;
+        const int c0 = (int)(i - r * g8) << 3;
+        const float* src = x + r * C + c0;
+        OutT v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (OutT)((c0 + k < C) ? __ldg(src + k) : 0.f);
+        *reinterpret_cast<uint4*>(out + r * Cpad + c0) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+extern "C" int atvs_pad_cast(const float* x, long long rows, int C, int Cpad, void* out, int out_dtype, atvs_stream_t stream) {
+    ATVS_CHECK_ARG(x && out, ATVS_E_NULL, "atvs_pad_cast: NULL pointer");
+    ATVS_CHECK_ARG(rows > 0 && C > 0 && Cpad >= C && (Cpad & 7) == 0, ATVS_E_SHAPE, "atvs_pad_cast: rows=%lld C=%d Cpad=%d (Cpad >= C, multiple of 8)", rows, C, Cpad);
+    ATVS_CHECK_ARG(((uintptr_t)out & 15) == 0, ATVS_E_SHAPE, "atvs_pad_cast: out must be 16-byte aligned");
+    const unsigned grid = grid_for(rows * (Cpad >> 3), 256, 4);
+    if (out_dtype == ATVS_F16) k_pad_cast<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, Cpad, (__half*)out);
+    else if (out_dtype == ATVS_BF16) k_pad_cast<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, Cpad, (__nv_bfloat16*)out);
+    else {
+        atvs_set_error("atvs_pad_cast: out_dtype %d (ATVS_F16 | ATVS_BF16)", out_dtype);
+        return ATVS_E_DTYPE;
+    }
+    ATVS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int atvs_add(const void* a, const void* b, void* out, int dtype, long long n, atvs_stream_t stream) {
     ATVS_CHECK_ARG(a && b && out, ATVS_E_NULL, "atvs_add: NULL pointer");
     if (n <= 0) return 0;

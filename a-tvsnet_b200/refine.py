@@ -96,8 +96,9 @@ def _pad_channels(x, cpad, dt):
     B, D, h, w, C = x.shape
     if C == cpad:
         return N.to_dtype(x.contiguous(), dt)
-    out = torch.zeros((B, D, h, w, cpad), dtype=dt, device=x.device)
-    out[..., :C] = x
+    x = L.f32c(x)
+    out = torch.empty((B, D, h, w, cpad), dtype=dt, device=x.device)
+    L.call("atvs_pad_cast", L.ptr(x), B * D * h * w, C, cpad, L.ptr(out), L.dtype_code(out), L.stream())
     return out
 
 

@@ -150,6 +150,10 @@ int atvs_bn_relu_add_pair(const void* raw_a, const double* stats_a, const void* 
 /* ---- elementwise helpers (dtype plumbing for NDHWC volumes) */
 int atvs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n,
               atvs_stream_t stream);
+/* fp32 rows (rows, C) -> 16-bit rows (rows, Cpad), channels C..Cpad-1 zero: the input groups of the refinement U-Net
+ * (48 / 19 / 1 channels, model.py:328-333) in the tensor-core kernels' channel counts.  Cpad % 8 == 0.                  */
+int atvs_pad_cast(const float* x, long long rows, int C, int Cpad, void* out, int out_dtype /* ATVS_F16 | ATVS_BF16 */,
+                  atvs_stream_t stream);
 int atvs_add(const void* a, const void* b, void* out, int dtype, long long n, atvs_stream_t stream);
 
 /* ---- attention aggregation (AAM) ------------------------------- network.py:282-351, 379-408
