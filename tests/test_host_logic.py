@@ -145,3 +145,51 @@ def test_sharded_attention_combine_gloo_world2():
         p.join(60)
         assert p.exitcode == 0
     assert err < 1e-5, err
+
+
+def test_attention_fused_applicability():
+    """network.attention_fused_ok: the one-kernel AAM covers 2..8 views of (B,D,H,W,8) 16-bit volumes with D >= 3 and
+    H, W >= 8; everything else (fp32, other channel counts, one view, tiny planes, the flag off) takes the two-kernel path."""
+    import torch
+    import atvsnet_b200 as A
+    N = A.network
+    mk = lambda shape, dt=torch.float16: torch.empty(shape, dtype=dt, device='meta')
+    ok = mk((1, 16, 32, 40, 8))
+    assert N.attention_fused_ok([ok] * 2) and N.attention_fused_ok([ok] * 4) and N.attention_fused_ok([ok] * 8)
+    assert N.attention_fused_ok([mk((2, 3, 8, 8, 8), torch.bfloat16)] * 3)
+    assert not N.attention_fused_ok([ok])                                   # softmax over one view: identity path
+    assert not N.attention_fused_ok([ok] * 9)
+    assert not N.attention_fused_ok([mk((1, 16, 32, 40, 8), torch.float32)] * 4)
+    assert not N.attention_fused_ok([mk((1, 16, 32, 40, 16))] * 4)
+    assert not N.attention_fused_ok([mk((1, 2, 32, 40, 8))] * 4)
+    assert not N.attention_fused_ok([mk((1, 16, 4, 40, 8))] * 4)
+    A.FLAGS.attention_fused = False
+    try:
+        assert not N.attention_fused_ok([ok] * 4)
+    finally:
+        A.FLAGS.attention_fused = True
+
+
+def test_shallow_cache_computes_every_view_once(monkeypatch):
+    """refine.shallow_cache: inside the context the shallow features of a view are computed once however many
+    (reference, source) pairs ask for them; outside it every call computes both (the reference's behaviour)."""
+    import torch
+    import atvsnet_b200 as A
+    R = A.refine
+    calls = []
+
+    def fake(image):
+        calls.append(image.data_ptr())
+        return image.sum()
+    monkeypatch.setattr(R, 'shallow_features', fake)
+    images = torch.arange(5 * 4, dtype=torch.float32).reshape(1, 5, 2, 2, 1)
+    for v in range(1, 5):
+        R.extract_feature_shallow(images, 0, v)
+    assert len(calls) == 8
+    del calls[:]
+    with R.shallow_cache():
+        outs = [R.extract_feature_shallow(images, 0, v) for v in range(1, 5)]
+    assert len(calls) == 5                                                  # view 0 once + 4 sources
+    assert all(float(o[0]) == float(images[:, 0].sum()) for o in outs)
+    assert [float(o[1]) for o in outs] == [float(images[:, v].sum()) for v in range(1, 5)]
+    assert R._SHALLOW_MEMO is None                                          # the context cleans up after itself
